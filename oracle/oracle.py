@@ -1,0 +1,295 @@
+"""
+ctypes front-end for oracle/libsl_oracle.so -- the CPU restatement of the
+SafeLife step path.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  Nothing under
+safelife_b200/ imports this module.
+
+Function names and argument meaning follow the reference binding
+(safelife/speedups_src/module.c:515-556) with one addition: the RNG is an
+explicit uint64[4] PCG64 state {state_hi, state_lo, inc_hi, inc_lo} instead of
+the reference's process-global bit generator (speedups_src/random.c:21-22).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsl_oracle.so")
+
+
+def build():
+    """Compile the oracle (and oracle/_ref when the reference is present)."""
+    subprocess.check_call(["make", "-C", _HERE, "-s"], stdout=subprocess.DEVNULL)
+
+
+def _load():
+    if not os.path.exists(_LIB_PATH):
+        build()
+    return ctypes.CDLL(_LIB_PATH)
+
+
+_lib = _load()
+_u16p = ctypes.POINTER(ctypes.c_uint16)
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_i32p = ctypes.POINTER(ctypes.c_int32)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+_f32p = ctypes.POINTER(ctypes.c_float)
+
+
+def _p(arr, typ):
+    return arr.ctypes.data_as(typ)
+
+
+_lib.orc_pcg64_next_double.restype = ctypes.c_double
+_lib.orc_pcg64_next_u64.restype = ctypes.c_uint64
+
+
+# ---------------------------------------------------------------- RNG helpers
+def rng_from_generator(gen):
+    """uint64[4] PCG64 state of a numpy Generator (or BitGenerator)."""
+    bg = getattr(gen, "bit_generator", gen)
+    st = bg.state
+    assert st["bit_generator"] == "PCG64", st["bit_generator"]
+    s, inc = st["state"]["state"], st["state"]["inc"]
+    m = (1 << 64) - 1
+    return np.array([s >> 64, s & m, inc >> 64, inc & m], dtype=np.uint64)
+
+
+def rng_from_seed(seed):
+    """State of np.random.default_rng(seed) (safelife_game.py:175-180)."""
+    return rng_from_generator(np.random.default_rng(seed))
+
+
+def rng_state_int(rng):
+    """(state, inc) as Python ints, comparable with bit_generator.state."""
+    r = [int(x) for x in rng]
+    return (r[0] << 64) | r[1], (r[2] << 64) | r[3]
+
+
+def next_double(rng):
+    return _lib.orc_pcg64_next_double(_p(rng, _u64p))
+
+
+def _null_rng():
+    return np.zeros(4, dtype=np.uint64)
+
+
+# ------------------------------------------------------ speedups-shaped calls
+def _board2d(board):
+    board = np.ascontiguousarray(board, dtype=np.uint16)
+    if board.ndim != 2 or board.size == 0:
+        raise ValueError("board must be 2-dimensional and non-empty")
+    if board.shape[0] < 3 or board.shape[1] < 3:
+        raise ValueError("board must be at least 3x3")
+    return board
+
+
+def advance_board(board, spawn_prob=0.3, n_step=1, rng=None):
+    """module.c:20-49 -> advance_board.c:128-149. Returns a new array."""
+    board = _board2d(board)
+    if n_step < 1:
+        raise ValueError("n_step must be >= 1")
+    rng = _null_rng() if rng is None else rng
+    out = np.empty_like(board)
+    _lib.orc_advance_board_nstep(
+        _p(board, _u16p), _p(out, _u16p), board.shape[0], board.shape[1],
+        ctypes.c_float(spawn_prob), int(n_step), _p(rng, _u64p))
+    return out
+
+
+def life_occupancy(board, spawn_prob=0.3, n_step=1000, rng=None):
+    """module.c:52-81 -> advance_board.c:164-189. int32[H,W,8]."""
+    board = _board2d(board)
+    if n_step < 1:
+        raise ValueError("n_step must be >= 1")
+    rng = _null_rng() if rng is None else rng
+    counts = np.zeros(board.shape + (8,), dtype=np.int32)
+    _lib.orc_life_occupancy(
+        _p(board, _u16p), _p(counts, _i32p), board.shape[0], board.shape[1],
+        ctypes.c_float(spawn_prob), int(n_step), _p(rng, _u64p))
+    return counts
+
+
+def alive_counts(board, goals):
+    """module.c:99-132 -> advance_board.c:192-207. int64[8,9]."""
+    board = np.ascontiguousarray(board, dtype=np.uint16)
+    goals = np.ascontiguousarray(goals, dtype=np.uint16)
+    if board.size != goals.size:
+        raise ValueError("Board and goals must have same size.")
+    out = np.zeros((8, 9), dtype=np.int64)
+    _lib.orc_alive_counts(_p(board, _u16p), _p(goals, _u16p), board.size, _p(out, _i64p))
+    return out
+
+
+def execute_actions(board, locations, actions):
+    """module.c:155-202 -> advance_board.c:217-300. In place, returns None."""
+    if board.dtype != np.uint16 or not board.flags.c_contiguous or board.ndim != 2:
+        raise ValueError("Board should be 2-dimensional contiguous uint16.")
+    if board.shape[0] < 3 or board.shape[1] < 3:
+        raise ValueError("Board must be at least 3x3.")
+    if locations.dtype != np.int64 or not locations.flags.c_contiguous:
+        raise ValueError("locations must be contiguous int64")
+    actions = np.ascontiguousarray(np.atleast_1d(actions), dtype=np.int64)
+    n_agents = locations.size // 2
+    if actions.size != n_agents and actions.size != 1:
+        raise ValueError("Locations should be shape (n_agent, 2).")
+    _lib.orc_execute_actions(
+        _p(board, _u16p), board.shape[0], board.shape[1], _p(locations, _i64p),
+        _p(actions, _i64p), n_agents, 1 if actions.size == n_agents else 0)
+
+
+def wrapped_label(data):
+    """module.c:223-249 -> wrapped_label.c:5-55. (int32 labels, count)."""
+    arr = np.array(data, dtype=np.int32, order="C")
+    if arr.ndim != 2 or arr.size == 0:
+        raise ValueError("data must be 2-dimensional and non-empty")
+    n = _lib.orc_wrapped_label(_p(arr, _i32p), arr.shape[0], arr.shape[1])
+    return arr, int(n)
+
+
+def get_view(board, goals, loc, exits, view_shape, remove_white_goals=True):
+    """safelife_env.py:105-133 + helper_utils.py:42-75 -> uint32[vh,vw]."""
+    board = np.ascontiguousarray(board, dtype=np.uint16)
+    goals = np.ascontiguousarray(goals, dtype=np.uint16)
+    exits = np.ascontiguousarray(exits, dtype=np.int32)
+    vh, vw = view_shape
+    out = np.empty((vh, vw), dtype=np.uint32)
+    _lib.orc_get_view(_p(board, _u16p), _p(goals, _u16p), board.shape[0], board.shape[1],
+                      int(loc[0]), int(loc[1]), _p(exits, _i32p), exits.size,
+                      vh, vw, int(bool(remove_white_goals)), _p(out, _u32p))
+    return out
+
+
+def get_obs(board, goals, loc, exits, view_shape, output_channels, remove_white_goals=True):
+    """safelife_env.py:135-146: bit-plane expansion of the packed view."""
+    view = get_view(board, goals, loc, exits, view_shape, remove_white_goals)
+    if not output_channels:
+        return view
+    shift = np.array(list(output_channels), dtype=np.uint32)
+    return ((view[..., None] >> shift) & 1).astype(np.uint8)
+
+
+def side_effect_cells(board, baseline, exits):
+    """env_wrappers.py:177-213 (ignore_reward_cells=False) cell count."""
+    board = np.ascontiguousarray(board, dtype=np.uint16)
+    baseline = np.ascontiguousarray(baseline, dtype=np.uint16)
+    exits = np.ascontiguousarray(exits, dtype=np.int32)
+    return int(_lib.orc_side_effect_cells(_p(board, _u16p), _p(baseline, _u16p), board.size,
+                                          _p(exits, _i32p), exits.size))
+
+
+# ------------------------------------------------------------ level constants
+DEFAULT_POINTS_TABLE = np.array([   # safelife_game.py:595-605
+    [+0, -1, +0, +0, +0, +0, +0, +0, 0],
+    [-3, +3, -3, +0, -3, +0, -3, -3, 0],
+    [+0, -3, +5, +0, +0, +0, +3, +0, 0],
+    [-3, +0, +0, +3, +0, +0, +0, +0, 0],
+    [+3, -3, +3, +0, +5, +3, +3, +3, 0],
+    [-3, +3, -3, +0, -3, +5, -3, -3, 0],
+    [+3, -3, +3, +0, +3, +0, +5, +3, 0],
+    [+0, -1, +0, +0, +0, +0, +0, +0, 0],
+], dtype=np.int64)
+
+
+def level_constants(board, goals, table, min_performance):
+    """
+    Per-episode constants of GameWithGoals (safelife_game.py:665-714), taken
+    on the just-deserialised board (before update_exit_colors):
+    exit cell indices, sum(table*initial_counts), required_points.
+    """
+    board = np.asarray(board, dtype=np.uint16)
+    table = np.asarray(table, dtype=np.int64).reshape(8, 9)
+    exits = np.flatnonzero((board & (0x100 | 0x2)) == 0x100).astype(np.int32)  # :533-535
+    counts = alive_counts(board, goals)
+    init_points = int((table * counts).sum())
+    colors = np.zeros(9, dtype=bool)
+    gen = board[(board & (0x2 | 0x1 | 0x80)) > 0] & 0x0E00
+    colors[np.unique(gen) >> 9] = True
+    colors[8] = True
+    max_points = (table * colors).max(axis=1)
+    available = int((max_points * counts.sum(axis=1)).sum()) - init_points
+    required = max(0, int(np.int64(np.ceil(float(min_performance) * available))))
+    return exits, init_points, required
+
+
+# ------------------------------------------------------------- batched env
+class _Batch(ctypes.Structure):
+    _fields_ = [
+        ("n_envs", ctypes.c_int), ("H", ctypes.c_int), ("W", ctypes.c_int),
+        ("max_exits", ctypes.c_int), ("time_limit", ctypes.c_int),
+        ("board", _u16p), ("goals", _u16p), ("loc", _i32p), ("has_agent", _u8p),
+        ("rng", _u64p), ("table", _i32p), ("exits", _i32p), ("init_points", _i32p),
+        ("required", _i32p), ("spawn_prob", _f32p), ("static_goals", _u8p),
+        ("num_steps", _i32p), ("old_value", _i32p), ("active", _u8p),
+        ("ep_length", _i32p), ("ep_reward", _f32p), ("reward", _f32p),
+        ("done", _u8p), ("success", _u8p), ("times_up", _u8p),
+    ]
+
+
+class OracleEnv(object):
+    """
+    Batched single-agent restatement of SafeLifeEnv reset/step
+    (safelife_env.py:148-218) without observations or auto-reset.
+
+    `levels` is a list of dicts with keys board, goals, agent_loc (row, col) or
+    None, points_table [8,9], min_performance, spawn_prob; `rngs` a list of
+    uint64[4] states (one per env).
+    """
+
+    def __init__(self, levels, rngs, time_limit=1000):
+        n = len(levels)
+        H, W = levels[0]["board"].shape
+        self.n, self.H, self.W, self.time_limit = n, H, W, time_limit
+        consts = [level_constants(lv["board"], lv["goals"], lv["points_table"],
+                                  lv["min_performance"]) for lv in levels]
+        self.max_exits = max(1, max(len(c[0]) for c in consts))
+        self.board = np.stack([np.asarray(lv["board"], dtype=np.uint16) for lv in levels])
+        self.goals = np.stack([np.asarray(lv["goals"], dtype=np.uint16) for lv in levels])
+        self.loc = np.zeros((n, 2), dtype=np.int32)
+        self.has_agent = np.zeros(n, dtype=np.uint8)
+        for i, lv in enumerate(levels):
+            if lv.get("agent_loc") is not None:
+                self.loc[i] = lv["agent_loc"]
+                self.has_agent[i] = 1
+        self.rng = np.stack([np.asarray(r, dtype=np.uint64) for r in rngs])
+        self.table = np.stack([np.asarray(lv["points_table"], dtype=np.int64).reshape(72)
+                               for lv in levels]).astype(np.int32)
+        self.exits = np.full((n, self.max_exits), -1, dtype=np.int32)
+        for i, c in enumerate(consts):
+            self.exits[i, :len(c[0])] = c[0]
+        self.init_points = np.array([c[1] for c in consts], dtype=np.int32)
+        self.required = np.array([c[2] for c in consts], dtype=np.int32)
+        self.spawn_prob = np.array([lv["spawn_prob"] for lv in levels], dtype=np.float32)
+        self.static_goals = np.zeros(n, dtype=np.uint8)
+        self.num_steps = np.zeros(n, dtype=np.int32)
+        self.old_value = np.zeros(n, dtype=np.int32)
+        self.active = np.zeros(n, dtype=np.uint8)
+        self.ep_length = np.zeros(n, dtype=np.int32)
+        self.ep_reward = np.zeros(n, dtype=np.float32)
+        self.reward = np.zeros(n, dtype=np.float32)
+        self.done = np.zeros(n, dtype=np.uint8)
+        self.success = np.zeros(n, dtype=np.uint8)
+        self.times_up = np.zeros(n, dtype=np.uint8)
+        self._b = _Batch(
+            n, H, W, self.max_exits, time_limit,
+            _p(self.board, _u16p), _p(self.goals, _u16p), _p(self.loc, _i32p),
+            _p(self.has_agent, _u8p), _p(self.rng, _u64p), _p(self.table, _i32p),
+            _p(self.exits, _i32p), _p(self.init_points, _i32p), _p(self.required, _i32p),
+            _p(self.spawn_prob, _f32p), _p(self.static_goals, _u8p),
+            _p(self.num_steps, _i32p), _p(self.old_value, _i32p), _p(self.active, _u8p),
+            _p(self.ep_length, _i32p), _p(self.ep_reward, _f32p), _p(self.reward, _f32p),
+            _p(self.done, _u8p), _p(self.success, _u8p), _p(self.times_up, _u8p))
+        for e in range(n):
+            _lib.orc_env_reset(ctypes.byref(self._b), e)
+
+    def step(self, actions):
+        actions = np.ascontiguousarray(actions, dtype=np.int64)
+        assert actions.shape == (self.n,)
+        _lib.orc_env_step(ctypes.byref(self._b), _p(actions, _i64p))
+        return self.reward.copy(), self.done.astype(bool)
