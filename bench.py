@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""
+bench.py -- env-steps/sec of the batched SafeLife step path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--envs E] [--pool NAME] [--kernel 0|1|2]
+
+One "step" = one pass of the hot path (SafeLifeEnv.step minus observation:
+execute_actions + advance_board (+ goals when dynamic) + points / exit colours /
+reward / done, then the auto-reset of finished envs) over the whole batch.
+Workload (BASELINE.json configs[1]): 4096 envs per GPU of 25x25 append-still
+procedural boards (pool generated with the reference procgen, committed under
+tests/golden/pools), uniform random actions, time_limit 1000.  N GPUs run N
+independent shards of 4096 envs (weak scaling, no collective on the step path).
+
+Prints ONE JSON line on rank 0.  `value` is device-timed with the state
+resident in HBM and the L2 flushed between steps; `e2e` goes through the public
+BatchedSafeLifeEnv API with pinned host actions in and host reward/done out.
+`--impl reference` times the reference's own C extension (oracle/_ref, compiled
+from the reference sources) on the host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+POOL_DIR = os.path.join(ROOT, "tests", "golden", "pools")
+METRIC = "env-steps/sec (batched boards) at 1/2/4/8 B200 vs C-ext on host cores"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--pool", default="append-still-25")
+    ap.add_argument("--kernel", type=int, default=0)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------
+# CPU arm: the reference C extension ("C-ext trio")
+# --------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Steps a subset of envs with the reference speedups; returns timed seconds."""
+    levels, seeds, actions, warmup, steps, barrier, kind = args
+    if kind == "reference":
+        from oracle import refload
+        sp = refload.load_ref_speedups()
+    else:
+        sp = None
+    from oracle import oracle as orc
+    n = len(levels)
+    boards = [np.array(lv["board"], dtype=np.uint16) for lv in levels]
+    goals = [np.array(lv["goals"], dtype=np.uint16) for lv in levels]
+    locs = [np.array([lv["agent_loc"]], dtype=np.int64) for lv in levels]
+    tables = [np.asarray(lv["points_table"], dtype=np.int64).reshape(8, 9) for lv in levels]
+    gens = [np.random.default_rng(s) for s in seeds]
+    rngs = [orc.rng_from_generator(g) for g in gens]
+    static = [None] * n
+    total = 0
+
+    def one_step(t):
+        nonlocal total
+        for i in range(n):
+            a = int(actions[t, i])
+            p = levels[i]["spawn_prob"]
+            if kind == "reference":
+                # SafeLifeGame.execute_actions / advance_board / alive_counts
+                # (safelife_game.py:380-389, 746-761, 657-663) on the reference C code
+                sp.execute_actions(boards[i], locs[i], a)
+                sp.set_bit_generator(gens[i].bit_generator)
+                boards[i] = sp.advance_board(boards[i], p)
+                if not static[i]:
+                    new_goals = sp.advance_board(goals[i], p)
+                    if static[i] is None:
+                        static[i] = (not (new_goals & 128).any()) and (new_goals == goals[i]).all()
+                    goals[i] = new_goals
+                counts = sp.alive_counts(boards[i], goals[i])
+            else:
+                orc.execute_actions(boards[i], locs[i], a)
+                boards[i] = orc.advance_board(boards[i], p, 1, rngs[i])
+                if not static[i]:
+                    new_goals = orc.advance_board(goals[i], p, 1, rngs[i])
+                    if static[i] is None:
+                        static[i] = (not (new_goals & 128).any()) and (new_goals == goals[i]).all()
+                    goals[i] = new_goals
+                counts = orc.alive_counts(boards[i], goals[i])
+            total += int((tables[i] * counts).sum())
+
+    for t in range(warmup):
+        one_step(t)
+    barrier.wait()
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        one_step(t)
+    return time.perf_counter() - t0, total
+
+
+def cpu_arm(levels, n_envs, steps, warmup, seconds_budget):
+    """
+    Aggregate env-steps/s of the reference C-extension trio + 72-term dot
+    product, one process per host core.  The sample (envs per step) is bounded
+    so that warmup + steps fit the time budget.
+    """
+    import multiprocessing as mp
+    from oracle import refload
+    kind = "reference" if refload.have_ref_so() else "port"
+    cores = os.cpu_count() or 1
+    # calibrate on one core
+    m = mp.Manager()
+    probe = 64
+    acts = np.random.default_rng(7).integers(0, 9, (warmup + steps + 2, max(n_envs, probe))).astype(np.uint8)
+    t, _ = _cpu_worker(([levels[i % len(levels)] for i in range(probe)], list(range(probe)),
+                        acts, 0, 2, m.Barrier(1), kind))
+    per_env_step = t / (2 * probe)
+    cap = int(seconds_budget * cores / (per_env_step * (warmup + steps)))
+    sample = max(cores, min(n_envs, cap))
+    sample -= sample % cores
+    per = sample // cores
+    barrier = m.Barrier(cores)
+    jobs = []
+    for w in range(cores):
+        idx = list(range(w * per, (w + 1) * per))
+        jobs.append(([levels[i % len(levels)] for i in idx], idx, acts[:, idx], warmup, steps,
+                     barrier, kind))
+    with mp.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+    elapsed = max(r[0] for r in res)
+    value = sample * steps / elapsed
+    return {
+        "value": value, "unit": "env-steps/s", "cores": cores, "kind": kind,
+        "sample": "%d envs x %d steps (of %d envs/step), %s speedups execute_actions+advance_board"
+                  "+alive_counts+dot from a Python loop, one process per core" % (
+                      sample, steps, n_envs, "reference C" if kind == "reference" else "oracle"),
+    }, elapsed
+
+
+def run_reference(args, levels):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_total = args.envs * args.gpus
+    base, elapsed = cpu_arm(levels, n_total, args.steps, args.warmup, 60.0)
+    H, W = levels[0]["board"].shape
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+        "config": {"workload": "%d envs x %dx%d %s, random actions (CPU sample: see cpu_baseline)" % (
+            n_total, H, W, args.pool), "envs_per_gpu": args.envs, "pool": args.pool},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4)
+                          if r[2 + k].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_ours(args, levels):
+    import torch
+    import torch.distributed as dist
+    from safelife_b200.env import BatchedSafeLifeEnv, seed_rng_states
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run)" % (
+            args.gpus, world))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    n = args.envs
+    lo = rank * n                      # contiguous env range of this rank
+    my_levels = [levels[(lo + i) % len(levels)] for i in range(n)]
+    H, W = levels[0]["board"].shape
+    env = BatchedSafeLifeEnv(my_levels, n, device=dev, kernel=args.kernel, time_limit=1000)
+    env.set_rng_state(seed_rng_states(4, n * world)[lo:lo + n])   # global-index-derived streams
+    env.reset()
+    K, Wm = args.steps, args.warmup
+    g = torch.Generator(device=dev)
+    g.manual_seed(2 + rank)
+    actions = torch.randint(0, 9, (K + Wm, n), generator=g, device=dev, dtype=torch.uint8)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lib, bref = env._lib, env._batch_ref
+    from safelife_b200 import _lib
+    flags = _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS
+    stream = env._stream()
+    done_ptr = env._t["done"].data_ptr()
+
+    def step_kernels(t, ev_mid=None):
+        _lib.check(lib.sl_env_step(bref, actions[t].data_ptr(), args.kernel, stream))
+        if ev_mid is not None:
+            ev_mid.record()
+        _lib.check(lib.sl_env_reset(bref, done_ptr, None, flags, stream))
+
+    for t in range(Wm):
+        step_kernels(t)
+    barrier()
+    # ---- value: device-timed, state resident in HBM, L2 flushed between steps ----
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    wall0 = time.perf_counter()
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        ev[t][0].record()
+        step_kernels(Wm + t, ev[t][1])
+        ev[t][2].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = sum(e[0].elapsed_time(e[1]) for e in ev)        # step kernel only
+    total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)       # step + auto-reset
+    static = env._t["static_goals"].cpu().numpy()
+    dyn = int((static == 2).sum())
+    bytes_per_launch = (n - dyn) * (6 * H * W + 64) + dyn * (8 * H * W + 64)
+
+    # ---- e2e: public API, pinned host actions in, host reward/done out ----
+    host_actions = torch.randint(0, 9, (K, n), dtype=torch.uint8).pin_memory()
+    host_reward = torch.empty(n, dtype=torch.float32).pin_memory()
+    host_done = torch.empty(n, dtype=torch.uint8).pin_memory()
+    e2e_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    barrier()
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        e2e_ev[t][0].record()
+        env.step_physics(host_actions[t])                 # H2D inside
+        _lib.check(lib.sl_env_reset(bref, done_ptr, None, flags, stream))
+        host_reward.copy_(env._t["reward"], non_blocking=True)
+        host_done.copy_(env._t["done"], non_blocking=True)
+        e2e_ev[t][1].record()
+        e2e_ev[t][1].synchronize()                        # the host consumes the result
+    barrier()
+    e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_ev)
+
+    times = torch.tensor([total_ms, step_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, step_ms, e2e_ms = (float(x) for x in times.cpu())
+    if rank == 0:
+        peak, peak_src = peaks()
+        achieved = bytes_per_launch / (step_ms / K * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": n * world * K / (total_ms * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u16", "data": "synthetic",
+            "config": {
+                "workload": "%d envs/GPU x %dx%d %s procgen pool (%d levels), uniform random "
+                            "actions, time_limit 1000, auto-reset" % (n, H, W, args.pool, len(levels)),
+                "envs_per_gpu": n, "board": [H, W], "pool": args.pool, "kernel": args.kernel,
+                "l2": "state %.1f MB < L2; L2 flushed (256 MiB fill) between timed steps, flush "
+                      "not timed" % (n * (4 * H * W) / 1e6) if flush is not None else "not flushed",
+                "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                "parallelism": "dp%d (independent env shards, no collective)" % world,
+            },
+            "clocks": clocks,
+            "e2e": {"value": n * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
+                    "h2d_bytes_per_step": n, "d2h_bytes_per_step": 5 * n,
+                    "api": "BatchedSafeLifeEnv.step_physics + auto-reset; pinned uint8 actions "
+                           "H2D, float32 reward + uint8 done D2H, host sync every step"},
+            "gpu_launches": 2 * K,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "kernel": "env step kernel",
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch,
+                "kernel_ms": step_ms / K, "dynamic_goal_envs": dyn,
+            },
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"], _ = cpu_arm(levels, n, min(K, 100), 2, args.cpu_seconds)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1 and "RANK" not in os.environ:
+        # convenience: re-launch under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+               "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
+               "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    from safelife_b200.levels import load_levels
+    levels = load_levels(os.path.join(POOL_DIR, args.pool + ".npz"))
+    if args.impl == "reference":
+        run_reference(args, levels)
+    else:
+        run_ours(args, levels)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+/*
+ * safelife_b200.h -- C ABI of libsafelife_b200.so, the B200 (sm_100a) batched
+ * SafeLife step engine.
+ *
+ * Every entry point is plain C: raw pointers, sizes, an opaque cudaStream_t
+ * (passed as void*, NULL = the legacy default stream), an int status return
+ * (SL_OK = 0).  No function throws, allocates caller-visible memory or keeps
+ * global simulation state; sl_last_error() returns a thread-local message for
+ * the last non-zero status.
+ *
+ * Each declaration cites the reference interface it replaces; paths are
+ * relative to the PartnershipOnAI/safelife checkout (v1.2.2).  The reference
+ * binding (safelife/speedups_src/module.c) works on one numpy board per call;
+ * the entry points here take a batch of `n` boards laid out [n, H, W] uint16,
+ * C-contiguous, row 0 = top -- the SafeLifeGame board layout
+ * (safelife/safelife_game.py:75-123, speedups_src/constants.h:4-33) with a
+ * leading batch axis.
+ *
+ * Pointers named *_dev / documented "device" must be device memory of the
+ * current CUDA device; the `_host` variants take host memory, stage it through
+ * the device and synchronise before returning.
+ *
+ * RNG: where the reference reads a process-global numpy bit generator
+ * (speedups_src/random.c:21-39, 76-83) these functions take the PCG64 state
+ * explicitly as uint64[n][4] = {state_hi, state_lo, inc_hi, inc_lo} per board
+ * and advance it in place by exactly the number of doubles the reference
+ * would have drawn (one per qualifying cell in raster order,
+ * speedups_src/advance_board.c:115).  rng may be NULL only if no board of the
+ * batch can draw (no SPAWNING cell); a NULL rng with spawners present leaves
+ * every draw "not spawned".
+ */
+#ifndef SAFELIFE_B200_H
+#define SAFELIFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SL_OK            0
+#define SL_ERR_ARG       1   /* invalid argument (the reference raises ValueError) */
+#define SL_ERR_CUDA      2   /* CUDA runtime error, see sl_last_error() */
+#define SL_ERR_NO_DEVICE 3   /* no usable CUDA device: there is no CPU fallback */
+
+#define SL_ABI_VERSION   1
+
+/* ---- library plumbing ------------------------------------------------ */
+int sl_abi_version(void);
+const char *sl_last_error(void);
+/* SM count / L2 bytes of the current device (for grid sizing by callers). */
+int sl_device_info(int *sm_count, int *l2_bytes, int *cc_major, int *cc_minor);
+/* 1 if the warp-per-env bit-plane kernels handle H x W boards, else 0
+ * (larger boards run on the generic CTA-per-env kernels). */
+int sl_warp_kernel_supported(int H, int W);
+
+/* ---- board operators (device pointers) ------------------------------- */
+
+/* n_steps >= 1 Life-variant steps on each of n toroidal boards.
+ * Replaces speedups.advance_board (module.c:20-49 -> advance_board.c:34-149).
+ * in and out may alias.  H, W >= 3.  spawn_prob is the C float the reference
+ * parses (module.c:23); it is compared with a double draw. */
+int sl_advance_board(const uint16_t *in, uint16_t *out, int n, int H, int W,
+                     float spawn_prob, int n_steps, uint64_t *rng, void *stream);
+
+/* Advance n_steps and accumulate, after every step, +1 into
+ * counts[b][y][x][colour] for cells ALIVE and none of AGENT|EXIT|FROZEN.
+ * counts is int32[n][H][W][8] and is ADDED to (the reference returns a fresh
+ * zero-initialised array: callers zero it first).  The boards are not
+ * modified.  Replaces speedups.life_occupancy (module.c:52-81 ->
+ * advance_board.c:153-189). */
+int sl_life_occupancy(const uint16_t *board, int32_t *counts, int n, int H, int W,
+                      float spawn_prob, int n_steps, uint64_t *rng, void *stream);
+
+/* out[b][goal_colour][cell_colour | 8=empty] histogram, int64[n][8][9],
+ * overwritten.  Replaces speedups.alive_counts (module.c:99-132 ->
+ * advance_board.c:192-207). */
+int sl_alive_counts(const uint16_t *board, const uint16_t *goals, int64_t *out,
+                    int n, int cells, void *stream);
+
+/* Agents act in index order on their board, in place.  locations is
+ * int64[n][n_agents][2] (row, col), updated in place; actions is
+ * int64[n][n_agents] (action_stride 1) or int64[n][1] (action_stride 0, one
+ * action broadcast to all agents of the board).  Replaces
+ * speedups.execute_actions (module.c:155-202 -> advance_board.c:217-300). */
+int sl_execute_actions(uint16_t *board, int64_t *locations, const int64_t *actions,
+                       int n, int H, int W, int n_agents, int action_stride,
+                       void *stream);
+
+/* 8-connected toroidal component labelling of the non-zero cells of each
+ * int32[H][W] grid, in place; num_labels[b] receives the label count.  Label
+ * numbering follows the reference's index-set visiting order.  Replaces
+ * speedups.wrapped_label (module.c:223-249 -> wrapped_label.c:5-55). */
+int sl_wrapped_label(int32_t *data, int32_t *num_labels, int n, int H, int W,
+                     void *stream);
+
+/* ---- the same operators on host buffers ------------------------------ */
+/* What a maintainer of module.c binds in place of the CPU loops: same
+ * arguments, host memory, one board batch per call, synchronous. */
+int sl_advance_board_host(const uint16_t *in, uint16_t *out, int n, int H, int W,
+                          float spawn_prob, int n_steps, uint64_t *rng);
+int sl_life_occupancy_host(const uint16_t *board, int32_t *counts, int n, int H, int W,
+                           float spawn_prob, int n_steps, uint64_t *rng);
+int sl_alive_counts_host(const uint16_t *board, const uint16_t *goals, int64_t *out,
+                         int n, int cells);
+int sl_execute_actions_host(uint16_t *board, int64_t *locations, const int64_t *actions,
+                            int n, int H, int W, int n_agents, int action_stride);
+int sl_wrapped_label_host(int32_t *data, int32_t *num_labels, int n, int H, int W);
+
+/* ---- batched environment (SafeLifeEnv.step / reset) ------------------- */
+
+/*
+ * Device-resident state of n_envs single-agent SafeLife environments plus the
+ * read-only level pool they reset from.  All pointers are device pointers
+ * owned by the caller (torch tensors in the Python host layer).
+ */
+typedef struct SlEnvBatch {
+    int32_t n_envs, H, W;
+    int32_t max_exits;     /* width of pool_exits */
+    int32_t time_limit;    /* SafeLifeEnv.time_limit, safelife_env.py:65 */
+    int32_t n_levels;
+    int32_t level_stride;  /* auto-reset rule: level_id <- (level_id + level_stride) % n_levels */
+
+    /* per-env state */
+    uint16_t *board;       /* [n_envs][H][W]  SafeLifeGame.board */
+    uint16_t *goals;       /* [n_envs][H][W]  SafeLifeGame.goals */
+    int32_t  *loc;         /* [n_envs][2] (row, col) of agent 0; row < 0: level has no agent */
+    uint64_t *rng;         /* [n_envs][4] PCG64 of the game (safelife_game.py:175-180) */
+    int32_t  *level_id;    /* [n_envs] index into the pool */
+    int32_t  *num_steps;   /* [n_envs] GameState.num_steps */
+    int32_t  *old_value;   /* [n_envs] SafeLifeEnv._old_game_value */
+    int32_t  *ep_length;   /* [n_envs] SafeLifeEnv.episode_length */
+    float    *ep_reward;   /* [n_envs] SafeLifeEnv.episode_reward */
+    uint8_t  *active;      /* [n_envs] SafeLifeEnv._is_active */
+    uint8_t  *static_goals;/* [n_envs] 0 = unknown (None), 1 = static, 2 = dynamic
+                              (GameWithGoals._static_goals, safelife_game.py:753-761) */
+    /* per-step outputs */
+    float    *reward;      /* [n_envs] float32 reward (safelife_env.py:157,172) */
+    uint8_t  *done;        /* [n_envs] */
+    uint8_t  *success;     /* [n_envs] has_exited (safelife_env.py:159) */
+    uint8_t  *times_up;    /* [n_envs] info['times_up'] */
+
+    /* level pool, read-only */
+    const uint16_t *pool_board;       /* [n_levels][H][W] as deserialised, before update_exit_colors */
+    const uint16_t *pool_goals;       /* [n_levels][H][W] */
+    const int32_t  *pool_loc;         /* [n_levels][2], row < 0: no agent */
+    const int32_t  *pool_table;       /* [n_levels][72] points_table[0] (safelife_game.py:595-605) */
+    const int32_t  *pool_exits;       /* [n_levels][max_exits] flat indices of exit cells, -1 padded,
+                                         raster order (GameState.exit_locs, safelife_game.py:533-535) */
+    const int32_t  *pool_init_points; /* [n_levels] sum(points_table * initial_counts) (:689-694) */
+    const int32_t  *pool_required;    /* [n_levels] required_points() (:711-714) */
+    const uint64_t *pool_spawn_thr;   /* [n_levels] ceil((double)(float)spawn_prob * 2^53): a draw
+                                         (u64 >> 11) spawns iff it is below this */
+} SlEnvBatch;
+
+/* One SafeLifeEnv.step for every env (safelife_env.py:148-201, single_agent):
+ * execute_actions -> advance_board (board, then goals unless static) ->
+ * update_exit_colors -> reward / done / episode counters.  actions is
+ * uint8[n_envs] (device), values as the reference's Discrete(9).
+ * kernel: 0 = pick automatically, 1 = generic CTA-per-env kernel,
+ * 2 = warp-per-env bit-plane kernel (requires H, W <= 32). */
+int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, void *stream);
+
+/* SafeLifeEnv.reset (safelife_env.py:203-218) for every env whose mask byte is
+ * non-zero (mask NULL = all envs): copy a level from the pool, then
+ * update_exit_colors and the episode counters.  The level is new_level[e]
+ * (device int32) if given, else level_id[e], advanced by level_stride when
+ * SL_RESET_NEXT_LEVEL is set.  With SL_RESET_KEEP_STATS ep_length / ep_reward
+ * keep the finished episode's totals until the env's next step (what
+ * info['episode'] reports after an auto-reset).  The RNG state is left as it
+ * is; callers that want the reference's per-level SeedSequence stream write
+ * rng[e] themselves. */
+#define SL_RESET_NEXT_LEVEL 1
+#define SL_RESET_KEEP_STATS 2
+int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *new_level,
+                 int flags, void *stream);
+
+/* SafeLifeEnv.get_obs (safelife_env.py:105-146) with recenter_view
+ * (helper_utils.py:42-75): agent-centred toroidal view of board | goal
+ * colours << 16, exit cells outside the view clamped to its perimeter.
+ * n_channels > 0: obs is uint8[n_envs][vh][vw][n_channels] with
+ * obs[...,k] = (view >> channels[k]) & 1 (channels: device int32);
+ * n_channels == 0: obs is uint32[n_envs][vh][vw] (output_channels=None). */
+int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw,
+               const int32_t *channels, int n_channels, int remove_white_goals,
+               void *stream);
+
+/* SimpleSideEffectPenalty.step cell count (env_wrappers.py:177-213,
+ * ignore_reward_cells=False): out[e] = number of cells whose non-player bits
+ * differ from baseline[e], exit cells excluded.  baseline: [n_envs][H][W]. */
+int sl_side_effect_cells(const SlEnvBatch *batch, const uint16_t *baseline, int32_t *out,
+                         void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAFELIFE_B200_H */

@@ -1,0 +1,116 @@
+"""
+Loader for libsafelife_b200.so (the C ABI declared in include/safelife_b200.h).
+
+The library is built in-tree with nvcc for sm_100a (see build()); it is loaded
+with plain ctypes.  There is no CPU fallback: if the library is missing it is
+compiled, and if no CUDA device is usable the entry points return
+SL_ERR_NO_DEVICE, which `check` raises as RuntimeError.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libsafelife_b200.so")
+_SRC = os.path.join(_PKG, "csrc")
+
+SL_OK, SL_ERR_ARG, SL_ERR_CUDA, SL_ERR_NO_DEVICE = 0, 1, 2, 3
+SL_RESET_NEXT_LEVEL, SL_RESET_KEEP_STATS = 1, 2
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--shared", "-Xcompiler", "-fPIC",
+]
+
+
+def _sources():
+    return sorted(os.path.join(_SRC, f) for f in os.listdir(_SRC))
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    deps = _sources() + [os.path.join(_ROOT, "include", "safelife_b200.h")]
+    return any(os.path.getmtime(p) > built for p in deps)
+
+
+def build(force=False, verbose=False):
+    """nvcc -gencode arch=compute_100a,code=sm_100a csrc/abi.cu -> libsafelife_b200.so"""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libsafelife_b200.so (no CPU fallback)")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-o", LIB_PATH, os.path.join(_SRC, "abi.cu")]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+class SlEnvBatch(ctypes.Structure):
+    """Mirror of struct SlEnvBatch (include/safelife_b200.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("n_envs", "H", "W", "max_exits", "time_limit", "n_levels", "level_stride")] + \
+               [(n, ctypes.c_void_p) for n in (
+                   "board", "goals", "loc", "rng", "level_id", "num_steps", "old_value",
+                   "ep_length", "ep_reward", "active", "static_goals",
+                   "reward", "done", "success", "times_up",
+                   "pool_board", "pool_goals", "pool_loc", "pool_table", "pool_exits",
+                   "pool_init_points", "pool_required", "pool_spawn_thr")]
+
+
+# name -> argtypes, exactly the prototypes of include/safelife_b200.h
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+PROTOTYPES = {
+    "sl_abi_version": [],
+    "sl_last_error": [],
+    "sl_device_info": [_vp, _vp, _vp, _vp],
+    "sl_warp_kernel_supported": [_i, _i],
+    "sl_advance_board": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "sl_life_occupancy": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "sl_alive_counts": [_vp, _vp, _vp, _i, _i, _vp],
+    "sl_execute_actions": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
+    "sl_wrapped_label": [_vp, _vp, _i, _i, _i, _vp],
+    "sl_advance_board_host": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "sl_life_occupancy_host": [_vp, _vp, _i, _i, _i, _f, _i, _vp],
+    "sl_alive_counts_host": [_vp, _vp, _vp, _i, _i],
+    "sl_execute_actions_host": [_vp, _vp, _vp, _i, _i, _i, _i, _i],
+    "sl_wrapped_label_host": [_vp, _vp, _i, _i, _i],
+    "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _vp],
+    "sl_env_reset": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _i, _vp],
+    "sl_get_obs": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _i, _i, _vp],
+    "sl_side_effect_cells": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _vp],
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library (built first if needed)."""
+    global _lib
+    if _lib is None:
+        build()
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p if name == "sl_last_error" else ctypes.c_int
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    """Turn a non-zero status into the exception the reference would raise."""
+    if status == SL_OK:
+        return
+    msg = lib().sl_last_error().decode("utf-8", "replace")
+    if status == SL_ERR_ARG:
+        raise ValueError(msg)
+    raise RuntimeError("libsafelife_b200: " + msg)

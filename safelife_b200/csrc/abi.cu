@@ -1,0 +1,410 @@
+// abi.cu -- extern "C" entry points of libsafelife_b200.so (include/safelife_b200.h).
+//
+// Argument checking mirrors the reference binding's error behaviour
+// (safelife/speedups_src/module.c: ValueError for shape problems -> SL_ERR_ARG);
+// nothing here throws or keeps simulation state between calls.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/safelife_b200.h"
+#include "cells.cuh"
+#include "generic_kernels.cuh"
+#include "warp_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define SL_CUDA(call)                                                               \
+    do {                                                                            \
+        cudaError_t err__ = (call);                                                 \
+        if (err__ != cudaSuccess)                                                   \
+            return fail(err__ == cudaErrorNoDevice || err__ == cudaErrorInsufficientDriver \
+                            ? SL_ERR_NO_DEVICE : SL_ERR_CUDA,                       \
+                        "%s: %s", #call, cudaGetErrorString(err__));                \
+    } while (0)
+
+int launch_status(const char *what) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess)
+        return fail(err == cudaErrorNoDevice || err == cudaErrorInsufficientDriver
+                        ? SL_ERR_NO_DEVICE : SL_ERR_CUDA,
+                    "%s launch: %s", what, cudaGetErrorString(err));
+    return SL_OK;
+}
+
+// draw < (double)spawn_prob  <=>  (u64 >> 11) < ceil((double)spawn_prob * 2^53)
+uint64_t spawn_threshold(float spawn_prob) {
+    double t = (double)spawn_prob * 9007199254740992.0;
+    if (!(t > 0.0)) return 0;
+    if (t >= 9007199254740992.0) return 1ull << 53;
+    return (uint64_t)ceil(t);
+}
+
+struct DeviceProps {
+    int sm_count = 0, l2_bytes = 0, major = 0, minor = 0, max_smem_optin = 0;
+    bool ok = false;
+};
+
+int device_props(DeviceProps *out) {
+    static thread_local int cached_dev = -1;
+    static thread_local DeviceProps cached;
+    int dev;
+    SL_CUDA(cudaGetDevice(&dev));
+    if (dev != cached_dev) {
+        DeviceProps p;
+        SL_CUDA(cudaDeviceGetAttribute(&p.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        SL_CUDA(cudaDeviceGetAttribute(&p.l2_bytes, cudaDevAttrL2CacheSize, dev));
+        SL_CUDA(cudaDeviceGetAttribute(&p.major, cudaDevAttrComputeCapabilityMajor, dev));
+        SL_CUDA(cudaDeviceGetAttribute(&p.minor, cudaDevAttrComputeCapabilityMinor, dev));
+        SL_CUDA(cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        p.ok = true;
+        cached = p;
+        cached_dev = dev;
+    }
+    *out = cached;
+    return SL_OK;
+}
+
+template <typename K>
+int prepare_smem(K kernel, size_t bytes) {
+    DeviceProps p;
+    int rc = device_props(&p);
+    if (rc) return rc;
+    if (bytes > (size_t)p.max_smem_optin)
+        return fail(SL_ERR_ARG, "board too large: needs %zu bytes of shared memory (max %d)",
+                    bytes, p.max_smem_optin);
+    if (bytes > 48 * 1024)
+        SL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return SL_OK;
+}
+
+int check_board_args(const void *p, int n, int H, int W) {
+    if (n < 0) return fail(SL_ERR_ARG, "n must be >= 0");
+    if (H < 3 || W < 3) return fail(SL_ERR_ARG, "Board must be at least 3x3.");
+    if ((long long)H * W > (1 << 24)) return fail(SL_ERR_ARG, "board too large");
+    if (n > 0 && p == nullptr) return fail(SL_ERR_ARG, "null board pointer");
+    return SL_OK;
+}
+
+int grid_for(int n) { return n < 1 ? 1 : (n > (1 << 20) ? (1 << 20) : n); }
+
+int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int H, int W,
+                 float spawn_prob, int n_steps, uint64_t *rng, cudaStream_t st) {
+    int rc = check_board_args(in, n, H, W);
+    if (rc) return rc;
+    if (n_steps < 1) return fail(SL_ERR_ARG, "n_steps must be >= 1");
+    if (n == 0) return SL_OK;
+    if (counts == nullptr && out == nullptr) return fail(SL_ERR_ARG, "null output pointer");
+    if (sl::warp_kernel_supports(H, W)) {
+        sl::launch_advance_warp(in, out, counts, n, H, W, spawn_threshold(spawn_prob), n_steps,
+                                rng, st);
+        return launch_status("k_advance_warp");
+    }
+    size_t smem = sl::generic_smem_bytes(H * W);
+    rc = prepare_smem(sl::k_advance_generic, smem);
+    if (rc) return rc;
+    sl::k_advance_generic<<<grid_for(n), sl::GENERIC_THREADS, smem, st>>>(
+        in, out, counts, n, H, W, spawn_threshold(spawn_prob), n_steps, rng);
+    return launch_status("k_advance_generic");
+}
+
+// Scratch device buffer for the *_host entry points (per thread, grown on demand).
+struct HostStage {
+    void *ptr = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    int reserve(size_t bytes) {
+        int cur;
+        SL_CUDA(cudaGetDevice(&cur));
+        if (bytes <= cap && cur == dev) return SL_OK;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        SL_CUDA(cudaMalloc(&ptr, bytes));
+        cap = bytes;
+        dev = cur;
+        return SL_OK;
+    }
+};
+thread_local HostStage g_stage;
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+int sl_abi_version(void) { return SL_ABI_VERSION; }
+
+const char *sl_last_error(void) { return g_err; }
+
+int sl_device_info(int *sm_count, int *l2_bytes, int *cc_major, int *cc_minor) {
+    DeviceProps p;
+    int rc = device_props(&p);
+    if (rc) return rc;
+    if (sm_count) *sm_count = p.sm_count;
+    if (l2_bytes) *l2_bytes = p.l2_bytes;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    return SL_OK;
+}
+
+int sl_warp_kernel_supported(int H, int W) { return sl::warp_kernel_supports(H, W) ? 1 : 0; }
+
+int sl_advance_board(const uint16_t *in, uint16_t *out, int n, int H, int W, float spawn_prob,
+                     int n_steps, uint64_t *rng, void *stream) {
+    return advance_impl(in, out, nullptr, n, H, W, spawn_prob, n_steps, rng, (cudaStream_t)stream);
+}
+
+int sl_life_occupancy(const uint16_t *board, int32_t *counts, int n, int H, int W,
+                      float spawn_prob, int n_steps, uint64_t *rng, void *stream) {
+    if (n > 0 && counts == nullptr) return fail(SL_ERR_ARG, "null counts pointer");
+    return advance_impl(board, nullptr, counts, n, H, W, spawn_prob, n_steps, rng,
+                        (cudaStream_t)stream);
+}
+
+int sl_alive_counts(const uint16_t *board, const uint16_t *goals, int64_t *out, int n, int cells,
+                    void *stream) {
+    if (n < 0 || cells < 0) return fail(SL_ERR_ARG, "negative size");
+    if (n == 0) return SL_OK;
+    if (!board || !goals || !out) return fail(SL_ERR_ARG, "null pointer");
+    sl::k_alive_counts<<<grid_for(n), sl::GENERIC_THREADS, 0, (cudaStream_t)stream>>>(
+        board, goals, out, n, cells);
+    return launch_status("k_alive_counts");
+}
+
+int sl_execute_actions(uint16_t *board, int64_t *locations, const int64_t *actions, int n, int H,
+                       int W, int n_agents, int action_stride, void *stream) {
+    int rc = check_board_args(board, n, H, W);
+    if (rc) return rc;
+    if (n_agents < 0) return fail(SL_ERR_ARG, "Locations should be shape (n_agent, 2).");
+    if (action_stride != 0 && action_stride != 1)
+        return fail(SL_ERR_ARG, "action_stride must be 0 (broadcast) or 1");
+    if (n == 0 || n_agents == 0) return SL_OK;
+    if (!locations || !actions) return fail(SL_ERR_ARG, "null pointer");
+    sl::k_execute_actions<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+        board, locations, actions, n, H, W, n_agents, action_stride);
+    return launch_status("k_execute_actions");
+}
+
+int sl_wrapped_label(int32_t *data, int32_t *num_labels, int n, int H, int W, void *stream) {
+    if (n < 0) return fail(SL_ERR_ARG, "n must be >= 0");
+    if (H < 1 || W < 1) return fail(SL_ERR_ARG, "grid must be non-empty");
+    if (n == 0) return SL_OK;
+    if (!data || !num_labels) return fail(SL_ERR_ARG, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t *scratch = nullptr;
+    SL_CUDA(cudaMallocAsync((void **)&scratch, (size_t)n * H * W * 3 * sizeof(int32_t), st));
+    sl::k_wrapped_label<<<(n + 31) / 32, 32, 0, st>>>(data, num_labels, scratch, n, H, W);
+    int rc = launch_status("k_wrapped_label");
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// ---- host-buffer variants ------------------------------------------------
+
+int sl_advance_board_host(const uint16_t *in, uint16_t *out, int n, int H, int W, float spawn_prob,
+                          int n_steps, uint64_t *rng) {
+    int rc = check_board_args(in, n, H, W);
+    if (rc) return rc;
+    if (n_steps < 1) return fail(SL_ERR_ARG, "n_steps must be >= 1");
+    if (n == 0) return SL_OK;
+    if (!out) return fail(SL_ERR_ARG, "null output pointer");
+    size_t bbytes = (size_t)n * H * W * 2, rbytes = rng ? (size_t)n * 32 : 0;
+    rc = g_stage.reserve(align256(bbytes) + align256(rbytes) + 256);
+    if (rc) return rc;
+    uint16_t *d_board = (uint16_t *)g_stage.ptr;
+    uint64_t *d_rng = rng ? (uint64_t *)((char *)g_stage.ptr + align256(bbytes)) : nullptr;
+    SL_CUDA(cudaMemcpyAsync(d_board, in, bbytes, cudaMemcpyHostToDevice, 0));
+    if (rng) SL_CUDA(cudaMemcpyAsync(d_rng, rng, rbytes, cudaMemcpyHostToDevice, 0));
+    rc = advance_impl(d_board, d_board, nullptr, n, H, W, spawn_prob, n_steps, d_rng, 0);
+    if (rc) return rc;
+    SL_CUDA(cudaMemcpyAsync(out, d_board, bbytes, cudaMemcpyDeviceToHost, 0));
+    if (rng) SL_CUDA(cudaMemcpyAsync(rng, d_rng, rbytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaStreamSynchronize(0));
+    return SL_OK;
+}
+
+int sl_life_occupancy_host(const uint16_t *board, int32_t *counts, int n, int H, int W,
+                           float spawn_prob, int n_steps, uint64_t *rng) {
+    int rc = check_board_args(board, n, H, W);
+    if (rc) return rc;
+    if (n_steps < 1) return fail(SL_ERR_ARG, "n_steps must be >= 1");
+    if (n == 0) return SL_OK;
+    if (!counts) return fail(SL_ERR_ARG, "null counts pointer");
+    size_t bbytes = (size_t)n * H * W * 2, cbytes = (size_t)n * H * W * 8 * 4,
+           rbytes = rng ? (size_t)n * 32 : 0;
+    rc = g_stage.reserve(align256(bbytes) + align256(cbytes) + align256(rbytes) + 256);
+    if (rc) return rc;
+    char *base = (char *)g_stage.ptr;
+    uint16_t *d_board = (uint16_t *)base;
+    int32_t *d_counts = (int32_t *)(base + align256(bbytes));
+    uint64_t *d_rng = rng ? (uint64_t *)(base + align256(bbytes) + align256(cbytes)) : nullptr;
+    SL_CUDA(cudaMemcpyAsync(d_board, board, bbytes, cudaMemcpyHostToDevice, 0));
+    SL_CUDA(cudaMemcpyAsync(d_counts, counts, cbytes, cudaMemcpyHostToDevice, 0));
+    if (rng) SL_CUDA(cudaMemcpyAsync(d_rng, rng, rbytes, cudaMemcpyHostToDevice, 0));
+    rc = advance_impl(d_board, nullptr, d_counts, n, H, W, spawn_prob, n_steps, d_rng, 0);
+    if (rc) return rc;
+    SL_CUDA(cudaMemcpyAsync(counts, d_counts, cbytes, cudaMemcpyDeviceToHost, 0));
+    if (rng) SL_CUDA(cudaMemcpyAsync(rng, d_rng, rbytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaStreamSynchronize(0));
+    return SL_OK;
+}
+
+int sl_alive_counts_host(const uint16_t *board, const uint16_t *goals, int64_t *out, int n,
+                         int cells) {
+    if (n < 0 || cells < 0) return fail(SL_ERR_ARG, "negative size");
+    if (n == 0) return SL_OK;
+    if (!board || !goals || !out) return fail(SL_ERR_ARG, "null pointer");
+    size_t bbytes = (size_t)n * cells * 2, obytes = (size_t)n * 72 * 8;
+    int rc = g_stage.reserve(2 * align256(bbytes) + align256(obytes) + 256);
+    if (rc) return rc;
+    char *base = (char *)g_stage.ptr;
+    uint16_t *d_board = (uint16_t *)base, *d_goals = (uint16_t *)(base + align256(bbytes));
+    int64_t *d_out = (int64_t *)(base + 2 * align256(bbytes));
+    SL_CUDA(cudaMemcpyAsync(d_board, board, bbytes, cudaMemcpyHostToDevice, 0));
+    SL_CUDA(cudaMemcpyAsync(d_goals, goals, bbytes, cudaMemcpyHostToDevice, 0));
+    rc = sl_alive_counts(d_board, d_goals, d_out, n, cells, nullptr);
+    if (rc) return rc;
+    SL_CUDA(cudaMemcpyAsync(out, d_out, obytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaStreamSynchronize(0));
+    return SL_OK;
+}
+
+int sl_execute_actions_host(uint16_t *board, int64_t *locations, const int64_t *actions, int n,
+                            int H, int W, int n_agents, int action_stride) {
+    int rc = check_board_args(board, n, H, W);
+    if (rc) return rc;
+    if (n_agents < 0) return fail(SL_ERR_ARG, "Locations should be shape (n_agent, 2).");
+    if (action_stride != 0 && action_stride != 1)
+        return fail(SL_ERR_ARG, "action_stride must be 0 (broadcast) or 1");
+    if (n == 0 || n_agents == 0) return SL_OK;
+    if (!locations || !actions) return fail(SL_ERR_ARG, "null pointer");
+    size_t bbytes = (size_t)n * H * W * 2, lbytes = (size_t)n * n_agents * 16,
+           abytes = (size_t)n * (action_stride ? n_agents : 1) * 8;
+    rc = g_stage.reserve(align256(bbytes) + align256(lbytes) + align256(abytes) + 256);
+    if (rc) return rc;
+    char *base = (char *)g_stage.ptr;
+    uint16_t *d_board = (uint16_t *)base;
+    int64_t *d_loc = (int64_t *)(base + align256(bbytes));
+    int64_t *d_act = (int64_t *)(base + align256(bbytes) + align256(lbytes));
+    SL_CUDA(cudaMemcpyAsync(d_board, board, bbytes, cudaMemcpyHostToDevice, 0));
+    SL_CUDA(cudaMemcpyAsync(d_loc, locations, lbytes, cudaMemcpyHostToDevice, 0));
+    SL_CUDA(cudaMemcpyAsync(d_act, actions, abytes, cudaMemcpyHostToDevice, 0));
+    rc = sl_execute_actions(d_board, d_loc, d_act, n, H, W, n_agents, action_stride, nullptr);
+    if (rc) return rc;
+    SL_CUDA(cudaMemcpyAsync(board, d_board, bbytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaMemcpyAsync(locations, d_loc, lbytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaStreamSynchronize(0));
+    return SL_OK;
+}
+
+int sl_wrapped_label_host(int32_t *data, int32_t *num_labels, int n, int H, int W) {
+    if (n < 0) return fail(SL_ERR_ARG, "n must be >= 0");
+    if (H < 1 || W < 1) return fail(SL_ERR_ARG, "grid must be non-empty");
+    if (n == 0) return SL_OK;
+    if (!data || !num_labels) return fail(SL_ERR_ARG, "null pointer");
+    size_t dbytes = (size_t)n * H * W * 4, nbytes = (size_t)n * 4;
+    int rc = g_stage.reserve(align256(dbytes) + align256(nbytes) + 256);
+    if (rc) return rc;
+    char *base = (char *)g_stage.ptr;
+    int32_t *d_data = (int32_t *)base, *d_num = (int32_t *)(base + align256(dbytes));
+    SL_CUDA(cudaMemcpyAsync(d_data, data, dbytes, cudaMemcpyHostToDevice, 0));
+    rc = sl_wrapped_label(d_data, d_num, n, H, W, nullptr);
+    if (rc) return rc;
+    SL_CUDA(cudaMemcpyAsync(data, d_data, dbytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaMemcpyAsync(num_labels, d_num, nbytes, cudaMemcpyDeviceToHost, 0));
+    SL_CUDA(cudaStreamSynchronize(0));
+    return SL_OK;
+}
+
+// ---- batched environment ---------------------------------------------------
+
+static int check_batch(const SlEnvBatch *b) {
+    if (!b) return fail(SL_ERR_ARG, "null batch");
+    int rc = check_board_args(b->board, b->n_envs, b->H, b->W);
+    if (rc) return rc;
+    if (b->n_levels < 1 || b->max_exits < 0) return fail(SL_ERR_ARG, "bad level pool sizes");
+    if (b->n_envs > 0 &&
+        (!b->goals || !b->loc || !b->rng || !b->level_id || !b->num_steps || !b->old_value ||
+         !b->ep_length || !b->ep_reward || !b->active || !b->static_goals || !b->reward ||
+         !b->done || !b->success || !b->times_up || !b->pool_board || !b->pool_goals ||
+         !b->pool_loc || !b->pool_table || !b->pool_init_points || !b->pool_required ||
+         !b->pool_spawn_thr || (b->max_exits > 0 && !b->pool_exits)))
+        return fail(SL_ERR_ARG, "null pointer in SlEnvBatch");
+    return SL_OK;
+}
+
+int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (batch->n_envs == 0) return SL_OK;
+    if (!actions) return fail(SL_ERR_ARG, "null actions");
+    if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
+    if (kernel == 2 && !warp_ok)
+        return fail(SL_ERR_ARG, "warp kernel needs H, W <= %d", sl::WARP_MAX_DIM);
+    if (kernel == 2 || (kernel == 0 && warp_ok)) {
+        sl::launch_env_step_warp(*batch, actions, st);
+        return launch_status("k_env_step_warp");
+    }
+    size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
+    rc = prepare_smem(sl::k_env_step_generic, smem);
+    if (rc) return rc;
+    sl::k_env_step_generic<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, st>>>(*batch, actions);
+    return launch_status("k_env_step_generic");
+}
+
+int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *new_level,
+                 int flags, void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (batch->n_envs == 0) return SL_OK;
+    size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
+    rc = prepare_smem(sl::k_env_reset, smem);
+    if (rc) return rc;
+    sl::k_env_reset<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, (cudaStream_t)stream>>>(
+        *batch, mask, new_level, flags);
+    return launch_status("k_env_reset");
+}
+
+int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw, const int32_t *channels,
+               int n_channels, int remove_white_goals, void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (vh < 1 || vw < 1 || n_channels < 0) return fail(SL_ERR_ARG, "bad view shape");
+    if (batch->n_envs == 0) return SL_OK;
+    if (!obs || (n_channels > 0 && !channels)) return fail(SL_ERR_ARG, "null pointer");
+    size_t smem = (size_t)vh * vw * 4;
+    rc = prepare_smem(sl::k_get_obs, smem);
+    if (rc) return rc;
+    sl::k_get_obs<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, (cudaStream_t)stream>>>(
+        *batch, obs, vh, vw, channels, n_channels, remove_white_goals);
+    return launch_status("k_get_obs");
+}
+
+int sl_side_effect_cells(const SlEnvBatch *batch, const uint16_t *baseline, int32_t *out,
+                         void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (batch->n_envs == 0) return SL_OK;
+    if (!baseline || !out) return fail(SL_ERR_ARG, "null pointer");
+    sl::k_side_effect_cells<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, 0, (cudaStream_t)stream>>>(
+        *batch, baseline, out);
+    return launch_status("k_side_effect_cells");
+}
+
+}  // extern "C"

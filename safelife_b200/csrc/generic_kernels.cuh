@@ -1,0 +1,507 @@
+// generic_kernels.cuh -- CTA-per-board kernels for any board size H, W >= 3.
+//
+// These are the general path: one thread block per board, the board staged in
+// shared memory, each thread owning a contiguous raster-order run of cells so
+// that the reference's raster-order RNG draws (advance_board.c:115) can be
+// reproduced with a block prefix sum of "qualifying cell" counts and a PCG64
+// jump-ahead per thread.  The warp-per-env bit-plane kernels in
+// warp_kernels.cuh are the fast path for boards up to 32x32.
+#pragma once
+#include "cells.cuh"
+#include "../../include/safelife_b200.h"
+
+namespace sl {
+
+constexpr int GENERIC_THREADS = 128;
+
+// Exclusive prefix sum of one int per thread across the block.
+// scratch: int[33] shared.  Returns this thread's prefix; *total = block sum.
+__device__ inline int block_exclusive_scan(int v, int *scratch, int *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        int w = lane < nw ? scratch[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, d);
+            if (lane >= d) winc += t;
+        }
+        if (lane < nw) scratch[lane] = winc - w;
+        if (lane == 31) scratch[32] = winc;
+    }
+    __syncthreads();
+    int res = scratch[warp] + inc - v;
+    *total = scratch[32];
+    __syncthreads();
+    return res;
+}
+
+__device__ inline int block_sum(int v, int *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5, s = 0;
+    for (int w = 0; w < nw; w++) s += scratch[w];
+    __syncthreads();
+    return s;
+}
+
+// One stencil step src -> dst (both shared, `cells` uint16 each) for the whole
+// block.  rng_sh: uint64[4] in shared memory, advanced by the number of draws
+// (thr == 0 or rng_sh == nullptr: every draw fails and no state is written).
+// Ends with a __syncthreads().
+__device__ inline void block_advance(const uint16_t *src, uint16_t *dst, int H, int W,
+                                     uint64_t thr, uint64_t *rng_sh, int *scratch) {
+    const int cells = H * W;
+    const int chunk = (cells + blockDim.x - 1) / blockDim.x;
+    const int begin = min(cells, (int)threadIdx.x * chunk);
+    const int end = min(cells, begin + chunk);
+    auto at = [src](int i) -> uint32_t { return src[i]; };
+    int nq = 0;
+    for (int i = begin; i < end; i++) {
+        int y = i / W, x = i - y * W;
+        Hood h = gather_hood(at, y, x, H, W);
+        bool q;
+        uint32_t r = apply_rule(src[i], h, &q);
+        // a qualifying cell is dead and not frozen, so bit 15 (PULLABLE) of the
+        // would-be spawned word is free to tag it until the draw is resolved
+        dst[i] = (uint16_t)(q ? (r | 0x8000u) : r);
+        nq += q;
+    }
+    int total;
+    int prefix = block_exclusive_scan(nq, scratch, &total);
+    if (total > 0) {
+        if (nq > 0) {
+            Pcg g;
+            bool have = rng_sh != nullptr;
+            if (have) {
+                g = {{rng_sh[0], rng_sh[1]}, {rng_sh[2], rng_sh[3]}};
+                g.state = pcg_jump(g.state, g.inc, (uint32_t)prefix);
+            }
+            for (int i = begin; i < end; i++) {
+                uint32_t r = dst[i];
+                if (!(src[i] & ALIVE) && (r & 0x8000u) && (r & ALIVE)) {
+                    // tagged: a dead cell only comes out ALIVE with bit 15 set
+                    // through the tag above (births and spawns never carry it)
+                    bool ok = have && pcg_next_below(g, thr);
+                    dst[i] = ok ? (uint16_t)(r & 0x7fffu) : src[i];
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && rng_sh != nullptr) {
+            u128 s = pcg_jump({rng_sh[0], rng_sh[1]}, {rng_sh[2], rng_sh[3]}, (uint32_t)total);
+            rng_sh[0] = s.hi;
+            rng_sh[1] = s.lo;
+        }
+    }
+    __syncthreads();
+}
+
+__host__ __device__ inline size_t generic_smem_bytes(int cells) {
+    // three uint16 planes (16-byte aligned each) + scratch
+    size_t plane = ((size_t)cells * 2 + 15) & ~(size_t)15;
+    return 3 * plane + 64 * sizeof(int);
+}
+
+struct GenericSmem {
+    uint16_t *a, *b, *c;
+    int *scratch;       // int[33]
+    uint64_t *rng;      // uint64[4]
+    int *misc;          // int[8]
+    __device__ GenericSmem(unsigned char *base, int cells) {
+        size_t plane = ((size_t)cells * 2 + 15) & ~(size_t)15;
+        a = (uint16_t *)base;
+        b = (uint16_t *)(base + plane);
+        c = (uint16_t *)(base + 2 * plane);
+        scratch = (int *)(base + 3 * plane);
+        rng = (uint64_t *)(scratch + 40);
+        misc = scratch + 48;
+    }
+};
+
+// ------------------------------------------------------------------------
+// n-step advance, optionally accumulating life occupancy.
+// counts == nullptr : out[b] = board after n_steps (module.c:20-49).
+// counts != nullptr : counts[b][cell][colour] += occupancy after each step
+//                     (module.c:52-81); `out` unused.
+// ------------------------------------------------------------------------
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_advance_generic(const uint16_t *in, uint16_t *out,   // may alias
+                  int32_t *__restrict__ counts, int n, int H, int W, uint64_t thr,
+                  int n_steps, uint64_t *__restrict__ rng) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cells = H * W;
+    GenericSmem sm(smem_raw, cells);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        const uint16_t *src = in + (size_t)b * cells;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.a[i] = src[i];
+        if (rng != nullptr && threadIdx.x < 4) sm.rng[threadIdx.x] = rng[4 * (size_t)b + threadIdx.x];
+        __syncthreads();
+        uint16_t *cur = sm.a, *nxt = sm.b;
+        for (int s = 0; s < n_steps; s++) {
+            block_advance(cur, nxt, H, W, thr, rng ? sm.rng : nullptr, sm.scratch);
+            if (counts != nullptr) {
+                int32_t *cnt = counts + (size_t)b * cells * 8;
+                for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                    uint32_t c = nxt[i];
+                    if ((c & ALIVE) && !(c & (AGENT | EXIT | FROZEN)))
+                        cnt[8 * i + ((c & COLORS) >> COLOR_SHIFT)] += 1;
+                }
+            }
+            uint16_t *t = cur; cur = nxt; nxt = t;
+        }
+        if (counts == nullptr) {
+            uint16_t *dst = out + (size_t)b * cells;
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) dst[i] = cur[i];
+        }
+        if (rng != nullptr && threadIdx.x < 2) rng[4 * (size_t)b + threadIdx.x] = sm.rng[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// out[b][72] histogram (advance_board.c:192-207).
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_alive_counts(const uint16_t *__restrict__ board, const uint16_t *__restrict__ goals,
+               int64_t *__restrict__ out, int n, int cells) {
+    __shared__ int hist[72];
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        if (threadIdx.x < 72) hist[threadIdx.x] = 0;
+        __syncthreads();
+        const uint16_t *bd = board + (size_t)b * cells, *gl = goals + (size_t)b * cells;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            int bin = count_bin(bd[i], gl[i]);
+            if (bin >= 0) atomicAdd(&hist[bin], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 72) out[(size_t)b * 72 + threadIdx.x] = hist[threadIdx.x];
+        __syncthreads();
+    }
+}
+
+// One thread per board; agents act in index order (advance_board.c:220).
+__global__ void k_execute_actions(uint16_t *__restrict__ board, int64_t *__restrict__ locations,
+                                  const int64_t *__restrict__ actions, int n, int H, int W,
+                                  int n_agents, int action_stride) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    uint16_t *bd = board + (size_t)b * H * W;
+    int64_t *loc = locations + (size_t)b * n_agents * 2;
+    const int64_t *act = actions + (size_t)b * (action_stride ? n_agents : 1);
+    for (int k = 0; k < n_agents; k++) {
+        int64_t a = act[action_stride ? k : 0];
+        if (a == 0) continue;
+        int y0 = (int)(loc[2 * k] % H), x0 = (int)(loc[2 * k + 1] % W);
+        int y = y0, x = x0;
+        // action >= 5 toggles, direction (a-1)&3: fold large values into that form
+        int act_small = (a >= 5) ? 5 + (int)((a - 1) & 3) : 1 + (int)((a - 1) & 3);
+        agent_action(bd, H, W, y, x, act_small);
+        if (y != y0 || x != x0) {
+            loc[2 * k] = y;
+            loc[2 * k + 1] = x;
+        }
+    }
+}
+
+// Sequential emulation of wrapped_label.c:5-55 (incl. the iset visiting order
+// of iset.c:6-61), one thread per grid; work arrays in global scratch.
+__global__ void k_wrapped_label(int32_t *__restrict__ data, int32_t *__restrict__ num_labels,
+                                int32_t *__restrict__ scratch, int n, int H, int W) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    const int size = H * W;
+    int32_t *d = data + (size_t)b * size;
+    int32_t *order = scratch + (size_t)b * size * 3, *pos = order + size, *stack = pos + size;
+    for (int i = 0; i < size; i++) order[i] = pos[i] = i;
+    int nvis = 0, label = 0;
+    while (nvis < size) {
+        int seed = order[nvis++];
+        if (!d[seed]) continue;
+        d[seed] = ++label;
+        int top = 0;
+        stack[top++] = seed;
+        while (top > 0) {
+            int cur = stack[--top];
+            int r = cur / W, c = cur - r * W;
+            for (int dy = -1; dy <= 1; dy++) {
+                int y = wrap_idx(r + dy, H);
+                for (int dx = -1; dx <= 1; dx++) {
+                    int x = wrap_idx(c + dx, W);
+                    int j = y * W + x;
+                    bool seen = pos[j] < nvis;
+                    if (d[j] > 0 && !seen) {
+                        d[j] = label;
+                        stack[top++] = j;
+                    }
+                    if (!seen) {
+                        int k = pos[j], other = order[nvis];
+                        order[nvis] = j; pos[j] = nvis;
+                        order[k] = other; pos[other] = k;
+                        nvis++;
+                    }
+                }
+            }
+        }
+    }
+    num_labels[b] = label;
+}
+
+// ------------------------------------------------------------------------
+// Exit / points logic shared by step and reset (single thread per env).
+// GameWithGoals.can_exit + update_exit_colors (safelife_game.py:537-552,
+// 716-719) on the board in `bd` (shared or global); returns current_points
+// (:684-687) AFTER the update.  count_points = sum(table * alive_counts).
+// ------------------------------------------------------------------------
+template <typename T>
+__device__ inline int exit_update(T *bd, int W, int row, int col, int count_points,
+                                  int init_points, int required, const int32_t *exits,
+                                  int max_exits, bool *agent_alive, bool *exited) {
+    bool can_exit = false;
+    int idx = -1;
+    if (row >= 0) {
+        idx = row * W + col;
+        uint32_t a = bd[idx];
+        int earned = count_points - init_points + (((a & (AGENT | EXIT)) == EXIT) ? 1 : 0);
+        earned = max(earned, 0);
+        can_exit = (a & AGENT) && earned >= required;
+        bd[idx] = (T)((a & ~(uint32_t)EXIT) | (can_exit ? (uint32_t)EXIT : 0u));
+    }
+    T exit_type = (T)(LEVEL_EXIT | (can_exit ? (uint32_t)COLOR_R : 0u));
+    for (int k = 0; k < max_exits; k++) {
+        int e = exits[k];
+        if (e >= 0) bd[e] = exit_type;
+    }
+    *agent_alive = false;
+    *exited = false;
+    if (idx < 0) return count_points;
+    uint32_t a = bd[idx];
+    *agent_alive = (a & AGENT) != 0;
+    *exited = (a & (AGENT | EXIT)) == EXIT;
+    return count_points + (*exited ? 1 : 0);
+}
+
+// sum(table * alive_counts) over a board/goals pair by the whole block.
+__device__ inline int block_points(const uint16_t *bd, const uint16_t *gl, int cells,
+                                   const int32_t *__restrict__ table, int *scratch) {
+    int s = 0;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        int bin = count_bin(bd[i], gl[i]);
+        if (bin >= 0) s += __ldg(table + bin);
+    }
+    return block_sum(s, scratch);
+}
+
+// SafeLifeEnv.step, one CTA per env (safelife_env.py:148-201).
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_env_step_generic(SlEnvBatch B, const uint8_t *__restrict__ actions) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = B.H, W = B.W, cells = H * W;
+    GenericSmem sm(smem_raw, cells);
+    for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
+        uint16_t *board = B.board + (size_t)e * cells;
+        uint16_t *goals = B.goals + (size_t)e * cells;
+        const int lvl = B.level_id[e];
+        const uint64_t thr = B.pool_spawn_thr[lvl];
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.a[i] = board[i];
+        if (threadIdx.x < 4) sm.rng[threadIdx.x] = B.rng[4 * (size_t)e + threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int row = B.loc[2 * e], col = B.loc[2 * e + 1];
+            if (row >= 0) agent_action(sm.a, H, W, row, col, (int)actions[e]);
+            sm.misc[0] = row;
+            sm.misc[1] = col;
+        }
+        __syncthreads();
+        block_advance(sm.a, sm.b, H, W, thr, sm.rng, sm.scratch);   // board: a -> b
+        // goals (safelife_game.py:753-761): advanced from the same stream
+        // after the board unless known static.
+        int sg = B.static_goals[e];
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.a[i] = goals[i];
+        __syncthreads();
+        const uint16_t *gl = sm.a;
+        if (sg != 1) {
+            block_advance(sm.a, sm.c, H, W, thr, sm.rng, sm.scratch);   // goals: a -> c
+            if (sg == 0) {
+                int diff = 0;
+                for (int i = threadIdx.x; i < cells; i += blockDim.x)
+                    diff |= ((sm.c[i] & SPAWNING) || (sm.c[i] != sm.a[i])) ? 1 : 0;
+                diff = block_sum(diff, sm.scratch);
+                sg = diff ? 2 : 1;
+            }
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) goals[i] = sm.c[i];
+            gl = sm.c;
+        }
+        int pts = block_points(sm.b, gl, cells, B.pool_table + (size_t)lvl * 72, sm.scratch);
+        if (threadIdx.x == 0) {
+            bool agent_alive, exited;
+            int row = sm.misc[0], col = sm.misc[1];
+            int value = exit_update(sm.b, W, row, col, pts, B.pool_init_points[lvl],
+                                    B.pool_required[lvl], B.pool_exits + (size_t)lvl * B.max_exits,
+                                    B.max_exits, &agent_alive, &exited);
+            int steps = B.num_steps[e] + 1;
+            bool times_up = steps >= B.time_limit;
+            bool active = B.active[e] != 0;
+            float reward;
+            bool done, success;
+            if (row >= 0) {
+                reward = (float)((value - B.old_value[e]) * (active ? 1 : 0));
+                success = exited;
+                done = !agent_alive || times_up;
+            } else {
+                reward = 0.f; done = true; success = false;
+            }
+            B.num_steps[e] = steps;
+            B.old_value[e] = value;
+            // first step of an episode: totals restart (see SL_RESET_KEEP_STATS)
+            B.ep_reward[e] = (steps == 1 ? 0.f : B.ep_reward[e]) + reward;
+            B.ep_length[e] = (steps == 1 ? 0 : B.ep_length[e]) + (active ? 1 : 0);
+            B.active[e] = (active && !done) ? 1 : 0;
+            B.static_goals[e] = (uint8_t)sg;
+            B.reward[e] = reward;
+            B.done[e] = done;
+            B.success[e] = success;
+            B.times_up[e] = times_up;
+            B.loc[2 * e] = row;
+            B.loc[2 * e + 1] = col;
+        }
+        if (threadIdx.x < 2) B.rng[4 * (size_t)e + threadIdx.x] = sm.rng[threadIdx.x];
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) board[i] = sm.b[i];
+        __syncthreads();
+    }
+}
+
+// SafeLifeEnv.reset for masked envs (safelife_env.py:203-218), CTA per env.
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_env_reset(SlEnvBatch B, const uint8_t *__restrict__ mask, const int32_t *__restrict__ new_level,
+            int flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = B.H, W = B.W, cells = H * W;
+    GenericSmem sm(smem_raw, cells);
+    for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
+        if (mask != nullptr && !mask[e]) continue;
+        int lvl = new_level != nullptr ? new_level[e] : B.level_id[e];
+        if (new_level == nullptr && (flags & SL_RESET_NEXT_LEVEL))
+            lvl = (int)(((long long)lvl + B.level_stride) % B.n_levels);
+        const uint16_t *pb = B.pool_board + (size_t)lvl * cells;
+        const uint16_t *pg = B.pool_goals + (size_t)lvl * cells;
+        uint16_t *board = B.board + (size_t)e * cells;
+        uint16_t *goals = B.goals + (size_t)e * cells;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            sm.a[i] = pb[i];
+            uint16_t g = pg[i];
+            sm.b[i] = g;
+            goals[i] = g;
+        }
+        __syncthreads();
+        int pts = block_points(sm.a, sm.b, cells, B.pool_table + (size_t)lvl * 72, sm.scratch);
+        if (threadIdx.x == 0) {
+            bool agent_alive, exited;
+            int row = B.pool_loc[2 * lvl], col = B.pool_loc[2 * lvl + 1];
+            int value = exit_update(sm.a, W, row, col, pts, B.pool_init_points[lvl],
+                                    B.pool_required[lvl], B.pool_exits + (size_t)lvl * B.max_exits,
+                                    B.max_exits, &agent_alive, &exited);
+            B.level_id[e] = lvl;
+            B.loc[2 * e] = row;
+            B.loc[2 * e + 1] = col;
+            B.num_steps[e] = 0;
+            B.old_value[e] = value;
+            if (!(flags & SL_RESET_KEEP_STATS)) {
+                B.ep_length[e] = 0;
+                B.ep_reward[e] = 0.f;
+            }
+            B.active[e] = 1;
+            B.static_goals[e] = 0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) board[i] = sm.a[i];
+        __syncthreads();
+    }
+}
+
+// SafeLifeEnv.get_obs (safelife_env.py:105-146, helper_utils.py:42-75).
+// One CTA per env: build the uint32 view in shared memory, then expand.
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
+          const int32_t *__restrict__ channels, int n_channels, int remove_white) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *view = (uint32_t *)smem_raw;
+    const int H = B.H, W = B.W, cells = H * W, vcells = vh * vw;
+    for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
+        const uint16_t *board = B.board + (size_t)e * cells;
+        const uint16_t *goals = B.goals + (size_t)e * cells;
+        int y0 = B.loc[2 * e], x0 = B.loc[2 * e + 1];
+        if (y0 < 0) { y0 = 0; x0 = 0; }
+        auto packed = [&](int idx) -> uint32_t {
+            uint32_t g = goals[idx] & COLORS;
+            if (remove_white && g == COLORS) g = 0;
+            return (uint32_t)board[idx] | (g << 16);
+        };
+        for (int i = threadIdx.x; i < vcells; i += blockDim.x) {
+            int r = i / vw, c = i - r * vw;
+            int y = ((y0 - vh / 2 + r) % H + H) % H;
+            int x = ((x0 - vw / 2 + c) % W + W) % W;
+            view[i] = packed(y * W + x);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int32_t *exits = B.pool_exits + (size_t)B.level_id[e] * B.max_exits;
+            for (int k = 0; k < B.max_exits; k++) {
+                int idx = exits[k];
+                if (idx < 0) continue;
+                int iy = idx / W, ix = idx - iy * W;
+                int jy = ((iy - y0 + H / 2) % H + H) % H - H / 2 + vh / 2;
+                int jx = ((ix - x0 + W / 2) % W + W) % W - W / 2 + vw / 2;
+                jy = min(max(jy, 0), vh - 1);
+                jx = min(max(jx, 0), vw - 1);
+                view[jy * vw + jx] = packed(idx);
+            }
+        }
+        __syncthreads();
+        if (n_channels == 0) {
+            uint32_t *o = (uint32_t *)obs + (size_t)e * vcells;
+            for (int i = threadIdx.x; i < vcells; i += blockDim.x) o[i] = view[i];
+        } else {
+            uint8_t *o = (uint8_t *)obs + (size_t)e * vcells * n_channels;
+            const int total = vcells * n_channels;
+            for (int i = threadIdx.x; i < total; i += blockDim.x) {
+                int cell = i / n_channels, k = i - cell * n_channels;
+                o[i] = (uint8_t)((view[cell] >> __ldg(channels + k)) & 1u);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// SimpleSideEffectPenalty cell count (env_wrappers.py:177-213).
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_side_effect_cells(SlEnvBatch B, const uint16_t *__restrict__ baseline, int32_t *__restrict__ out) {
+    __shared__ int scratch[40];
+    const int cells = B.H * B.W;
+    const uint32_t keep = 0xffffu & ~(AGENT | DESTRUCTIBLE | FROZEN | PRESERVING | INHIBITING);
+    for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
+        const uint16_t *bd = B.board + (size_t)e * cells, *bl = baseline + (size_t)e * cells;
+        const int32_t *exits = B.pool_exits + (size_t)B.level_id[e] * B.max_exits;
+        int s = 0;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            bool is_exit = false;
+            for (int k = 0; k < B.max_exits; k++) is_exit |= (exits[k] == i);
+            if (!is_exit && ((bd[i] ^ bl[i]) & keep)) s++;
+        }
+        s = block_sum(s, scratch);
+        if (threadIdx.x == 0) out[e] = s;
+    }
+}
+
+}  // namespace sl

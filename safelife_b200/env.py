@@ -1,0 +1,276 @@
+"""
+BatchedSafeLifeEnv -- the reference's ``SafeLifeEnv`` gym API
+(safelife/safelife_env.py:13-246) over a batch of N single-agent environments
+whose whole state lives on one B200 and is stepped by libsafelife_b200.
+
+    env = BatchedSafeLifeEnv(levels, num_envs=4096, view_shape=(25, 25))
+    obs = env.reset()                              # uint8 [N, vh, vw, C] (cuda)
+    obs, reward, done, info = env.step(actions)    # reward f32 [N], done bool [N]
+
+Same keyword arguments as the reference (safelife_env.py:64-73): single_agent,
+time_limit, remove_white_goals, view_shape, output_channels,
+side_effect_weights, should_calculate_side_effects; unknown keys raise
+ValueError like ``load_kwargs`` (helper_utils.py:78-87).  ``action_space`` is
+Discrete(9) and ``observation_space`` a Box of the per-env observation shape.
+
+Differences that come with batching, all deliberate:
+  * `levels` is a list of level dicts / a path (see safelife_b200.levels), held
+    on the device as a pool; env e starts on level e % L and, when an episode
+    ends and ``auto_reset`` is on, moves to level (current + N) % L -- the
+    batched form of ``BaseAlgo.act_on_envs`` calling ``env.reset()`` on done
+    (training/base_algo.py:231-236).  The returned `obs` of a finished env is
+    the first observation of its next episode, as in that loop.
+  * each env owns a PCG64 stream (uint64[4]); the reference swaps a global
+    generator in and out per game (safelife/random.py:19-32).
+  * `info` holds batched tensors: board, goals, agent_locs, times_up, and
+    episode = {length, reward, success} (safelife_env.py:177-201).  After an
+    auto-reset the episode totals stay readable until that env's next step.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from .levels import LevelPool, load_levels
+
+
+class Discrete(object):
+    def __init__(self, n):
+        self.n = n
+
+
+class Box(object):
+    def __init__(self, low, high, shape, dtype):
+        self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
+
+
+def _as_i16(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint16).view(np.int16))
+
+
+def _as_i64(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint64).view(np.int64))
+
+
+def seed_rng_states(seed, n):
+    """
+    PCG64 states of ``default_rng(s)`` for s in SeedSequence(seed).spawn(n) --
+    how the reference seeds one game per level (level_iterator.py:218,
+    safelife_game.py:175-180).  uint64[n,4] = state_hi, state_lo, inc_hi, inc_lo.
+    """
+    ss = seed if isinstance(seed, np.random.SeedSequence) else np.random.SeedSequence(seed)
+    out = np.zeros((n, 4), dtype=np.uint64)
+    m = (1 << 64) - 1
+    for i, child in enumerate(ss.spawn(n)):
+        st = np.random.PCG64(child).state["state"]
+        out[i] = [st["state"] >> 64, st["state"] & m, st["inc"] >> 64, st["inc"] & m]
+    return out
+
+
+class GameView(object):
+    """Host copy of one env with SafeLifeGame's attribute names (safelife_game.py:126-160)."""
+
+
+class BatchedSafeLifeEnv(object):
+    # defaults as in the reference (safelife_env.py:64-73)
+    single_agent = True
+    time_limit = 1000
+    remove_white_goals = True
+    view_shape = (15, 15)
+    output_channels = tuple(range(16)) + (25, 26, 27)
+    side_effect_weights = None
+    should_calculate_side_effects = False
+
+    def __init__(self, levels, num_envs, device=None, seed=None, auto_reset=True,
+                 min_performance_fraction=1.0, kernel=0, **kwargs):
+        for key, val in kwargs.items():
+            if key.startswith("_") or not hasattr(type(self), key):
+                raise ValueError("Unrecognized parameter: '%s'" % (key,))
+            setattr(self, key, val)
+        if not self.single_agent:
+            raise ValueError("BatchedSafeLifeEnv supports single_agent=True only")
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedSafeLifeEnv needs a CUDA device: there is no CPU fallback")
+        self._lib = _lib.lib()
+        self.device = torch.device(device if device is not None else
+                                   "cuda:%d" % torch.cuda.current_device())
+        if isinstance(levels, str):
+            levels = load_levels(levels)
+        self.pool = levels if isinstance(levels, LevelPool) else LevelPool(
+            levels, min_performance_fraction)
+        self.num_envs = int(num_envs)
+        self.auto_reset = bool(auto_reset)
+        self.kernel = int(kernel)
+        self.view_shape = tuple(int(v) for v in self.view_shape)
+        self.action_space = Discrete(9)
+        if self.output_channels is None:
+            self.observation_space = Box(0, 2 ** 15, self.view_shape, np.uint32)
+        else:
+            self.output_channels = tuple(int(c) for c in self.output_channels)
+            self.observation_space = Box(0, 1, self.view_shape + (len(self.output_channels),),
+                                         np.uint8)
+        N, H, W, dev = self.num_envs, self.pool.H, self.pool.W, self.device
+        with torch.cuda.device(dev):
+            p = self.pool
+            self._pool_t = {
+                "pool_board": _as_i16(p.board).to(dev), "pool_goals": _as_i16(p.goals).to(dev),
+                "pool_loc": torch.from_numpy(p.loc).to(dev),
+                "pool_table": torch.from_numpy(p.table).to(dev),
+                "pool_exits": torch.from_numpy(p.exits).to(dev),
+                "pool_init_points": torch.from_numpy(p.init_points).to(dev),
+                "pool_required": torch.from_numpy(p.required).to(dev),
+                "pool_spawn_thr": _as_i64(p.spawn_thr).to(dev),
+            }
+            z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+            self._t = {
+                "board": z((N, H, W), torch.int16), "goals": z((N, H, W), torch.int16),
+                "loc": z((N, 2), torch.int32), "rng": z((N, 4), torch.int64),
+                "level_id": (torch.arange(N, dtype=torch.int64) % len(p)).to(torch.int32).to(dev),
+                "num_steps": z((N,), torch.int32), "old_value": z((N,), torch.int32),
+                "ep_length": z((N,), torch.int32), "ep_reward": z((N,), torch.float32),
+                "active": z((N,), torch.uint8), "static_goals": z((N,), torch.uint8),
+                "reward": z((N,), torch.float32), "done": z((N,), torch.uint8),
+                "success": z((N,), torch.uint8), "times_up": z((N,), torch.uint8),
+            }
+            self._t["rng"].copy_(_as_i64(seed_rng_states(seed, N)))
+            if self.output_channels is None:
+                self._obs = z((N,) + self.view_shape, torch.int32)
+                self._channels = None
+            else:
+                self._obs = z((N,) + self.view_shape + (len(self.output_channels),), torch.uint8)
+                self._channels = torch.tensor(self.output_channels, dtype=torch.int32, device=dev)
+            self._actions = z((N,), torch.uint8)
+        self._batch = _lib.SlEnvBatch(
+            n_envs=N, H=H, W=W, max_exits=p.max_exits, time_limit=int(self.time_limit),
+            n_levels=len(p), level_stride=N % len(p),
+            **{k: t.data_ptr() for k, t in self._t.items()},
+            **{k: t.data_ptr() for k, t in self._pool_t.items()})
+        self._batch_ref = ctypes.byref(self._batch)
+        self._has_reset = False
+
+    # ------------------------------------------------------------ tensors
+    @property
+    def board(self):
+        """uint16 [N,H,W] view of the device boards (SafeLifeGame.board layout)."""
+        return self._t["board"].view(torch.uint16)
+
+    @property
+    def goals(self):
+        return self._t["goals"].view(torch.uint16)
+
+    @property
+    def agent_locs(self):
+        """int32 [N,1,2] (row, col), as SafeLifeGame.agent_locs."""
+        return self._t["loc"].view(self.num_envs, 1, 2)
+
+    @property
+    def rng_state(self):
+        """uint64[N,4] PCG64 words as a numpy array (host copy)."""
+        return self._t["rng"].cpu().numpy().view(np.uint64)
+
+    def set_rng_state(self, states):
+        self._t["rng"].copy_(_as_i64(states))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # -------------------------------------------------------------- gym API
+    def reset(self, levels=None):
+        """
+        SafeLifeEnv.reset for every env (safelife_env.py:203-218).  `levels`
+        optionally assigns a pool index per env (int array [N]).
+        """
+        with torch.cuda.device(self.device):
+            new_level = None
+            if levels is not None:
+                new_level = torch.as_tensor(np.asarray(levels, dtype=np.int32)).to(self.device)
+                if new_level.shape != (self.num_envs,):
+                    raise ValueError("levels must have shape (num_envs,)")
+                if int(new_level.min()) < 0 or int(new_level.max()) >= len(self.pool):
+                    raise ValueError("level index out of range")
+            _lib.check(self._lib.sl_env_reset(
+                self._batch_ref, None, new_level.data_ptr() if new_level is not None else None,
+                0, self._stream()))
+            self._has_reset = True
+            return self.get_obs()
+
+    def get_obs(self):
+        """SafeLifeEnv.get_obs (safelife_env.py:105-146) for all envs."""
+        with torch.cuda.device(self.device):
+            nch = 0 if self._channels is None else len(self.output_channels)
+            _lib.check(self._lib.sl_get_obs(
+                self._batch_ref, self._obs.data_ptr(), self.view_shape[0], self.view_shape[1],
+                self._channels.data_ptr() if nch else None, nch,
+                int(bool(self.remove_white_goals)), self._stream()))
+        return self._obs if self._channels is not None else self._obs.view(torch.uint32)
+
+    def step_physics(self, actions):
+        """The step path alone (no observation, no auto-reset): safelife_env.py:148-175."""
+        if not torch.is_tensor(actions):
+            a = np.asarray(actions)
+            if a.shape != (self.num_envs,):
+                raise ValueError("actions must have shape (num_envs,)")
+            if a.size and (a.min() < 0 or a.max() > 8):
+                raise ValueError("actions must be in [0, 8]")
+            actions = torch.from_numpy(a.astype(np.uint8))
+        if actions.shape != (self.num_envs,):
+            raise ValueError("actions must have shape (num_envs,)")
+        self._actions.copy_(actions, non_blocking=True)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_env_step(self._batch_ref, self._actions.data_ptr(),
+                                             self.kernel, self._stream()))
+
+    def step(self, actions):
+        assert self._has_reset, "Game state is not initialized."
+        self.step_physics(actions)
+        t = self._t
+        reward, done = t["reward"], t["done"].bool()
+        info = {
+            "times_up": t["times_up"].bool(),
+            "episode": {"length": t["ep_length"], "reward": t["ep_reward"],
+                        "success": t["success"].bool()},
+        }
+        if self.auto_reset:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.sl_env_reset(
+                    self._batch_ref, t["done"].data_ptr(), None,
+                    _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS, self._stream()))
+        info["board"], info["goals"], info["agent_locs"] = self.board, self.goals, self.agent_locs
+        return self.get_obs(), reward, done, info
+
+    def render(self, mode="ansi"):
+        raise NotImplementedError("rendering is out of scope (SURVEY.md section 2)")
+
+    def close(self):
+        pass
+
+    # ------------------------------------------------------------ host views
+    def game_view(self, i):
+        """Host copy of env i shaped like a SafeLifeGame (for loggers / side_effect_score)."""
+        g = GameView()
+        lvl = int(self._t["level_id"][i])
+        g.board = self.board[i].cpu().numpy()
+        g.goals = self.goals[i].cpu().numpy()
+        loc = self._t["loc"][i].cpu().numpy()
+        g.agent_locs = loc.reshape(1, 2).astype(np.int64) if loc[0] >= 0 else np.empty((0, 2), int)
+        g.agent_names = np.array(["agent%i" % k for k in range(len(g.agent_locs))])
+        level = self.pool.levels[lvl]
+        g.spawn_prob = level["spawn_prob"]
+        g.num_steps = int(self._t["num_steps"][i])
+        g.points_table = np.asarray(level["points_table"]).reshape(1, 8, 9)
+        g.min_performance = level["min_performance"]
+        ex = self.pool.exits[lvl]
+        ex = ex[ex >= 0]
+        g.exit_locs = (ex // self.pool.W, ex % self.pool.W)
+        g._init_data = {"board": level["board"], "goals": level["goals"]}
+        return g
+
+    def get_state(self):
+        """All per-env tensors (clones), e.g. for checkpointing a rollout."""
+        return {k: v.clone() for k, v in self._t.items()}
+
+    def set_state(self, state):
+        for k, v in state.items():
+            self._t[k].copy_(v)
+        self._has_reset = True

@@ -1,0 +1,132 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every declared
+symbol; host logic (level constants, spawn threshold, kwargs) is right."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import oracle as orc
+from safelife_b200 import _lib, levels as lv
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "safelife_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sl_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    _lib.build()
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 17
+    for name in names:
+        assert hasattr(handle, name), name
+    assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
+    assert handle.sl_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    # 7 int32 + padding + 23 pointers
+    assert ctypes.sizeof(_lib.SlEnvBatch) == 32 + 23 * 8
+    assert _lib.SlEnvBatch.board.offset == 32
+
+
+def test_argument_errors_without_gpu():
+    lib = _lib.lib()
+    b = np.zeros((2, 2), dtype=np.uint16)
+    rc = lib.sl_advance_board_host(b.ctypes.data, b.ctypes.data, 1, 2, 2, 0.3, 1, None)
+    assert rc == _lib.SL_ERR_ARG
+    assert b"3x3" in lib.sl_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    b = np.zeros((3, 3), dtype=np.uint16)
+    assert lib.sl_advance_board_host(b.ctypes.data, b.ctypes.data, 1, 3, 3, 0.3, 0, None) == _lib.SL_ERR_ARG
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from safelife_b200 import speedups
+    with pytest.raises(RuntimeError):
+        speedups.advance_board(np.zeros((5, 5), dtype=np.uint16))
+    from safelife_b200.env import BatchedSafeLifeEnv
+    level = {"board": np.zeros((5, 5), np.uint16), "goals": np.zeros((5, 5), np.uint16),
+             "agent_loc": None, "points_table": lv.DEFAULT_POINTS_TABLE,
+             "min_performance": -1, "spawn_prob": 0.3}
+    with pytest.raises(RuntimeError):
+        BatchedSafeLifeEnv([level], 1)
+    with pytest.raises(ValueError):
+        BatchedSafeLifeEnv([level], 1, no_such_option=1)
+
+
+def test_product_tree_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "safelife_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower().replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_spawn_threshold_is_the_float_double_compare():
+    rs = np.random.default_rng(0)
+    for p in list(rs.random(200)) + [0.0, 1.0, 0.3, 1e-9, -0.5, 2.0, 0.5]:
+        thr = lv.spawn_threshold(p)
+        pf = float(np.float32(p))
+        u = rs.integers(0, 1 << 53, 2000, dtype=np.uint64)
+        # values right around the threshold
+        around = np.clip(np.array([thr - 2, thr - 1, thr, thr + 1], dtype=np.int64), 0, (1 << 53) - 1)
+        u = np.concatenate([u, around.astype(np.uint64)])
+        draws = u.astype(np.float64) * (1.0 / 9007199254740992.0)
+        assert np.array_equal(draws < pf, u < np.uint64(thr)), p
+
+
+@pytest.mark.parametrize("group", gu.traj_groups())
+def test_level_pool_constants_match_oracle(group):
+    d = gu.load_traj(group)
+    levels = gu.levels_of(d)
+    pool = lv.LevelPool(levels)
+    for i, level in enumerate(levels):
+        exits, init_points, required = orc.level_constants(
+            level["board"], level["goals"], level["points_table"], level["min_performance"])
+        assert np.array_equal(pool.exits[i][pool.exits[i] >= 0], exits)
+        assert pool.init_points[i] == init_points
+        assert pool.required[i] == required
+        assert np.array_equal(lv.alive_counts_np(level["board"], level["goals"]),
+                              orc.alive_counts(level["board"], level["goals"]))
+
+
+def test_pool_roundtrip(tmp_path):
+    levels = gu.levels_of(gu.load_traj("mazes"))
+    path = str(tmp_path / "pool.npz")
+    lv.save_pool(path, levels)
+    back = lv.load_levels(path)
+    assert len(back) == len(levels)
+    for a, b in zip(levels, back):
+        assert np.array_equal(a["board"], b["board"]) and np.array_equal(a["goals"], b["goals"])
+        assert a["agent_loc"] == b["agent_loc"]
+        assert np.array_equal(np.asarray(a["points_table"]), b["points_table"])
+        assert a["min_performance"] == b["min_performance"]
+
+
+def test_normalize_level_old_and_new_keys():
+    board = np.zeros((6, 7), dtype=np.uint16)
+    board[2, 5] = 122 | (3 << 12)
+    old = {"board": board, "goals": np.zeros_like(board), "agent_loc": np.array([5, 2]),
+           "orientation": np.array(1)}
+    n = lv.normalize_level(old)
+    assert n["agent_loc"] == (2, 5)
+    assert n["board"][2, 5] == 122 | (1 << 12)
+    new = {"board": board, "goals": np.zeros_like(board), "agent_locs": np.array([[2, 5]]),
+           "min_performance": np.float64(0.5), "points_table": lv.DEFAULT_POINTS_TABLE[None]}
+    n = lv.normalize_level(new)
+    assert n["agent_loc"] == (2, 5) and n["min_performance"] == 0.5
+    with pytest.raises(ValueError):
+        lv.normalize_level({"board": board, "goals": board, "agent_locs": np.zeros((2, 2), int)})

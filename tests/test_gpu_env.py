@@ -1,0 +1,212 @@
+"""
+GPU parity of the batched environment (BatchedSafeLifeEnv -> sl_env_step /
+sl_env_reset / sl_get_obs through the C ABI) against the golden reference
+trajectories and the oracle.  Bit-exact boards, goals, RNG; exact float32
+rewards (integers).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [1, 2]   # generic CTA-per-env, warp bit-plane
+
+
+def _make_env(levels, n, time_limit, kernel, rng=None, **kw):
+    from safelife_b200.env import BatchedSafeLifeEnv
+    H, W = levels[0]["board"].shape
+    from safelife_b200 import _lib
+    if kernel == 2 and not _lib.lib().sl_warp_kernel_supported(H, W):
+        pytest.skip("warp kernel does not handle %dx%d boards" % (H, W))
+    env = BatchedSafeLifeEnv(levels, n, time_limit=time_limit, kernel=kernel, auto_reset=False, **kw)
+    if rng is not None:
+        env.set_rng_state(np.asarray(rng, dtype=np.uint64))
+    return env
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("group", gu.traj_groups())
+def test_env_matches_reference_trajectories(group, kernel):
+    d = gu.load_traj(group)
+    levels = gu.levels_of(d)
+    L = len(levels)
+    ch = tuple(int(c) for c in d["channels"]) or None
+    vs = tuple(int(v) for v in d["view_shape"])
+    env = _make_env(levels, L, int(d["time_limit"]), kernel, rng=d["rng_init"],
+                    view_shape=vs, output_channels=ch)
+    obs = env.reset().cpu().numpy()
+    board = env.board.cpu().numpy()
+    for i in range(L):
+        assert gu.crc(board[i]) == d["board0_crc"][i], (group, i)
+        assert gu.crc(obs[i]) == d["obs0_crc"][i], (group, i)
+    for t in range(d["action"].shape[1]):
+        obs, reward, done, info = env.step(d["action"][:, t])
+        obs, reward, done = obs.cpu().numpy(), reward.cpu().numpy(), done.cpu().numpy()
+        board, goals = env.board.cpu().numpy(), env.goals.cpu().numpy()
+        loc, rng = env.agent_locs.cpu().numpy()[:, 0], env.rng_state
+        success = info["episode"]["success"].cpu().numpy()
+        for i in np.flatnonzero(t < d["length"]):
+            where = (group, kernel, i, t)
+            assert reward[i] == d["reward"][i, t], where
+            assert done[i] == bool(d["done"][i, t]), where
+            assert success[i] == bool(d["success"][i, t]), where
+            assert gu.crc(board[i]) == d["board_crc"][i, t], where
+            assert gu.crc(goals[i]) == d["goals_crc"][i, t], where
+            assert np.array_equal(rng[i, :2], d["rng"][i, t]), where
+            if d["agent_loc"][i][0] >= 0:
+                assert np.array_equal(loc[i], d["loc"][i, t]), where
+            assert gu.crc(obs[i]) == d["obs_crc"][i, t], where
+            if t == d["length"][i] - 1:
+                assert np.array_equal(board[i], d["final_board"][i]), where
+                assert info["episode"]["reward"][i].item() == d["ep_reward"][i], where
+                assert info["episode"]["length"][i].item() == d["ep_length"][i], where
+
+
+def _random_levels(rs, n, H, W, spawners=True):
+    """Synthetic levels with every cell type, an agent, exits and coloured goals."""
+    kinds = np.array([0, 0, 0, 0, 0, 0, 9, 9, 1, 16, 32788, 17, 32789, 272, 48, 53, 85, 32884]
+                     + ([152, 144] if spawners else []), dtype=np.uint16)
+    levels = []
+    for _ in range(n):
+        b = kinds[rs.integers(0, len(kinds), (H, W))]
+        colour = (rs.integers(0, 8, (H, W)) << 9).astype(np.uint16)
+        b = np.where((b != 0) & (b != 272), b | colour, b).astype(np.uint16)
+        g = ((rs.integers(0, 8, (H, W)) << 9) * (rs.random((H, W)) < 0.3)).astype(np.uint16)
+        if rs.random() < 0.3:   # dynamic goals
+            g |= (rs.random((H, W)) < 0.2).astype(np.uint16)
+        y, x = int(rs.integers(0, H)), int(rs.integers(0, W))
+        b[y, x] = 122 | (int(rs.integers(0, 8)) << 9)
+        table = rs.integers(-3, 6, (8, 9))
+        table[:, 8] = rs.integers(-1, 2, 8) if rs.random() < 0.5 else 0
+        levels.append({"board": b, "goals": g, "agent_loc": (y, x), "points_table": table,
+                       "min_performance": float(rs.choice([-1, 0.0, 0.01, 0.5])),
+                       "spawn_prob": float(rs.choice([0.3, 0.05, 0.9]))})
+    return levels
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("shape", [(3, 3), (5, 9), (16, 16), (25, 25), (26, 26), (32, 32), (50, 50)])
+def test_env_random_levels_vs_oracle(shape, kernel):
+    H, W = shape
+    rs = np.random.default_rng(1000 * H + W)
+    n, T = 48, 60
+    levels = _random_levels(rs, n, H, W)
+    rng = np.stack([orc.rng_from_seed(i) for i in range(n)])
+    ora = orc.OracleEnv(levels, list(rng), time_limit=40)
+    env = _make_env(levels, n, 40, kernel, rng=rng, view_shape=(9, 11), output_channels=None)
+    obs = env.reset().cpu().numpy()
+    assert np.array_equal(env.board.cpu().numpy(), ora.board)
+    for t in range(T):
+        a = rs.integers(0, 9, n)
+        r0, d0 = ora.step(a.astype(np.int64))
+        obs, r1, d1, info = env.step(a)
+        where = (shape, kernel, t)
+        assert np.array_equal(env.board.cpu().numpy(), ora.board), where
+        assert np.array_equal(env.goals.cpu().numpy(), ora.goals), where
+        assert np.array_equal(env.rng_state, ora.rng), where
+        assert np.array_equal(env.agent_locs.cpu().numpy()[:, 0], ora.loc), where
+        assert np.array_equal(r1.cpu().numpy(), r0), where
+        assert np.array_equal(d1.cpu().numpy(), d0), where
+        assert np.array_equal(info["times_up"].cpu().numpy(), ora.times_up.astype(bool)), where
+        assert np.array_equal(info["episode"]["reward"].cpu().numpy(), ora.ep_reward), where
+        assert np.array_equal(info["episode"]["length"].cpu().numpy(), ora.ep_length), where
+        assert np.array_equal(env._t["static_goals"].cpu().numpy(), ora.static_goals), where
+        obs = obs.cpu().numpy()
+        for i in range(0, n, 7):
+            want = orc.get_obs(ora.board[i], ora.goals[i], ora.loc[i], ora.exits[i], (9, 11), None)
+            assert np.array_equal(obs[i], want), where
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_auto_reset_cycles_levels(kernel):
+    levels = gu.levels_of(gu.load_traj("mazes"))
+    L, n = len(levels), 5
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200 import _lib
+    if kernel == 2 and not _lib.lib().sl_warp_kernel_supported(10, 10):
+        pytest.skip("warp kernel not available")
+    env = BatchedSafeLifeEnv(levels, n, time_limit=7, kernel=kernel, view_shape=(5, 5))
+    env.reset()
+    assert env._t["level_id"].tolist() == [0, 1, 2, 3, 4]
+    pool_after_reset = None
+    for t in range(7):
+        obs, r, d, info = env.step(np.zeros(n, dtype=np.int64))
+    assert d.all() and info["times_up"].all()
+    assert env._t["level_id"].tolist() == [(i + n) % L for i in range(n)]
+    assert env._t["num_steps"].tolist() == [0] * n
+    assert info["episode"]["length"].tolist() == [7] * n
+    # boards are the fresh levels after update_exit_colors
+    ora = orc.OracleEnv([levels[(i + n) % L] for i in range(n)],
+                        [orc.rng_from_seed(0)] * n, time_limit=7)
+    assert np.array_equal(env.board.cpu().numpy(), ora.board)
+    obs, r, d, info = env.step(np.ones(n, dtype=np.int64))
+    assert info["episode"]["length"].tolist() == [1] * n and not d.any()
+
+
+def test_no_agent_level_and_argument_checks():
+    from safelife_b200.env import BatchedSafeLifeEnv
+    b = np.zeros((6, 6), dtype=np.uint16)
+    b[1, 1:4] = 9
+    level = {"board": b, "goals": np.zeros_like(b), "agent_loc": None,
+             "points_table": orc.DEFAULT_POINTS_TABLE, "min_performance": -1, "spawn_prob": 0.3}
+    env = BatchedSafeLifeEnv([level], 2, auto_reset=False)
+    env.reset()
+    obs, r, d, info = env.step([3, 4])
+    assert r.tolist() == [0.0, 0.0] and d.tolist() == [True, True]
+    want = orc.advance_board(b, 0.3, 1)
+    assert np.array_equal(env.board[0].cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        env.step([1, 2, 3])
+    with pytest.raises(ValueError):
+        env.step([1, 9])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_full_size_properties(kernel):
+    """BASELINE-size batch (4096 x 25x25): determinism, shard invariance, oracle spot check."""
+    pool_path = os.path.join(gu.GOLDEN, "pools", "append-still-25.npz")
+    if not os.path.exists(pool_path):
+        pytest.skip("pool fixture missing")
+    import torch
+    from safelife_b200 import _lib
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200.levels import load_levels
+    if kernel == 2 and not _lib.lib().sl_warp_kernel_supported(25, 25):
+        pytest.skip("warp kernel not available")
+    levels = load_levels(pool_path)
+    N, T = 4096, 30
+    acts = np.random.default_rng(2).integers(0, 9, (T, N)).astype(np.uint8)
+
+    def run(lo, hi):
+        env = BatchedSafeLifeEnv([levels[i % len(levels)] for i in range(lo, hi)], hi - lo,
+                                 kernel=kernel, auto_reset=False, seed=1)
+        from safelife_b200.env import seed_rng_states
+        env.set_rng_state(seed_rng_states(1, N)[lo:hi])
+        env.reset()
+        total = torch.zeros(hi - lo, device="cuda")
+        for t in range(T):
+            env.step_physics(acts[t, lo:hi])
+            total += env._t["reward"]
+        return env.board.cpu().numpy(), total.cpu().numpy(), env
+
+    b_all, r_all, env = run(0, N)
+    b_again, r_again, _ = run(0, N)
+    assert np.array_equal(b_all, b_again) and np.array_equal(r_all, r_again)
+    b_lo, r_lo, _ = run(0, N // 2)
+    b_hi, r_hi, _ = run(N // 2, N)
+    assert np.array_equal(np.concatenate([b_lo, b_hi]), b_all)
+    assert np.array_equal(np.concatenate([r_lo, r_hi]), r_all)
+    idx = list(range(0, N, 97))
+    ora = orc.OracleEnv([levels[i % len(levels)] for i in idx],
+                        [orc.rng_from_seed(0)] * len(idx))
+    tot = np.zeros(len(idx), dtype=np.float32)
+    for t in range(T):
+        r, _ = ora.step(acts[t, idx].astype(np.int64))
+        tot += r
+    assert np.array_equal(ora.board, b_all[idx])
+    assert np.array_equal(tot, r_all[idx])
