@@ -110,6 +110,34 @@ int sl_wrapped_label_host(int32_t *data, int32_t *num_labels, int n, int H, int 
 /* ---- batched environment (SafeLifeEnv.step / reset) ------------------- */
 
 /*
+ * Per-env scalar state, one 96-byte record per env (device memory).  Packed so
+ * that a warp reads the whole record with six 16-byte loads.
+ */
+typedef struct SlEnvState {
+    uint64_t rng[4];       /* PCG64 of the game: state_hi, state_lo, inc_hi, inc_lo
+                              (safelife_game.py:175-180) */
+    int32_t  loc_row;      /* agent 0 (row, col); row < 0: the level has no agent */
+    int32_t  loc_col;
+    int32_t  level_id;     /* index into the level pool */
+    int32_t  num_steps;    /* GameState.num_steps */
+    int32_t  old_value;    /* SafeLifeEnv._old_game_value */
+    int32_t  ep_length;    /* SafeLifeEnv.episode_length */
+    float    ep_reward;    /* SafeLifeEnv.episode_reward */
+    uint8_t  active;       /* SafeLifeEnv._is_active */
+    uint8_t  static_goals; /* 0 = unknown (None), 1 = static, 2 = dynamic
+                              (GameWithGoals._static_goals, safelife_game.py:753-761) */
+    uint8_t  empty_points; /* the level's points table has a non-zero "empty" column */
+    uint8_t  reserved0;
+    /* copied from the level pool by sl_env_reset */
+    uint64_t spawn_thr;    /* ceil((double)(float)spawn_prob * 2^53): a draw (u64 >> 11)
+                              spawns iff it is below this */
+    int32_t  init_points;  /* sum(points_table * initial_counts) (safelife_game.py:689-694) */
+    int32_t  required;     /* required_points() (:711-714) */
+    int32_t  count_points; /* sum(points_table * alive_counts) of the board in memory */
+    int32_t  reserved1[3];
+} SlEnvState;
+
+/*
  * Device-resident state of n_envs single-agent SafeLife environments plus the
  * read-only level pool they reset from.  All pointers are device pointers
  * owned by the caller (torch tensors in the Python host layer).
@@ -122,18 +150,9 @@ typedef struct SlEnvBatch {
     int32_t level_stride;  /* auto-reset rule: level_id <- (level_id + level_stride) % n_levels */
 
     /* per-env state */
-    uint16_t *board;       /* [n_envs][H][W]  SafeLifeGame.board */
-    uint16_t *goals;       /* [n_envs][H][W]  SafeLifeGame.goals */
-    int32_t  *loc;         /* [n_envs][2] (row, col) of agent 0; row < 0: level has no agent */
-    uint64_t *rng;         /* [n_envs][4] PCG64 of the game (safelife_game.py:175-180) */
-    int32_t  *level_id;    /* [n_envs] index into the pool */
-    int32_t  *num_steps;   /* [n_envs] GameState.num_steps */
-    int32_t  *old_value;   /* [n_envs] SafeLifeEnv._old_game_value */
-    int32_t  *ep_length;   /* [n_envs] SafeLifeEnv.episode_length */
-    float    *ep_reward;   /* [n_envs] SafeLifeEnv.episode_reward */
-    uint8_t  *active;      /* [n_envs] SafeLifeEnv._is_active */
-    uint8_t  *static_goals;/* [n_envs] 0 = unknown (None), 1 = static, 2 = dynamic
-                              (GameWithGoals._static_goals, safelife_game.py:753-761) */
+    uint16_t   *board;     /* [n_envs][H][W]  SafeLifeGame.board */
+    uint16_t   *goals;     /* [n_envs][H][W]  SafeLifeGame.goals */
+    SlEnvState *state;     /* [n_envs] */
     /* per-step outputs */
     float    *reward;      /* [n_envs] float32 reward (safelife_env.py:157,172) */
     uint8_t  *done;        /* [n_envs] */
@@ -147,10 +166,9 @@ typedef struct SlEnvBatch {
     const int32_t  *pool_table;       /* [n_levels][72] points_table[0] (safelife_game.py:595-605) */
     const int32_t  *pool_exits;       /* [n_levels][max_exits] flat indices of exit cells, -1 padded,
                                          raster order (GameState.exit_locs, safelife_game.py:533-535) */
-    const int32_t  *pool_init_points; /* [n_levels] sum(points_table * initial_counts) (:689-694) */
-    const int32_t  *pool_required;    /* [n_levels] required_points() (:711-714) */
-    const uint64_t *pool_spawn_thr;   /* [n_levels] ceil((double)(float)spawn_prob * 2^53): a draw
-                                         (u64 >> 11) spawns iff it is below this */
+    const int32_t  *pool_init_points; /* [n_levels] */
+    const int32_t  *pool_required;    /* [n_levels] */
+    const uint64_t *pool_spawn_thr;   /* [n_levels] */
 } SlEnvBatch;
 
 /* One SafeLifeEnv.step for every env (safelife_env.py:148-201, single_agent):

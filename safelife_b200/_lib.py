@@ -59,11 +59,22 @@ class SlEnvBatch(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("n_envs", "H", "W", "max_exits", "time_limit", "n_levels", "level_stride")] + \
                [(n, ctypes.c_void_p) for n in (
-                   "board", "goals", "loc", "rng", "level_id", "num_steps", "old_value",
-                   "ep_length", "ep_reward", "active", "static_goals",
-                   "reward", "done", "success", "times_up",
+                   "board", "goals", "state", "reward", "done", "success", "times_up",
                    "pool_board", "pool_goals", "pool_loc", "pool_table", "pool_exits",
                    "pool_init_points", "pool_required", "pool_spawn_thr")]
+
+
+# numpy mirror of struct SlEnvState (96 bytes per env)
+import numpy as _np  # noqa: E402
+
+ENV_STATE_DTYPE = _np.dtype([
+    ("rng", "<u8", 4), ("loc", "<i4", 2), ("level_id", "<i4"), ("num_steps", "<i4"),
+    ("old_value", "<i4"), ("ep_length", "<i4"), ("ep_reward", "<f4"), ("active", "u1"),
+    ("static_goals", "u1"), ("empty_points", "u1"), ("reserved0", "u1"), ("spawn_thr", "<u8"),
+    ("init_points", "<i4"), ("required", "<i4"), ("count_points", "<i4"), ("reserved1", "<i4", 3),
+])
+assert ENV_STATE_DTYPE.itemsize == 96
+ENV_STATE_WORDS = 24   # int32 words per record
 
 
 # name -> argtypes, exactly the prototypes of include/safelife_b200.h

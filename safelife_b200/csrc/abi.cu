@@ -107,7 +107,7 @@ int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int 
     if (n_steps < 1) return fail(SL_ERR_ARG, "n_steps must be >= 1");
     if (n == 0) return SL_OK;
     if (counts == nullptr && out == nullptr) return fail(SL_ERR_ARG, "null output pointer");
-    if (sl::warp_kernel_supports(H, W)) {
+    if (sl::warp_advance_supports(H, W)) {
         sl::launch_advance_warp(in, out, counts, n, H, W, spawn_threshold(spawn_prob), n_steps,
                                 rng, st);
         return launch_status("k_advance_warp");
@@ -337,9 +337,10 @@ static int check_batch(const SlEnvBatch *b) {
     int rc = check_board_args(b->board, b->n_envs, b->H, b->W);
     if (rc) return rc;
     if (b->n_levels < 1 || b->max_exits < 0) return fail(SL_ERR_ARG, "bad level pool sizes");
+    static_assert(sizeof(SlEnvState) == 96, "SlEnvState must stay 96 bytes");
+    if (((uintptr_t)b->state & 15) != 0) return fail(SL_ERR_ARG, "state must be 16-byte aligned");
     if (b->n_envs > 0 &&
-        (!b->goals || !b->loc || !b->rng || !b->level_id || !b->num_steps || !b->old_value ||
-         !b->ep_length || !b->ep_reward || !b->active || !b->static_goals || !b->reward ||
+        (!b->goals || !b->state || !b->reward ||
          !b->done || !b->success || !b->times_up || !b->pool_board || !b->pool_goals ||
          !b->pool_loc || !b->pool_table || !b->pool_init_points || !b->pool_required ||
          !b->pool_spawn_thr || (b->max_exits > 0 && !b->pool_exits)))

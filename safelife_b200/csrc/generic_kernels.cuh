@@ -257,16 +257,25 @@ __global__ void k_wrapped_label(int32_t *__restrict__ data, int32_t *__restrict_
     num_labels[b] = label;
 }
 
+// Points contribution of one cell (alive_counts bin x points table).
+__device__ inline int cell_points(uint32_t b, uint32_t g, const int32_t *__restrict__ table) {
+    int bin = count_bin(b, g);
+    return bin < 0 ? 0 : __ldg(table + bin);
+}
+
 // ------------------------------------------------------------------------
 // Exit / points logic shared by step and reset (single thread per env).
 // GameWithGoals.can_exit + update_exit_colors (safelife_game.py:537-552,
 // 716-719) on the board in `bd` (shared or global); returns current_points
-// (:684-687) AFTER the update.  count_points = sum(table * alive_counts).
+// (:684-687) AFTER the update.  count_points = sum(table * alive_counts) of
+// the board as it is on entry; *delta_mem is what the exit-cell overwrite adds
+// to that sum (0 unless something other than an exit sits on an exit cell).
 // ------------------------------------------------------------------------
 template <typename T>
-__device__ inline int exit_update(T *bd, int W, int row, int col, int count_points,
+__device__ inline int exit_update(T *bd, const T *gl, int W, int row, int col, int count_points,
                                   int init_points, int required, const int32_t *exits,
-                                  int max_exits, bool *agent_alive, bool *exited) {
+                                  int max_exits, const int32_t *__restrict__ table,
+                                  bool *agent_alive, bool *exited, int *delta_mem) {
     bool can_exit = false;
     int idx = -1;
     if (row >= 0) {
@@ -277,11 +286,18 @@ __device__ inline int exit_update(T *bd, int W, int row, int col, int count_poin
         can_exit = (a & AGENT) && earned >= required;
         bd[idx] = (T)((a & ~(uint32_t)EXIT) | (can_exit ? (uint32_t)EXIT : 0u));
     }
-    T exit_type = (T)(LEVEL_EXIT | (can_exit ? (uint32_t)COLOR_R : 0u));
+    const uint32_t exit_type = LEVEL_EXIT | (can_exit ? (uint32_t)COLOR_R : 0u);
+    int delta = 0;
     for (int k = 0; k < max_exits; k++) {
         int e = exits[k];
-        if (e >= 0) bd[e] = exit_type;
+        if (e < 0) continue;
+        uint32_t old = bd[e];
+        if (old != exit_type) {
+            if ((old & ~(uint32_t)COLORS) != LEVEL_EXIT) delta -= cell_points(old, gl[e], table);
+            bd[e] = (T)exit_type;
+        }
     }
+    *delta_mem = delta;
     *agent_alive = false;
     *exited = false;
     if (idx < 0) return count_points;
@@ -289,6 +305,38 @@ __device__ inline int exit_update(T *bd, int W, int row, int col, int count_poin
     *agent_alive = (a & AGENT) != 0;
     *exited = (a & (AGENT | EXIT)) == EXIT;
     return count_points + (*exited ? 1 : 0);
+}
+
+// Scalar tail of SafeLifeEnv.step (safelife_env.py:155-175) for one env.
+__device__ inline void finish_step(const SlEnvBatch &B, int e, SlEnvState &st, int row, int col,
+                                   int value, bool agent_alive, bool exited, int static_goals,
+                                   int count_points_mem) {
+    int steps = st.num_steps + 1;
+    bool times_up = steps >= B.time_limit;
+    bool active = st.active != 0;
+    float reward;
+    bool done, success;
+    if (row >= 0) {
+        reward = (float)((value - st.old_value) * (active ? 1 : 0));
+        success = exited;
+        done = !agent_alive || times_up;
+    } else {   // no agent: safelife_env.py:163-166
+        reward = 0.f; done = true; success = false;
+    }
+    st.num_steps = steps;
+    st.old_value = value;
+    // first step of an episode: totals restart (see SL_RESET_KEEP_STATS)
+    st.ep_reward = (steps == 1 ? 0.f : st.ep_reward) + reward;
+    st.ep_length = (steps == 1 ? 0 : st.ep_length) + (active ? 1 : 0);
+    st.active = (active && !done) ? 1 : 0;
+    st.static_goals = (uint8_t)static_goals;
+    st.loc_row = row;
+    st.loc_col = col;
+    st.count_points = count_points_mem;
+    B.reward[e] = reward;
+    B.done[e] = done;
+    B.success[e] = success;
+    B.times_up[e] = times_up;
 }
 
 // sum(table * alive_counts) over a board/goals pair by the whole block.
@@ -311,13 +359,14 @@ k_env_step_generic(SlEnvBatch B, const uint8_t *__restrict__ actions) {
     for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
         uint16_t *board = B.board + (size_t)e * cells;
         uint16_t *goals = B.goals + (size_t)e * cells;
-        const int lvl = B.level_id[e];
-        const uint64_t thr = B.pool_spawn_thr[lvl];
+        SlEnvState *stp = B.state + e;
+        const int lvl = stp->level_id;
+        const uint64_t thr = stp->spawn_thr;
         for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.a[i] = board[i];
-        if (threadIdx.x < 4) sm.rng[threadIdx.x] = B.rng[4 * (size_t)e + threadIdx.x];
+        if (threadIdx.x < 4) sm.rng[threadIdx.x] = stp->rng[threadIdx.x];
         __syncthreads();
         if (threadIdx.x == 0) {
-            int row = B.loc[2 * e], col = B.loc[2 * e + 1];
+            int row = stp->loc_row, col = stp->loc_col;
             if (row >= 0) agent_action(sm.a, H, W, row, col, (int)actions[e]);
             sm.misc[0] = row;
             sm.misc[1] = col;
@@ -326,7 +375,7 @@ k_env_step_generic(SlEnvBatch B, const uint8_t *__restrict__ actions) {
         block_advance(sm.a, sm.b, H, W, thr, sm.rng, sm.scratch);   // board: a -> b
         // goals (safelife_game.py:753-761): advanced from the same stream
         // after the board unless known static.
-        int sg = B.static_goals[e];
+        int sg = stp->static_goals;
         for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.a[i] = goals[i];
         __syncthreads();
         const uint16_t *gl = sm.a;
@@ -342,40 +391,20 @@ k_env_step_generic(SlEnvBatch B, const uint8_t *__restrict__ actions) {
             for (int i = threadIdx.x; i < cells; i += blockDim.x) goals[i] = sm.c[i];
             gl = sm.c;
         }
-        int pts = block_points(sm.b, gl, cells, B.pool_table + (size_t)lvl * 72, sm.scratch);
+        const int32_t *table = B.pool_table + (size_t)lvl * 72;
+        int pts = block_points(sm.b, gl, cells, table, sm.scratch);
         if (threadIdx.x == 0) {
             bool agent_alive, exited;
-            int row = sm.misc[0], col = sm.misc[1];
-            int value = exit_update(sm.b, W, row, col, pts, B.pool_init_points[lvl],
-                                    B.pool_required[lvl], B.pool_exits + (size_t)lvl * B.max_exits,
-                                    B.max_exits, &agent_alive, &exited);
-            int steps = B.num_steps[e] + 1;
-            bool times_up = steps >= B.time_limit;
-            bool active = B.active[e] != 0;
-            float reward;
-            bool done, success;
-            if (row >= 0) {
-                reward = (float)((value - B.old_value[e]) * (active ? 1 : 0));
-                success = exited;
-                done = !agent_alive || times_up;
-            } else {
-                reward = 0.f; done = true; success = false;
-            }
-            B.num_steps[e] = steps;
-            B.old_value[e] = value;
-            // first step of an episode: totals restart (see SL_RESET_KEEP_STATS)
-            B.ep_reward[e] = (steps == 1 ? 0.f : B.ep_reward[e]) + reward;
-            B.ep_length[e] = (steps == 1 ? 0 : B.ep_length[e]) + (active ? 1 : 0);
-            B.active[e] = (active && !done) ? 1 : 0;
-            B.static_goals[e] = (uint8_t)sg;
-            B.reward[e] = reward;
-            B.done[e] = done;
-            B.success[e] = success;
-            B.times_up[e] = times_up;
-            B.loc[2 * e] = row;
-            B.loc[2 * e + 1] = col;
+            int row = sm.misc[0], col = sm.misc[1], delta;
+            SlEnvState st = *stp;
+            int value = exit_update(sm.b, gl, W, row, col, pts, st.init_points, st.required,
+                                    B.pool_exits + (size_t)lvl * B.max_exits, B.max_exits, table,
+                                    &agent_alive, &exited, &delta);
+            st.rng[0] = sm.rng[0];
+            st.rng[1] = sm.rng[1];
+            finish_step(B, e, st, row, col, value, agent_alive, exited, sg, pts + delta);
+            *stp = st;
         }
-        if (threadIdx.x < 2) B.rng[4 * (size_t)e + threadIdx.x] = sm.rng[threadIdx.x];
         __syncthreads();
         for (int i = threadIdx.x; i < cells; i += blockDim.x) board[i] = sm.b[i];
         __syncthreads();
@@ -391,7 +420,8 @@ k_env_reset(SlEnvBatch B, const uint8_t *__restrict__ mask, const int32_t *__res
     GenericSmem sm(smem_raw, cells);
     for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
         if (mask != nullptr && !mask[e]) continue;
-        int lvl = new_level != nullptr ? new_level[e] : B.level_id[e];
+        SlEnvState *stp = B.state + e;
+        int lvl = new_level != nullptr ? new_level[e] : stp->level_id;
         if (new_level == nullptr && (flags & SL_RESET_NEXT_LEVEL))
             lvl = (int)(((long long)lvl + B.level_stride) % B.n_levels);
         const uint16_t *pb = B.pool_board + (size_t)lvl * cells;
@@ -405,24 +435,34 @@ k_env_reset(SlEnvBatch B, const uint8_t *__restrict__ mask, const int32_t *__res
             goals[i] = g;
         }
         __syncthreads();
-        int pts = block_points(sm.a, sm.b, cells, B.pool_table + (size_t)lvl * 72, sm.scratch);
+        const int32_t *table = B.pool_table + (size_t)lvl * 72;
+        int pts = block_points(sm.a, sm.b, cells, table, sm.scratch);
         if (threadIdx.x == 0) {
             bool agent_alive, exited;
-            int row = B.pool_loc[2 * lvl], col = B.pool_loc[2 * lvl + 1];
-            int value = exit_update(sm.a, W, row, col, pts, B.pool_init_points[lvl],
-                                    B.pool_required[lvl], B.pool_exits + (size_t)lvl * B.max_exits,
-                                    B.max_exits, &agent_alive, &exited);
-            B.level_id[e] = lvl;
-            B.loc[2 * e] = row;
-            B.loc[2 * e + 1] = col;
-            B.num_steps[e] = 0;
-            B.old_value[e] = value;
+            int row = B.pool_loc[2 * lvl], col = B.pool_loc[2 * lvl + 1], delta;
+            SlEnvState st = *stp;
+            st.init_points = B.pool_init_points[lvl];
+            st.required = B.pool_required[lvl];
+            st.spawn_thr = B.pool_spawn_thr[lvl];
+            bool empty = false;
+            for (int g = 0; g < 8; g++) empty |= table[g * 9 + 8] != 0;
+            st.empty_points = empty;
+            int value = exit_update(sm.a, sm.b, W, row, col, pts, st.init_points, st.required,
+                                    B.pool_exits + (size_t)lvl * B.max_exits, B.max_exits, table,
+                                    &agent_alive, &exited, &delta);
+            st.level_id = lvl;
+            st.loc_row = row;
+            st.loc_col = col;
+            st.num_steps = 0;
+            st.old_value = value;
+            st.count_points = pts + delta;
             if (!(flags & SL_RESET_KEEP_STATS)) {
-                B.ep_length[e] = 0;
-                B.ep_reward[e] = 0.f;
+                st.ep_length = 0;
+                st.ep_reward = 0.f;
             }
-            B.active[e] = 1;
-            B.static_goals[e] = 0;
+            st.active = 1;
+            st.static_goals = 0;
+            *stp = st;
         }
         __syncthreads();
         for (int i = threadIdx.x; i < cells; i += blockDim.x) board[i] = sm.a[i];
@@ -441,7 +481,7 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
     for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
         const uint16_t *board = B.board + (size_t)e * cells;
         const uint16_t *goals = B.goals + (size_t)e * cells;
-        int y0 = B.loc[2 * e], x0 = B.loc[2 * e + 1];
+        int y0 = B.state[e].loc_row, x0 = B.state[e].loc_col;
         if (y0 < 0) { y0 = 0; x0 = 0; }
         auto packed = [&](int idx) -> uint32_t {
             uint32_t g = goals[idx] & COLORS;
@@ -456,7 +496,7 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const int32_t *exits = B.pool_exits + (size_t)B.level_id[e] * B.max_exits;
+            const int32_t *exits = B.pool_exits + (size_t)B.state[e].level_id * B.max_exits;
             for (int k = 0; k < B.max_exits; k++) {
                 int idx = exits[k];
                 if (idx < 0) continue;
@@ -492,7 +532,7 @@ k_side_effect_cells(SlEnvBatch B, const uint16_t *__restrict__ baseline, int32_t
     const uint32_t keep = 0xffffu & ~(AGENT | DESTRUCTIBLE | FROZEN | PRESERVING | INHIBITING);
     for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
         const uint16_t *bd = B.board + (size_t)e * cells, *bl = baseline + (size_t)e * cells;
-        const int32_t *exits = B.pool_exits + (size_t)B.level_id[e] * B.max_exits;
+        const int32_t *exits = B.pool_exits + (size_t)B.state[e].level_id * B.max_exits;
         int s = 0;
         for (int i = threadIdx.x; i < cells; i += blockDim.x) {
             bool is_exit = false;

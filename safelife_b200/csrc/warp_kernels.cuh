@@ -1,20 +1,498 @@
 // warp_kernels.cuh -- warp-per-env bit-plane kernels (boards up to 32x32).
+//
+// The fast path for the BASELINE shapes (25x25, 26x26).  One warp owns one
+// env; lane r owns board row r.  A CTA of 8 warps stages the 8 consecutive env
+// slabs it owns ([8][H][W] uint16, 16-byte aligned as a group for any H, W)
+// from HBM into shared memory with 128-bit loads, and writes them back the
+// same way.  Inside the warp:
+//
+//   1. lane r reads its row (W uint16) and transposes it in registers into 16
+//      bit-plane words (bit j of plane p = bit p of cell j) with a 4-stage
+//      butterfly: one byte-permute stage and three masked shift stages;
+//   2. the 3x3 toroidal neighbourhood aggregate of advance_board.c:34-125 is
+//      evaluated on whole rows at once with bitwise adders: horizontal
+//      neighbours are 1-bit rotations of the row word, vertical neighbours come
+//      from lanes r-1 / r+1 by warp shuffle;
+//   3. the spawn draws of the reference (one PCG64 double per qualifying cell
+//      in raster order, advance_board.c:115) are produced 32 at a time by
+//      leapfrogging the LCG across lanes and handed to the rows by prefix sum;
+//   4. only cells that changed are written back into the uint16 slab.
+//
+// No tensor cores: the path is integer / bitwise and bound by HBM and the
+// integer pipes.
 #pragma once
 #include <cuda_runtime.h>
 #include "cells.cuh"
+#include "generic_kernels.cuh"
 #include "../../include/safelife_b200.h"
 
 namespace sl {
 
 constexpr int WARP_MAX_DIM = 32;
+constexpr int WARP_ENVS_PER_CTA = 8;
+constexpr unsigned FULL = 0xffffffffu;
 
 inline bool warp_kernel_supports(int H, int W) {
+    return H >= 3 && W >= 3 && H <= WARP_MAX_DIM && W <= WARP_MAX_DIM;
+}
+
+// Per-lane leapfrog constants (A^(l+1), G_(l+1)); global memory so that each
+// lane reads its own entry without constant-cache serialisation.
+__device__ const uint64_t d_lane_a[32][2] = SL_PCG_LANE_A;
+__device__ const uint64_t d_lane_g[32][2] = SL_PCG_LANE_G;
+
+// Bit planes of one board row that the physics reads or rewrites.
+struct RowPlanes {
+    uint32_t A, D, F, P, I, S, E, R, G, B;   // stencil inputs
+    uint32_t PU, PL, AG;                      // pushable, pullable, agent
+};
+
+// 16 cells-pairs words -> 16 plane words.  x[k] = cell(k) | cell(k+16) << 16.
+__device__ __forceinline__ void transpose16(uint32_t (&x)[16]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {            // bytes: cell bit 3 <-> plane bit 3
+        uint32_t a = x[k], b = x[k + 8];
+        x[k] = __byte_perm(a, b, 0x6240);
+        x[k + 8] = __byte_perm(a, b, 0x7351);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {           // nibbles
+        if (k & 4) continue;
+        uint32_t a = x[k], b = x[k + 4];
+        x[k] = (a & 0x0f0f0f0fu) | ((b << 4) & 0xf0f0f0f0u);
+        x[k + 4] = ((a >> 4) & 0x0f0f0f0fu) | (b & 0xf0f0f0f0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) {           // bit pairs
+        if (k & 2) continue;
+        uint32_t a = x[k], b = x[k + 2];
+        x[k] = (a & 0x33333333u) | ((b << 2) & 0xccccccccu);
+        x[k + 2] = ((a >> 2) & 0x33333333u) | (b & 0xccccccccu);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k += 2) {        // bits
+        uint32_t a = x[k], b = x[k + 1];
+        x[k] = (a & 0x55555555u) | ((b << 1) & 0xaaaaaaaau);
+        x[k + 1] = ((a >> 1) & 0x55555555u) | (b & 0xaaaaaaaau);
+    }
+}
+
+// Row r of a slab (shared memory) -> plane words.  Reads 32 cells starting at
+// the row (the slab is padded so that this never leaves shared memory) and
+// masks the planes to the W valid columns; lanes past the last row get zeros
+// through their empty wmask.
+__device__ __forceinline__ RowPlanes load_row_planes(const uint16_t *slab, int r, int W,
+                                                     uint32_t wmask) {
+    uint32_t x[16];
+    const uint16_t *row = slab + r * W;
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = __byte_perm(row[k], row[k + 16], 0x5410);
+    transpose16(x);
+    RowPlanes p;
+    p.A = x[0] & wmask; p.AG = x[1] & wmask; p.PU = x[2] & wmask; p.D = x[3] & wmask;
+    p.F = x[4] & wmask; p.P = x[5] & wmask; p.I = x[6] & wmask; p.S = x[7] & wmask;
+    p.E = x[8] & wmask; p.R = x[9] & wmask; p.G = x[10] & wmask; p.B = x[11] & wmask;
+    p.PL = x[15] & wmask;
+    return p;
+}
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    return (a & b) | (a & c) | (b & c);
+}
+
+// What one stencil step does to a row (before the spawn draws are resolved).
+struct RowDelta {
+    uint32_t die;      // alive cells that die
+    uint32_t born;     // dead cells that come alive through n == 3
+    uint32_t cand;     // dead cells that take a spawn draw
+    uint32_t tR, tG, tB;   // inherited colour bits of a new cell
+    uint32_t dn;       // births that are DESTRUCTIBLE
+};
+
+struct Torus {
+    int H, W, up, down;   // source lanes of the rows above / below
+    uint32_t wmask;
+    __device__ __forceinline__ uint32_t west(uint32_t x) const {   // bit j <- cell j-1
+        return ((x << 1) | (x >> (W - 1))) & wmask;
+    }
+    __device__ __forceinline__ uint32_t east(uint32_t x) const {   // bit j <- cell j+1
+        return ((x >> 1) | (x << (W - 1))) & wmask;
+    }
+    __device__ __forceinline__ uint32_t north(uint32_t x) const { return __shfl_sync(FULL, x, up); }
+    __device__ __forceinline__ uint32_t south(uint32_t x) const { return __shfl_sync(FULL, x, down); }
+};
+
+__device__ __forceinline__ Torus make_torus(int H, int W, int lane) {
+    Torus t;
+    t.H = H; t.W = W;
+    int r = lane < H ? lane : 0;
+    t.up = r == 0 ? H - 1 : r - 1;
+    t.down = r == H - 1 ? 0 : r + 1;
+    // lanes past the last row carry an empty mask so that they never create,
+    // kill or draw anything
+    t.wmask = lane < H ? (W == 32 ? FULL : ((1u << W) - 1u)) : 0u;
+    return t;
+}
+
+// "at least one" / "at least two" of a plane over the 3x3 neighbourhood.
+struct Any2 { uint32_t one, two; };
+
+__device__ __forceinline__ uint32_t any3x3(const Torus &t, uint32_t x) {
+    uint32_t h = x | t.west(x) | t.east(x);
+    return h | t.north(h) | t.south(h);
+}
+
+__device__ __forceinline__ uint32_t two3x3(const Torus &t, uint32_t x) {
+    uint32_t w = t.west(x), e = t.east(x);
+    uint32_t one = x | w | e, two = maj3(x, w, e);
+    uint32_t on = t.north(one), os = t.south(one);
+    return two | t.north(two) | t.south(two) | maj3(one, on, os);
+}
+
+// advance_board.c:34-125 on bit planes.
+__device__ __forceinline__ RowDelta stencil_row(const Torus &t, const RowPlanes &p) {
+    // n = alive cells in the 3x3 (centre included), as 4 bit planes
+    uint32_t w = t.west(p.A), e = t.east(p.A);
+    uint32_t s0 = p.A ^ w ^ e, s1 = maj3(p.A, w, e);
+    uint32_t s0n = t.north(s0), s0s = t.south(s0), s1n = t.north(s1), s1s = t.south(s1);
+    uint32_t n0 = s0 ^ s0n ^ s0s, c0 = maj3(s0, s0n, s0s);
+    uint32_t a = s1 ^ s1n ^ s1s, b = maj3(s1, s1n, s1s);
+    uint32_t n1 = a ^ c0, c1 = a & c0;
+    uint32_t n2 = b ^ c1, n3 = b & c1;
+    uint32_t is3 = n0 & n1 & ~n2 & ~n3;
+    uint32_t is4 = ~n0 & ~n1 & n2 & ~n3;
+
+    uint32_t any_p = any3x3(t, p.P), any_i = any3x3(t, p.I), any_s = any3x3(t, p.S);
+    RowDelta d;
+    d.die = p.A & ~(p.F | any_p | is3 | is4);
+    uint32_t open = ~p.A & ~p.F & ~any_i & t.wmask;   // dead, not frozen, not inhibited
+    d.born = open & is3;
+    d.cand = open & ~is3 & any_s;
+    // colours / destructibility only matter where something may be created
+    if (__any_sync(FULL, (d.born | d.cand) != 0)) {
+        d.tR = two3x3(t, p.A & p.R) | any3x3(t, p.S & p.R);
+        d.tG = two3x3(t, p.A & p.G) | any3x3(t, p.S & p.G);
+        d.tB = two3x3(t, p.A & p.B) | any3x3(t, p.S & p.B);
+        d.dn = two3x3(t, p.A & (p.D | p.E));
+    } else {
+        d.tR = d.tG = d.tB = d.dn = 0;
+    }
+    return d;
+}
+
+// Resolve the spawn draws of one board: lane r holds its candidate mask; on
+// return `spawned` is the subset whose draw was below thr and the (uniform)
+// state has advanced by the total number of candidates.  Raster order = row
+// order, then bit order within the row.
+__device__ __forceinline__ uint32_t warp_spawn_draws(u128 &state, const u128 &inc, uint64_t thr,
+                                                     uint32_t cand, int lane) {
+    if (!__any_sync(FULL, cand != 0)) return 0u;
+    int cnt = __popc(cand), incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    int k = incl - cnt;                      // index of this lane's first draw
+    const u128 la = {__ldg(&d_lane_a[lane][0]), __ldg(&d_lane_a[lane][1])};
+    const u128 lg = {__ldg(&d_lane_g[lane][0]), __ldg(&d_lane_g[lane][1])};
+    const u128 ginc = mul128(lg, inc);
+    uint32_t spawned = 0, todo = cand;
+    for (int base = 0; base < total; base += 32) {
+        u128 s = add128(mul128(la, state), ginc);          // state after lane+1 more steps
+        uint32_t ok = __ballot_sync(FULL, (pcg_output(s) >> 11) < thr);
+        while (todo != 0 && k < base + 32) {
+            int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            spawned |= ((ok >> (k - base)) & 1u) << j;
+            k++;
+        }
+        int last = min(31, total - base - 1);
+        state.hi = __shfl_sync(FULL, s.hi, last);
+        state.lo = __shfl_sync(FULL, s.lo, last);
+    }
+    return spawned;
+}
+
+// Apply a resolved step to the planes and write the changed cells of this row
+// back into the uint16 slab.  Returns the mask of changed cells; when `table`
+// is given, *delta accumulates what the changes add to sum(table * alive_counts)
+// (goal colours read from the goals slab).
+__device__ __forceinline__ uint32_t apply_row(RowPlanes &p, const RowDelta &d, uint32_t spawned,
+                                              uint16_t *slab, int r, int W,
+                                              const uint16_t *goals = nullptr,
+                                              const int32_t *__restrict__ table = nullptr,
+                                              int *delta = nullptr) {
+    const uint32_t fresh = d.born | spawned;
+    const uint32_t changed = d.die | fresh;
+    if (changed == 0) return 0u;
+    const uint32_t keep = ~changed;
+    p.A = (p.A & keep) | fresh;
+    p.D = (p.D & keep) | (d.dn & d.born) | spawned;
+    p.R = (p.R & keep) | (d.tR & fresh);
+    p.G = (p.G & keep) | (d.tG & fresh);
+    p.B = (p.B & keep) | (d.tB & fresh);
+    p.P &= keep; p.I &= keep; p.S &= keep; p.E &= keep;
+    p.PU &= keep; p.PL &= keep; p.AG &= keep;   // (F is already 0 on every changed cell)
+    uint16_t *row = slab + r * W;
+    uint32_t m = changed;
+    while (m != 0) {
+        int j = __ffs(m) - 1;
+        m &= m - 1;
+        uint32_t v = ((p.A >> j) & 1u) | (((p.D >> j) & 1u) << 3) | (((p.R >> j) & 1u) << 9) |
+                     (((p.G >> j) & 1u) << 10) | (((p.B >> j) & 1u) << 11);
+        if (table != nullptr) {
+            uint32_t g = goals[r * W + j];
+            *delta += cell_points(v, g, table) - cell_points(row[j], g, table);
+        }
+        row[j] = (uint16_t)v;
+    }
+    return changed;
+}
+
+// sum(table * alive_counts) of a board given its planes and the goals slab
+// (advance_board.c:192-207 + safelife_game.py:684-687), reduced over the warp.
+__device__ __forceinline__ int warp_points(const RowPlanes &p, const uint16_t *goals, int r, int W,
+                                           uint32_t wmask, const int32_t *__restrict__ table,
+                                           bool empty_column) {
+    const uint32_t countable = ((p.D | p.PU | p.PL) | ~p.F) & wmask;
+    const uint16_t *grow = goals + r * W;
+    int pts = 0;
+    uint32_t m = p.A & countable;
+    while (m != 0) {
+        int j = __ffs(m) - 1;
+        m &= m - 1;
+        int col = ((p.R >> j) & 1) | (((p.G >> j) & 1) << 1) | (((p.B >> j) & 1) << 2);
+        int g = (grow[j] >> COLOR_SHIFT) & 7;
+        pts += __ldg(table + g * 9 + col);
+    }
+    if (empty_column) {
+        m = ~p.A & countable;
+        while (m != 0) {
+            int j = __ffs(m) - 1;
+            m &= m - 1;
+            pts += __ldg(table + ((grow[j] >> COLOR_SHIFT) & 7) * 9 + 8);
+        }
+    }
+    return __reduce_add_sync(FULL, pts);
+}
+
+// Cooperative copy between a CTA's group of env slabs in global memory and
+// shared memory (fallback when the group is not 16-byte sized / aligned).
+__device__ __forceinline__ void copy_slabs(void *dst, const void *src, int bytes) {
+    const uint16_t *s2 = (const uint16_t *)src;
+    uint16_t *d2 = (uint16_t *)dst;
+    for (int i = threadIdx.x; i < (bytes >> 1); i += blockDim.x) d2[i] = s2[i];
+}
+
+// ---- bulk asynchronous copies (TMA, 1-D) and their mbarrier -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; "
+            "selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes,
+                                          uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_store(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem),
+                 "r"(smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+constexpr int WARP_SMEM_HEADER = 16;                       // mbarrier
+constexpr int WARP_SMEM_PAD = 2 * (32 * 32 + 32);          // row over-read of the last warp
+
+__host__ __device__ inline int warp_slab_stride(int cells) {
+    return (WARP_ENVS_PER_CTA * cells * 2 + 15) & ~15;
+}
+
+// SafeLifeEnv.step, one warp per env (safelife_env.py:148-201).
+__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32)
+k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = B.H, W = B.W, cells = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int e0 = blockIdx.x * WARP_ENVS_PER_CTA;
+    const int nenv = min(WARP_ENVS_PER_CTA, B.n_envs - e0);
+    const int group_bytes = nenv * cells * 2;
+    uint64_t *bar = (uint64_t *)smem_raw;
+    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_HEADER);
+    uint16_t *sgoals = (uint16_t *)(smem_raw + WARP_SMEM_HEADER + warp_slab_stride(cells));
+    uint16_t *gboard = B.board + (size_t)e0 * cells;
+    uint16_t *ggoals = B.goals + (size_t)e0 * cells;
+    const bool bulk = bulk_ok && (group_bytes & 15) == 0;
+
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, 2u * group_bytes);
+            bulk_load(sboard, gboard, group_bytes, bar);
+            bulk_load(sgoals, ggoals, group_bytes, bar);
+        }
+    } else {
+        copy_slabs(sboard, gboard, group_bytes);
+        copy_slabs(sgoals, ggoals, group_bytes);
+    }
+    // per-env record: every lane reads all of it (same address -> one transaction
+    // per 16-byte load) while the slabs are in flight
+    const int e = e0 + warp;
+    const bool have_env = warp < nenv;
+    SlEnvState st;
+    int action = 0;
+    if (have_env) {
+        const uint4 *src = (const uint4 *)(B.state + e);
+        uint4 *dst = (uint4 *)&st;
+#pragma unroll
+        for (int i = 0; i < 6; i++) dst[i] = src[i];
+        action = actions[e];
+    }
+    __syncthreads();                      // mbarrier init / fallback copy visible
+    if (bulk) mbar_wait(bar, 0);
+
+    bool goals_dirty = false;
+    if (have_env) {
+        uint16_t *board = sboard + warp * cells;
+        uint16_t *goals = sgoals + warp * cells;
+        const int lvl = st.level_id;
+        const uint64_t thr = st.spawn_thr;
+        const int32_t *table = B.pool_table + (size_t)lvl * 72;
+        u128 state = {st.rng[0], st.rng[1]};
+        const u128 inc = {st.rng[2], st.rng[3]};
+        int row = st.loc_row, col = st.loc_col;
+        int sg = st.static_goals;
+        int delta = 0;                    // change of sum(table * alive_counts), this lane
+
+        // ---- execute_actions (advance_board.c:217-300): lane 0 acts; lanes 0-3
+        //      account for the (at most four) cells it can touch
+        if (row >= 0 && action != 0) {
+            const int dir = (action - 1) & 3;
+            const int dy = (dir == 0) ? -1 : (dir == 2 ? 1 : 0);
+            const int dx = (dir == 1) ? 1 : (dir == 3 ? -1 : 0);
+            const int y1 = wrap_idx(row + dy, H), x1 = wrap_idx(col + dx, W);
+            int idx = row * W + col;                                           // lane 0: agent
+            if (lane == 1) idx = y1 * W + x1;                                  // ahead
+            if (lane == 2) idx = wrap_idx(y1 + dy, H) * W + wrap_idx(x1 + dx, W);   // two ahead
+            if (lane == 3) idx = wrap_idx(row - dy, H) * W + wrap_idx(col - dx, W); // behind
+            const int idx2 = __shfl_sync(FULL, idx, 2);
+            uint32_t before = lane < 4 ? board[idx] : 0u;
+            __syncwarp();
+            if (lane == 0) agent_action(board, H, W, row, col, action);
+            __syncwarp();
+            row = __shfl_sync(FULL, row, 0);
+            col = __shfl_sync(FULL, col, 0);
+            if (lane < 4 && !(lane == 3 && idx == idx2)) {
+                uint32_t after = board[idx];
+                if (after != before) {
+                    uint32_t g = goals[idx];
+                    delta += cell_points(after, g, table) - cell_points(before, g, table);
+                }
+            }
+        }
+
+        // ---- advance_board on bit planes
+        const Torus t = make_torus(H, W, lane);
+        RowPlanes p = load_row_planes(board, lane, W, t.wmask);
+        RowDelta d = stencil_row(t, p);
+        uint32_t spawned = warp_spawn_draws(state, inc, thr, d.cand, lane);
+        apply_row(p, d, spawned, board, lane, W, goals, table, &delta);
+
+        int pts;
+        if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
+            RowPlanes gp = load_row_planes(goals, lane, W, t.wmask);
+            RowDelta gd = stencil_row(t, gp);
+            uint32_t gspawned = warp_spawn_draws(state, inc, thr, gd.cand, lane);
+            uint32_t gchanged = apply_row(gp, gd, gspawned, goals, lane, W);
+            if (sg == 0) sg = __any_sync(FULL, (gchanged | gp.S) != 0) ? 2 : 1;
+            goals_dirty = true;
+            __syncwarp();
+        }
+        if (sg == 1) {
+            pts = st.count_points + __reduce_add_sync(FULL, delta);
+        } else {
+            pts = warp_points(p, goals, lane, W, t.wmask, table, st.empty_points != 0);
+        }
+
+        if (lane == 0) {
+            bool agent_alive, exited;
+            int dmem;
+            int value = exit_update(board, goals, W, row, col, pts, st.init_points, st.required,
+                                    B.pool_exits + (size_t)lvl * B.max_exits, B.max_exits, table,
+                                    &agent_alive, &exited, &dmem);
+            const bool drew = state.hi != st.rng[0] || state.lo != st.rng[1];
+            st.rng[0] = state.hi;
+            st.rng[1] = state.lo;
+            finish_step(B, e, st, row, col, value, agent_alive, exited, sg, pts + dmem);
+            uint4 *dst = (uint4 *)(B.state + e);
+            const uint4 *src = (const uint4 *)&st;
+            if (drew) dst[0] = src[0];
+            dst[2] = src[2];
+            dst[3] = src[3];
+            dst[5] = src[5];
+        }
+    }
+    if (bulk) {
+        fence_async_smem();               // generic-proxy writes -> visible to the bulk engine
+        const int any_goals_dirty = __syncthreads_or(goals_dirty);
+        if (threadIdx.x == 0) {
+            bulk_store(gboard, sboard, group_bytes);
+            if (any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
+            bulk_commit_and_wait_read();
+        }
+    } else {
+        const int any_goals_dirty = __syncthreads_or(goals_dirty);
+        copy_slabs(gboard, sboard, group_bytes);
+        if (any_goals_dirty) copy_slabs(ggoals, sgoals, group_bytes);
+    }
+}
+
+inline size_t warp_step_smem_bytes(int cells) {
+    return WARP_SMEM_HEADER + 2 * (size_t)warp_slab_stride(cells) + WARP_SMEM_PAD;
+}
+
+inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, cudaStream_t st) {
+    const int cells = B.H * B.W;
+    const int grid = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
+    const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals) & 15) == 0;
+    k_env_step_warp<<<grid, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(B, actions, bulk_ok);
+}
+
+inline bool warp_advance_supports(int H, int W) {
     (void)H; (void)W;
-    return false;   // enabled once the bit-plane kernels land
+    return false;   // multi-step bit-plane kernel: see k_advance_warp (to come)
 }
 
 inline void launch_advance_warp(const uint16_t *, uint16_t *, int32_t *, int, int, int, uint64_t,
                                 int, uint64_t *, cudaStream_t) {}
-inline void launch_env_step_warp(const SlEnvBatch &, const uint8_t *, cudaStream_t) {}
 
 }  // namespace sl

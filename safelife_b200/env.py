@@ -68,6 +68,17 @@ def seed_rng_states(seed, n):
     return out
 
 
+class _TensorTable(dict):
+    """The env's device tensors by name; per-env scalars are views into `state`."""
+
+    def __init__(self, owned, views):
+        super().__init__(owned)
+        self.views = views
+
+    def __missing__(self, key):
+        return self.views[key]
+
+
 class GameView(object):
     """Host copy of one env with SafeLifeGame's attribute names (safelife_game.py:126-160)."""
 
@@ -123,17 +134,24 @@ class BatchedSafeLifeEnv(object):
                 "pool_spawn_thr": _as_i64(p.spawn_thr).to(dev),
             }
             z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)  # noqa: E731
+            # struct SlEnvState[N] as int32 words; the named entries below are views into it
+            state = z((N, _lib.ENV_STATE_WORDS), torch.int32)
+            flags = state[:, 15:16].view(torch.uint8)
             self._t = {
                 "board": z((N, H, W), torch.int16), "goals": z((N, H, W), torch.int16),
-                "loc": z((N, 2), torch.int32), "rng": z((N, 4), torch.int64),
-                "level_id": (torch.arange(N, dtype=torch.int64) % len(p)).to(torch.int32).to(dev),
-                "num_steps": z((N,), torch.int32), "old_value": z((N,), torch.int32),
-                "ep_length": z((N,), torch.int32), "ep_reward": z((N,), torch.float32),
-                "active": z((N,), torch.uint8), "static_goals": z((N,), torch.uint8),
+                "state": state,
                 "reward": z((N,), torch.float32), "done": z((N,), torch.uint8),
                 "success": z((N,), torch.uint8), "times_up": z((N,), torch.uint8),
             }
-            self._t["rng"].copy_(_as_i64(seed_rng_states(seed, N)))
+            self._views = {
+                "rng": state[:, 0:8].view(torch.int64), "loc": state[:, 8:10],
+                "level_id": state[:, 10], "num_steps": state[:, 11], "old_value": state[:, 12],
+                "ep_length": state[:, 13], "ep_reward": state[:, 14:15].view(torch.float32)[:, 0],
+                "active": flags[:, 0], "static_goals": flags[:, 1],
+                "count_points": state[:, 20],
+            }
+            self._views["level_id"].copy_((torch.arange(N, dtype=torch.int64) % len(p)).to(torch.int32))
+            self._views["rng"].copy_(_as_i64(seed_rng_states(seed, N)))
             if self.output_channels is None:
                 self._obs = z((N,) + self.view_shape, torch.int32)
                 self._channels = None
@@ -148,6 +166,8 @@ class BatchedSafeLifeEnv(object):
             **{k: t.data_ptr() for k, t in self._pool_t.items()})
         self._batch_ref = ctypes.byref(self._batch)
         self._has_reset = False
+        # `_t` also answers for the named views of the state record
+        self._t = _TensorTable(self._t, self._views)
 
     # ------------------------------------------------------------ tensors
     @property
@@ -162,12 +182,12 @@ class BatchedSafeLifeEnv(object):
     @property
     def agent_locs(self):
         """int32 [N,1,2] (row, col), as SafeLifeGame.agent_locs."""
-        return self._t["loc"].view(self.num_envs, 1, 2)
+        return self._t["loc"].reshape(self.num_envs, 1, 2)
 
     @property
     def rng_state(self):
         """uint64[N,4] PCG64 words as a numpy array (host copy)."""
-        return self._t["rng"].cpu().numpy().view(np.uint64)
+        return self._t["rng"].contiguous().cpu().numpy().view(np.uint64)
 
     def set_rng_state(self, states):
         self._t["rng"].copy_(_as_i64(states))
@@ -268,7 +288,7 @@ class BatchedSafeLifeEnv(object):
 
     def get_state(self):
         """All per-env tensors (clones), e.g. for checkpointing a rollout."""
-        return {k: v.clone() for k, v in self._t.items()}
+        return {k: v.clone() for k, v in dict.items(self._t)}
 
     def set_state(self, state):
         for k, v in state.items():

@@ -32,9 +32,12 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 
 def test_struct_layout_matches_header():
-    # 7 int32 + padding + 23 pointers
-    assert ctypes.sizeof(_lib.SlEnvBatch) == 32 + 23 * 8
+    # 7 int32 + padding + 15 pointers; SlEnvState is 96 bytes
+    assert ctypes.sizeof(_lib.SlEnvBatch) == 32 + 15 * 8
     assert _lib.SlEnvBatch.board.offset == 32
+    dt = _lib.ENV_STATE_DTYPE
+    assert dt.itemsize == 96 and dt.fields["loc"][1] == 32 and dt.fields["spawn_thr"][1] == 64
+    assert dt.fields["count_points"][1] == 80 and dt.fields["ep_reward"][1] == 56
 
 
 def test_argument_errors_without_gpu():
