@@ -254,34 +254,32 @@ def run_ours(args, levels):
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     lib, bref = env._lib, env._batch_ref
     from safelife_b200 import _lib
-    flags = _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS
     stream = env._stream()
-    done_ptr = env._t["done"].data_ptr()
+    # generic kernel: the auto-reset is a second (masked) launch; warp kernel: fused
+    fused = bool(lib.sl_warp_kernel_supported(H, W)) and args.kernel != 1
+    launches_per_step = 1 if fused else 2
 
-    def step_kernels(t, ev_mid=None):
-        _lib.check(lib.sl_env_step(bref, actions[t].data_ptr(), args.kernel, stream))
-        if ev_mid is not None:
-            ev_mid.record()
-        _lib.check(lib.sl_env_reset(bref, done_ptr, None, flags, stream))
+    def step_kernels(t):
+        _lib.check(lib.sl_env_step(bref, actions[t].data_ptr(), args.kernel,
+                                   _lib.SL_STEP_AUTO_RESET, stream))
 
     for t in range(Wm):
         step_kernels(t)
     barrier()
     # ---- value: device-timed, state resident in HBM, L2 flushed between steps ----
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     sampler = ClockSampler(local) if rank == 0 else None
     wall0 = time.perf_counter()
     for t in range(K):
         if flush is not None:
             flush.fill_(t & 0xFF)
         ev[t][0].record()
-        step_kernels(Wm + t, ev[t][1])
-        ev[t][2].record()
+        step_kernels(Wm + t)
+        ev[t][1].record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler else None
-    step_ms = sum(e[0].elapsed_time(e[1]) for e in ev)        # step kernel only
-    total_ms = sum(e[0].elapsed_time(e[2]) for e in ev)       # step + auto-reset
+    total_ms = sum(e[0].elapsed_time(e[1]) for e in ev)       # step incl. auto-reset
+    step_ms = total_ms
     static = env._t["static_goals"].cpu().numpy()
     dyn = int((static == 2).sum())
     bytes_per_launch = (n - dyn) * (6 * H * W + 64) + dyn * (8 * H * W + 64)
@@ -296,14 +294,14 @@ def run_ours(args, levels):
         if flush is not None:
             flush.fill_(t & 0xFF)
         e2e_ev[t][0].record()
-        env.step_physics(host_actions[t])                 # H2D inside
-        _lib.check(lib.sl_env_reset(bref, done_ptr, None, flags, stream))
+        env.step_physics(host_actions[t], auto_reset=True)   # H2D inside
         host_reward.copy_(env._t["reward"], non_blocking=True)
         host_done.copy_(env._t["done"], non_blocking=True)
         e2e_ev[t][1].record()
         e2e_ev[t][1].synchronize()                        # the host consumes the result
     barrier()
     e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_ev)
+    clocks = sampler.stop() if sampler else None
 
     times = torch.tensor([total_ms, step_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -329,9 +327,9 @@ def run_ours(args, levels):
             "clocks": clocks,
             "e2e": {"value": n * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
                     "h2d_bytes_per_step": n, "d2h_bytes_per_step": 5 * n,
-                    "api": "BatchedSafeLifeEnv.step_physics + auto-reset; pinned uint8 actions "
+                    "api": "BatchedSafeLifeEnv.step_physics(auto_reset=True); pinned uint8 actions "
                            "H2D, float32 reward + uint8 done D2H, host sync every step"},
-            "gpu_launches": 2 * K,
+            "gpu_launches": launches_per_step * K,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "kernel": "env step kernel",

@@ -134,7 +134,9 @@ typedef struct SlEnvState {
     int32_t  init_points;  /* sum(points_table * initial_counts) (safelife_game.py:689-694) */
     int32_t  required;     /* required_points() (:711-714) */
     int32_t  count_points; /* sum(points_table * alive_counts) of the board in memory */
-    int32_t  reserved1[3];
+    int32_t  n_exits;      /* number of exit cells of the level */
+    int32_t  exit0, exit1; /* the first two of them (flat indices, -1: none); levels with more
+                              keep the full list in pool_exits */
 } SlEnvState;
 
 /*
@@ -176,8 +178,15 @@ typedef struct SlEnvBatch {
  * update_exit_colors -> reward / done / episode counters.  actions is
  * uint8[n_envs] (device), values as the reference's Discrete(9).
  * kernel: 0 = pick automatically, 1 = generic CTA-per-env kernel,
- * 2 = warp-per-env bit-plane kernel (requires H, W <= 32). */
-int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, void *stream);
+ * 2 = warp-per-env bit-plane kernel (requires H, W <= 32).
+ * flags: SL_STEP_AUTO_RESET resets every env that finished in this step in
+ * the same call, exactly as sl_env_reset(batch, done, NULL,
+ * SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS) would (the batched form of
+ * BaseAlgo.act_on_envs resetting on done, training/base_algo.py:231-236);
+ * reward / done / success / times_up still describe the finished step. */
+#define SL_STEP_AUTO_RESET 1
+int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                void *stream);
 
 /* SafeLifeEnv.reset (safelife_env.py:203-218) for every env whose mask byte is
  * non-zero (mask NULL = all envs): copy a level from the pool, then

@@ -18,6 +18,7 @@ _SRC = os.path.join(_PKG, "csrc")
 
 SL_OK, SL_ERR_ARG, SL_ERR_CUDA, SL_ERR_NO_DEVICE = 0, 1, 2, 3
 SL_RESET_NEXT_LEVEL, SL_RESET_KEEP_STATS = 1, 2
+SL_STEP_AUTO_RESET = 1
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -71,7 +72,8 @@ ENV_STATE_DTYPE = _np.dtype([
     ("rng", "<u8", 4), ("loc", "<i4", 2), ("level_id", "<i4"), ("num_steps", "<i4"),
     ("old_value", "<i4"), ("ep_length", "<i4"), ("ep_reward", "<f4"), ("active", "u1"),
     ("static_goals", "u1"), ("empty_points", "u1"), ("reserved0", "u1"), ("spawn_thr", "<u8"),
-    ("init_points", "<i4"), ("required", "<i4"), ("count_points", "<i4"), ("reserved1", "<i4", 3),
+    ("init_points", "<i4"), ("required", "<i4"), ("count_points", "<i4"), ("n_exits", "<i4"),
+    ("exit0", "<i4"), ("exit1", "<i4"),
 ])
 assert ENV_STATE_DTYPE.itemsize == 96
 ENV_STATE_WORDS = 24   # int32 words per record
@@ -94,7 +96,7 @@ PROTOTYPES = {
     "sl_alive_counts_host": [_vp, _vp, _vp, _i, _i],
     "sl_execute_actions_host": [_vp, _vp, _vp, _i, _i, _i, _i, _i],
     "sl_wrapped_label_host": [_vp, _vp, _i, _i, _i],
-    "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _vp],
+    "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_reset": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _i, _vp],
     "sl_get_obs": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _i, _i, _vp],
     "sl_side_effect_cells": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _vp],

@@ -348,7 +348,8 @@ static int check_batch(const SlEnvBatch *b) {
     return SL_OK;
 }
 
-int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, void *stream) {
+int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                void *stream) {
     int rc = check_batch(batch);
     if (rc) return rc;
     if (batch->n_envs == 0) return SL_OK;
@@ -358,15 +359,18 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, voi
     bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
     if (kernel == 2 && !warp_ok)
         return fail(SL_ERR_ARG, "warp kernel needs H, W <= %d", sl::WARP_MAX_DIM);
+    if (flags & ~SL_STEP_AUTO_RESET) return fail(SL_ERR_ARG, "unknown step flags");
     if (kernel == 2 || (kernel == 0 && warp_ok)) {
-        sl::launch_env_step_warp(*batch, actions, st);
+        sl::launch_env_step_warp(*batch, actions, flags, st);
         return launch_status("k_env_step_warp");
     }
     size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
     rc = prepare_smem(sl::k_env_step_generic, smem);
     if (rc) return rc;
     sl::k_env_step_generic<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, st>>>(*batch, actions);
-    return launch_status("k_env_step_generic");
+    rc = launch_status("k_env_step_generic");
+    if (rc || !(flags & SL_STEP_AUTO_RESET)) return rc;
+    return sl_env_reset(batch, batch->done, nullptr, SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS, stream);
 }
 
 int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *new_level,
@@ -377,7 +381,9 @@ int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *ne
     size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
     rc = prepare_smem(sl::k_env_reset, smem);
     if (rc) return rc;
-    sl::k_env_reset<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, (cudaStream_t)stream>>>(
+    // grid-stride over envs: a masked reset mostly skips, so keep the grid small
+    int grid = batch->n_envs < 2048 ? batch->n_envs : 2048;
+    sl::k_env_reset<<<grid, sl::GENERIC_THREADS, smem, (cudaStream_t)stream>>>(
         *batch, mask, new_level, flags);
     return launch_status("k_env_reset");
 }

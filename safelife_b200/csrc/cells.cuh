@@ -164,17 +164,32 @@ __device__ inline int count_bin(uint32_t b, uint32_t g) {
 
 // One agent's action on a board held in (shared or global) memory.
 // advance_board.c:217-300; (y0, x0) is updated when the agent moves.
+// The cells an action can touch: the agent's (i0), the one ahead (i1, at
+// (y1, x1)), two ahead (i2) and the one behind (i3), on the torus.
+struct ActionCells {
+    int dir, i0, i1, i2, i3, y1, x1;
+};
+
+__device__ inline ActionCells action_cells(int H, int W, int y0, int x0, int action) {
+    ActionCells c;
+    c.dir = (action - 1) & 3;   // 0 up, 1 right, 2 down, 3 left
+    const int dy = (c.dir == 0) ? -1 : (c.dir == 2 ? 1 : 0);
+    const int dx = (c.dir == 1) ? 1 : (c.dir == 3 ? -1 : 0);
+    c.y1 = wrap_idx(y0 + dy, H);
+    c.x1 = wrap_idx(x0 + dx, W);
+    c.i0 = y0 * W + x0;
+    c.i1 = c.y1 * W + c.x1;
+    c.i2 = wrap_idx(c.y1 + dy, H) * W + wrap_idx(c.x1 + dx, W);
+    c.i3 = wrap_idx(y0 - dy, H) * W + wrap_idx(x0 - dx, W);
+    return c;
+}
+
 template <typename T>
-__device__ inline void agent_action(T *board, int H, int W, int &y0, int &x0, int action) {
-    if (action == 0) return;
-    int dir = (action - 1) & 3;   // 0 up, 1 right, 2 down, 3 left
-    int dy = (dir == 0) ? -1 : (dir == 2 ? 1 : 0);
-    int dx = (dir == 1) ? 1 : (dir == 3 ? -1 : 0);
-    int i0 = y0 * W + x0;
-    int y1 = wrap_idx(y0 + dy, H), x1 = wrap_idx(x0 + dx, W);
-    int i1 = y1 * W + x1;
-    int i2 = wrap_idx(y1 + dy, H) * W + wrap_idx(x1 + dx, W);
-    int i3 = wrap_idx(y0 - dy, H) * W + wrap_idx(x0 - dx, W);
+__device__ inline void agent_action(T *board, int H, int W, int &y0, int &x0, int action);
+
+template <typename T>
+__device__ inline void agent_action_at(T *board, const ActionCells &c, int &y0, int &x0, int action) {
+    const int dir = c.dir, i0 = c.i0, i1 = c.i1, i2 = c.i2, i3 = c.i3, y1 = c.y1, x1 = c.x1;
     uint32_t me = board[i0];
     if (!(me & AGENT)) return;
     me = (me & ~(uint32_t)ORIENT) | ((uint32_t)dir << ORIENT_SHIFT);
@@ -222,6 +237,12 @@ __device__ inline void agent_action(T *board, int H, int W, int &y0, int &x0, in
     } else {
         board[i0] = 0;
     }
+}
+
+template <typename T>
+__device__ inline void agent_action(T *board, int H, int W, int &y0, int &x0, int action) {
+    if (action == 0) return;
+    agent_action_at(board, action_cells(H, W, y0, x0, action), y0, x0, action);
 }
 
 }  // namespace sl

@@ -258,9 +258,10 @@ __global__ void k_wrapped_label(int32_t *__restrict__ data, int32_t *__restrict_
 }
 
 // Points contribution of one cell (alive_counts bin x points table).
-__device__ inline int cell_points(uint32_t b, uint32_t g, const int32_t *__restrict__ table) {
+// (table may live in global or shared memory)
+__device__ inline int cell_points(uint32_t b, uint32_t g, const int32_t *table) {
     int bin = count_bin(b, g);
-    return bin < 0 ? 0 : __ldg(table + bin);
+    return bin < 0 ? 0 : table[bin];
 }
 
 // ------------------------------------------------------------------------
@@ -273,9 +274,10 @@ __device__ inline int cell_points(uint32_t b, uint32_t g, const int32_t *__restr
 // ------------------------------------------------------------------------
 template <typename T>
 __device__ inline int exit_update(T *bd, const T *gl, int W, int row, int col, int count_points,
-                                  int init_points, int required, const int32_t *exits,
-                                  int max_exits, const int32_t *__restrict__ table,
+                                  const SlEnvState &st, const int32_t *exits,
+                                  const int32_t *table,
                                   bool *agent_alive, bool *exited, int *delta_mem) {
+    const int init_points = st.init_points, required = st.required;
     bool can_exit = false;
     int idx = -1;
     if (row >= 0) {
@@ -288,9 +290,9 @@ __device__ inline int exit_update(T *bd, const T *gl, int W, int row, int col, i
     }
     const uint32_t exit_type = LEVEL_EXIT | (can_exit ? (uint32_t)COLOR_R : 0u);
     int delta = 0;
-    for (int k = 0; k < max_exits; k++) {
-        int e = exits[k];
-        if (e < 0) continue;
+    for (int k = 0; k < st.n_exits; k++) {
+        // the first two exit cells travel in the env record, the rest stay in the pool
+        int e = k == 0 ? st.exit0 : (k == 1 ? st.exit1 : exits[k]);
         uint32_t old = bd[e];
         if (old != exit_type) {
             if ((old & ~(uint32_t)COLORS) != LEVEL_EXIT) delta -= cell_points(old, gl[e], table);
@@ -308,7 +310,7 @@ __device__ inline int exit_update(T *bd, const T *gl, int W, int row, int col, i
 }
 
 // Scalar tail of SafeLifeEnv.step (safelife_env.py:155-175) for one env.
-__device__ inline void finish_step(const SlEnvBatch &B, int e, SlEnvState &st, int row, int col,
+__device__ inline bool finish_step(const SlEnvBatch &B, int e, SlEnvState &st, int row, int col,
                                    int value, bool agent_alive, bool exited, int static_goals,
                                    int count_points_mem) {
     int steps = st.num_steps + 1;
@@ -337,6 +339,7 @@ __device__ inline void finish_step(const SlEnvBatch &B, int e, SlEnvState &st, i
     B.done[e] = done;
     B.success[e] = success;
     B.times_up[e] = times_up;
+    return done;
 }
 
 // sum(table * alive_counts) over a board/goals pair by the whole block.
@@ -397,8 +400,8 @@ k_env_step_generic(SlEnvBatch B, const uint8_t *__restrict__ actions) {
             bool agent_alive, exited;
             int row = sm.misc[0], col = sm.misc[1], delta;
             SlEnvState st = *stp;
-            int value = exit_update(sm.b, gl, W, row, col, pts, st.init_points, st.required,
-                                    B.pool_exits + (size_t)lvl * B.max_exits, B.max_exits, table,
+            int value = exit_update(sm.b, gl, W, row, col, pts, st,
+                                    B.pool_exits + (size_t)lvl * B.max_exits, table,
                                     &agent_alive, &exited, &delta);
             st.rng[0] = sm.rng[0];
             st.rng[1] = sm.rng[1];
@@ -447,8 +450,13 @@ k_env_reset(SlEnvBatch B, const uint8_t *__restrict__ mask, const int32_t *__res
             bool empty = false;
             for (int g = 0; g < 8; g++) empty |= table[g * 9 + 8] != 0;
             st.empty_points = empty;
-            int value = exit_update(sm.a, sm.b, W, row, col, pts, st.init_points, st.required,
-                                    B.pool_exits + (size_t)lvl * B.max_exits, B.max_exits, table,
+            const int32_t *exits = B.pool_exits + (size_t)lvl * B.max_exits;
+            int n_exits = 0;
+            while (n_exits < B.max_exits && exits[n_exits] >= 0) n_exits++;
+            st.n_exits = n_exits;
+            st.exit0 = n_exits > 0 ? exits[0] : -1;
+            st.exit1 = n_exits > 1 ? exits[1] : -1;
+            int value = exit_update(sm.a, sm.b, W, row, col, pts, st, exits, table,
                                     &agent_alive, &exited, &delta);
             st.level_id = lvl;
             st.loc_row = row;

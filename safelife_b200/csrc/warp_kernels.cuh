@@ -222,7 +222,7 @@ __device__ __forceinline__ uint32_t warp_spawn_draws(u128 &state, const u128 &in
 __device__ __forceinline__ uint32_t apply_row(RowPlanes &p, const RowDelta &d, uint32_t spawned,
                                               uint16_t *slab, int r, int W,
                                               const uint16_t *goals = nullptr,
-                                              const int32_t *__restrict__ table = nullptr,
+                                              const int32_t *table = nullptr,
                                               int *delta = nullptr) {
     const uint32_t fresh = d.born | spawned;
     const uint32_t changed = d.die | fresh;
@@ -254,7 +254,7 @@ __device__ __forceinline__ uint32_t apply_row(RowPlanes &p, const RowDelta &d, u
 // sum(table * alive_counts) of a board given its planes and the goals slab
 // (advance_board.c:192-207 + safelife_game.py:684-687), reduced over the warp.
 __device__ __forceinline__ int warp_points(const RowPlanes &p, const uint16_t *goals, int r, int W,
-                                           uint32_t wmask, const int32_t *__restrict__ table,
+                                           uint32_t wmask, const int32_t *table,
                                            bool empty_column) {
     const uint32_t countable = ((p.D | p.PU | p.PL) | ~p.F) & wmask;
     const uint16_t *grow = goals + r * W;
@@ -265,14 +265,14 @@ __device__ __forceinline__ int warp_points(const RowPlanes &p, const uint16_t *g
         m &= m - 1;
         int col = ((p.R >> j) & 1) | (((p.G >> j) & 1) << 1) | (((p.B >> j) & 1) << 2);
         int g = (grow[j] >> COLOR_SHIFT) & 7;
-        pts += __ldg(table + g * 9 + col);
+        pts += table[g * 9 + col];
     }
     if (empty_column) {
         m = ~p.A & countable;
         while (m != 0) {
             int j = __ffs(m) - 1;
             m &= m - 1;
-            pts += __ldg(table + ((grow[j] >> COLOR_SHIFT) & 7) * 9 + 8);
+            pts += table[((grow[j] >> COLOR_SHIFT) & 7) * 9 + 8];
         }
     }
     return __reduce_add_sync(FULL, pts);
@@ -337,9 +337,70 @@ __host__ __device__ inline int warp_slab_stride(int cells) {
     return (WARP_ENVS_PER_CTA * cells * 2 + 15) & ~15;
 }
 
+// SafeLifeEnv.reset of one env by its warp, inside the step kernel
+// (safelife_env.py:203-218): next level of the pool into the shared-memory
+// slabs, points recount, update_exit_colors, fresh episode state.  Rare (once
+// per episode), so kept out of line.
+__device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, int e, int level_id,
+                                            int ep_length, float ep_reward, uint16_t *board,
+                                            uint16_t *goals, int32_t *table, int lane) {
+    const int H = B.H, W = B.W, cells = H * W;
+    const int lvl = (int)(((long long)level_id + B.level_stride) % B.n_levels);
+    const uint16_t *pb = B.pool_board + (size_t)lvl * cells;
+    const uint16_t *pg = B.pool_goals + (size_t)lvl * cells;
+    for (int i = lane; i < cells; i += 32) {
+        board[i] = pb[i];
+        goals[i] = pg[i];
+    }
+    const int32_t *gtable = B.pool_table + (size_t)lvl * 72;
+    table[lane] = gtable[lane];
+    table[lane + 32] = gtable[lane + 32];
+    if (lane < 8) table[lane + 64] = gtable[lane + 64];
+    __syncwarp();
+    const bool empty = __any_sync(FULL, lane < 8 && table[lane * 9 + 8] != 0);
+    const Torus t = make_torus(H, W, lane);
+    RowPlanes p = load_row_planes(board, lane, W, t.wmask);
+    const int pts = warp_points(p, goals, lane, W, t.wmask, table, empty);
+    if (lane == 0) {
+        const int32_t *exits = B.pool_exits + (size_t)lvl * B.max_exits;
+        int n_exits = 0;
+        while (n_exits < B.max_exits && exits[n_exits] >= 0) n_exits++;
+        SlEnvState st;
+        st.level_id = lvl;
+        st.init_points = B.pool_init_points[lvl];
+        st.required = B.pool_required[lvl];
+        st.spawn_thr = B.pool_spawn_thr[lvl];
+        st.empty_points = empty;
+        st.reserved0 = 0;
+        st.n_exits = n_exits;
+        st.exit0 = n_exits > 0 ? exits[0] : -1;
+        st.exit1 = n_exits > 1 ? exits[1] : -1;
+        bool agent_alive, exited;
+        int dmem;
+        const int row = B.pool_loc[2 * lvl], col = B.pool_loc[2 * lvl + 1];
+        const int value = exit_update(board, goals, W, row, col, pts, st, exits, table,
+                                      &agent_alive, &exited, &dmem);
+        st.loc_row = row;
+        st.loc_col = col;
+        st.num_steps = 0;
+        st.old_value = value;
+        st.ep_length = ep_length;   // episode totals stay (SL_RESET_KEEP_STATS)
+        st.ep_reward = ep_reward;
+        st.count_points = pts + dmem;
+        st.active = 1;
+        st.static_goals = 0;
+        uint4 *dst = (uint4 *)(B.state + e);
+        const uint4 *src = (const uint4 *)&st;
+#pragma unroll
+        for (int i = 2; i < 6; i++) dst[i] = src[i];
+    }
+    __syncwarp();
+}
+
 // SafeLifeEnv.step, one warp per env (safelife_env.py:148-201).
-__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32)
-k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) {
+__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, 4)
+k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
+                int bulk_ok, int flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = B.H, W = B.W, cells = H * W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -349,6 +410,7 @@ k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) 
     uint64_t *bar = (uint64_t *)smem_raw;
     uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_HEADER);
     uint16_t *sgoals = (uint16_t *)(smem_raw + WARP_SMEM_HEADER + warp_slab_stride(cells));
+    int32_t *stable = (int32_t *)(smem_raw + WARP_SMEM_HEADER + 2 * warp_slab_stride(cells) + WARP_SMEM_PAD);
     uint16_t *gboard = B.board + (size_t)e0 * cells;
     uint16_t *ggoals = B.goals + (size_t)e0 * cells;
     const bool bulk = bulk_ok && (group_bytes & 15) == 0;
@@ -386,7 +448,15 @@ k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) 
         uint16_t *goals = sgoals + warp * cells;
         const int lvl = st.level_id;
         const uint64_t thr = st.spawn_thr;
-        const int32_t *table = B.pool_table + (size_t)lvl * 72;
+        // this level's points table, staged per warp (lookups sit in divergent loops)
+        int32_t *table = stable + warp * 72;
+        {
+            const int32_t *gtable = B.pool_table + (size_t)lvl * 72;
+            table[lane] = __ldg(gtable + lane);
+            table[lane + 32] = __ldg(gtable + lane + 32);
+            if (lane < 8) table[lane + 64] = __ldg(gtable + lane + 64);
+            __syncwarp();
+        }
         u128 state = {st.rng[0], st.rng[1]};
         const u128 inc = {st.rng[2], st.rng[3]};
         int row = st.loc_row, col = st.loc_col;
@@ -396,22 +466,15 @@ k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) 
         // ---- execute_actions (advance_board.c:217-300): lane 0 acts; lanes 0-3
         //      account for the (at most four) cells it can touch
         if (row >= 0 && action != 0) {
-            const int dir = (action - 1) & 3;
-            const int dy = (dir == 0) ? -1 : (dir == 2 ? 1 : 0);
-            const int dx = (dir == 1) ? 1 : (dir == 3 ? -1 : 0);
-            const int y1 = wrap_idx(row + dy, H), x1 = wrap_idx(col + dx, W);
-            int idx = row * W + col;                                           // lane 0: agent
-            if (lane == 1) idx = y1 * W + x1;                                  // ahead
-            if (lane == 2) idx = wrap_idx(y1 + dy, H) * W + wrap_idx(x1 + dx, W);   // two ahead
-            if (lane == 3) idx = wrap_idx(row - dy, H) * W + wrap_idx(col - dx, W); // behind
-            const int idx2 = __shfl_sync(FULL, idx, 2);
+            const ActionCells ac = action_cells(H, W, row, col, action);
+            const int idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
             uint32_t before = lane < 4 ? board[idx] : 0u;
             __syncwarp();
-            if (lane == 0) agent_action(board, H, W, row, col, action);
+            if (lane == 0) agent_action_at(board, ac, row, col, action);
             __syncwarp();
             row = __shfl_sync(FULL, row, 0);
             col = __shfl_sync(FULL, col, 0);
-            if (lane < 4 && !(lane == 3 && idx == idx2)) {
+            if (lane < 4 && !(lane == 3 && ac.i3 == ac.i2)) {
                 uint32_t after = board[idx];
                 if (after != before) {
                     uint32_t g = goals[idx];
@@ -443,22 +506,31 @@ k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) 
             pts = warp_points(p, goals, lane, W, t.wmask, table, st.empty_points != 0);
         }
 
+        bool done = false;
         if (lane == 0) {
             bool agent_alive, exited;
             int dmem;
-            int value = exit_update(board, goals, W, row, col, pts, st.init_points, st.required,
-                                    B.pool_exits + (size_t)lvl * B.max_exits, B.max_exits, table,
+            int value = exit_update(board, goals, W, row, col, pts, st,
+                                    B.pool_exits + (size_t)lvl * B.max_exits, table,
                                     &agent_alive, &exited, &dmem);
             const bool drew = state.hi != st.rng[0] || state.lo != st.rng[1];
             st.rng[0] = state.hi;
             st.rng[1] = state.lo;
-            finish_step(B, e, st, row, col, value, agent_alive, exited, sg, pts + dmem);
+            done = finish_step(B, e, st, row, col, value, agent_alive, exited, sg, pts + dmem);
             uint4 *dst = (uint4 *)(B.state + e);
             const uint4 *src = (const uint4 *)&st;
             if (drew) dst[0] = src[0];
             dst[2] = src[2];
             dst[3] = src[3];
             dst[5] = src[5];
+        }
+        if (flags & SL_STEP_AUTO_RESET) {
+            if (__shfl_sync(FULL, (int)done, 0)) {
+                __syncwarp();
+                warp_reset_env(B, e, st.level_id, __shfl_sync(FULL, st.ep_length, 0),
+                               __shfl_sync(FULL, st.ep_reward, 0), board, goals, table, lane);
+                goals_dirty = true;
+            }
         }
     }
     if (bulk) {
@@ -477,14 +549,17 @@ k_env_step_warp(SlEnvBatch B, const uint8_t *__restrict__ actions, int bulk_ok) 
 }
 
 inline size_t warp_step_smem_bytes(int cells) {
-    return WARP_SMEM_HEADER + 2 * (size_t)warp_slab_stride(cells) + WARP_SMEM_PAD;
+    return WARP_SMEM_HEADER + 2 * (size_t)warp_slab_stride(cells) + WARP_SMEM_PAD +
+           WARP_ENVS_PER_CTA * 72 * sizeof(int32_t);
 }
 
-inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, cudaStream_t st) {
+inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
+                                 cudaStream_t st) {
     const int cells = B.H * B.W;
     const int grid = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
     const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals) & 15) == 0;
-    k_env_step_warp<<<grid, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(B, actions, bulk_ok);
+    k_env_step_warp<<<grid, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(
+        B, actions, bulk_ok, flags);
 }
 
 inline bool warp_advance_supports(int H, int W) {

@@ -225,8 +225,11 @@ class BatchedSafeLifeEnv(object):
                 int(bool(self.remove_white_goals)), self._stream()))
         return self._obs if self._channels is not None else self._obs.view(torch.uint32)
 
-    def step_physics(self, actions):
-        """The step path alone (no observation, no auto-reset): safelife_env.py:148-175."""
+    def step_physics(self, actions, auto_reset=False):
+        """
+        The step path alone (no observation): safelife_env.py:148-175, plus the
+        reset of finished envs in the same launch when `auto_reset` is set.
+        """
         if not torch.is_tensor(actions):
             a = np.asarray(actions)
             if a.shape != (self.num_envs,):
@@ -238,12 +241,13 @@ class BatchedSafeLifeEnv(object):
             raise ValueError("actions must have shape (num_envs,)")
         self._actions.copy_(actions, non_blocking=True)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.sl_env_step(self._batch_ref, self._actions.data_ptr(),
-                                             self.kernel, self._stream()))
+            _lib.check(self._lib.sl_env_step(
+                self._batch_ref, self._actions.data_ptr(), self.kernel,
+                _lib.SL_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
 
     def step(self, actions):
         assert self._has_reset, "Game state is not initialized."
-        self.step_physics(actions)
+        self.step_physics(actions, self.auto_reset)
         t = self._t
         reward, done = t["reward"], t["done"].bool()
         info = {
@@ -251,11 +255,6 @@ class BatchedSafeLifeEnv(object):
             "episode": {"length": t["ep_length"], "reward": t["ep_reward"],
                         "success": t["success"].bool()},
         }
-        if self.auto_reset:
-            with torch.cuda.device(self.device):
-                _lib.check(self._lib.sl_env_reset(
-                    self._batch_ref, t["done"].data_ptr(), None,
-                    _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS, self._stream()))
         info["board"], info["goals"], info["agent_locs"] = self.board, self.goals, self.agent_locs
         return self.get_obs(), reward, done, info
 
