@@ -38,7 +38,7 @@ METRIC = "env-steps/sec (batched boards) at 1/2/4/8 B200 vs C-ext on host cores"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
@@ -182,40 +183,100 @@ def run_reference(args, levels):
 # GPU arm
 # --------------------------------------------------------------------------
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons (NVML) polled while the timed regions run."""
 
-    def __init__(self, index):
-        self.rows, self.proc = [], None
+    def __init__(self, index, period_s=0.004):
+        self.sm, self.reasons, self.max_mhz, self.err = [], 0, None, None
+        self.marks = []
+        self._stop = threading.Event()
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:   # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, args=(period_s,), daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
+        except Exception as exc:   # noqa: BLE001
+            self.err = repr(exc)
+            self.thread = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self, period_s):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append((time.perf_counter(),
+                                float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))))
+                self.reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception as exc:   # noqa: BLE001
+                self.err = repr(exc)
+                break
+            time.sleep(period_s)
+
+    def mark(self):
+        self.marks.append(time.perf_counter())
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml: %s" % self.err]}
+        self._stop.set()
         self.thread.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4)
-                          if r[2 + k].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        nv = self.nv
+        lo, hi = (self.marks[0], self.marks[-1]) if len(self.marks) >= 2 else (0, float("inf"))
+        inside = [v for t, v in self.sm if lo <= t <= hi] or [v for _, v in self.sm]
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        return {"sm_mhz": float(np.median(inside)) if inside else None,
+                "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, bit in names.items() if self.reasons & bit),
+                "samples": len(inside), "source": "nvml, sampled during the timed regions"}
+
+
+def sweep(args, levels, dev, peak):
+    """
+    The same device-timed measurement at larger batches (state beyond the L2 at
+    65536 envs), 60 steps each: where the kernel leaves the launch-latency regime.
+    """
+    import torch
+    from safelife_b200 import _lib
+    from safelife_b200.env import BatchedSafeLifeEnv
+    out = []
+    H, W = levels[0]["board"].shape
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for n in (16384, 65536):
+        env = BatchedSafeLifeEnv([levels[i % len(levels)] for i in range(n)], n, device=dev,
+                                 kernel=args.kernel, time_limit=1000)
+        env.reset()
+        K = 60
+        actions = torch.randint(0, 9, (K + 5, n), device=dev, dtype=torch.uint8)
+        stream = env._stream()
+        for t in range(5):
+            _lib.check(env._lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), args.kernel,
+                                            _lib.SL_STEP_AUTO_RESET, stream))
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+        torch.cuda.synchronize()
+        for t in range(K):
+            flush.fill_(t & 0xFF)
+            ev[t][0].record()
+            _lib.check(env._lib.sl_env_step(env._batch_ref, actions[5 + t].data_ptr(), args.kernel,
+                                            _lib.SL_STEP_AUTO_RESET, stream))
+            ev[t][1].record()
+        torch.cuda.synchronize()
+        ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
+        gbs = n * (6 * H * W + 64) / (ms * 1e-3) / 1e9
+        out.append({"envs": n, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3),
+                    "achieved_gbs": gbs, "frac": gbs / peak})
+        del env
+    return out
 
 
 def run_ours(args, levels):
@@ -269,6 +330,8 @@ def run_ours(args, levels):
     # ---- value: device-timed, state resident in HBM, L2 flushed between steps ----
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     wall0 = time.perf_counter()
     for t in range(K):
         if flush is not None:
@@ -301,6 +364,8 @@ def run_ours(args, levels):
         e2e_ev[t][1].synchronize()                        # the host consumes the result
     barrier()
     e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_ev)
+    if sampler:
+        sampler.mark()
     clocks = sampler.stop() if sampler else None
 
     times = torch.tensor([total_ms, step_ms, e2e_ms], dtype=torch.float64, device=dev)
@@ -339,6 +404,8 @@ def run_ours(args, levels):
             },
             "wall_s_timed_region": wall,
         }
+        if not args.no_sweep and world == 1:
+            line["sweep"] = sweep(args, levels, dev, peak)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_arm(levels, n, min(K, 100), 2, args.cpu_seconds)
         print(json.dumps(line), flush=True)

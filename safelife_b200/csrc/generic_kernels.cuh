@@ -258,8 +258,11 @@ __global__ void k_wrapped_label(int32_t *__restrict__ data, int32_t *__restrict_
 }
 
 // Points contribution of one cell (alive_counts bin x points table).
-// (table may live in global or shared memory)
-__device__ inline int cell_points(uint32_t b, uint32_t g, const int32_t *table) {
+// (table may live in global or shared memory).  dead_counts = false skips the
+// lookup for dead cells when the table's "empty" column is all zero.
+__device__ inline int cell_points(uint32_t b, uint32_t g, const int32_t *table,
+                                  bool dead_counts = true) {
+    if (!dead_counts && !(b & ALIVE)) return 0;
     int bin = count_bin(b, g);
     return bin < 0 ? 0 : table[bin];
 }

@@ -223,7 +223,7 @@ __device__ __forceinline__ uint32_t apply_row(RowPlanes &p, const RowDelta &d, u
                                               uint16_t *slab, int r, int W,
                                               const uint16_t *goals = nullptr,
                                               const int32_t *table = nullptr,
-                                              int *delta = nullptr) {
+                                              int *delta = nullptr, bool dead_counts = true) {
     const uint32_t fresh = d.born | spawned;
     const uint32_t changed = d.die | fresh;
     if (changed == 0) return 0u;
@@ -244,7 +244,8 @@ __device__ __forceinline__ uint32_t apply_row(RowPlanes &p, const RowDelta &d, u
                      (((p.G >> j) & 1u) << 10) | (((p.B >> j) & 1u) << 11);
         if (table != nullptr) {
             uint32_t g = goals[r * W + j];
-            *delta += cell_points(v, g, table) - cell_points(row[j], g, table);
+            *delta += cell_points(v, g, table, dead_counts) -
+                      cell_points(row[j], g, table, dead_counts);
         }
         row[j] = (uint16_t)v;
     }
@@ -330,33 +331,44 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-constexpr int WARP_SMEM_HEADER = 16;                       // mbarrier
-constexpr int WARP_SMEM_PAD = 2 * (32 * 32 + 32);          // row over-read of the last warp
+// Shared memory of one CTA of the step kernel.
+constexpr int WARP_SMEM_BAR = 16;                                   // mbarrier
+constexpr int WARP_SMEM_STATE = WARP_ENVS_PER_CTA * 96;             // SlEnvState[8]
+constexpr int WARP_SMEM_TABLES = WARP_ENVS_PER_CTA * 72 * 4;        // points tables
+constexpr int WARP_SMEM_PAD = 2 * (32 * 32 + 32);                   // row over-read of the last warp
 
 __host__ __device__ inline int warp_slab_stride(int cells) {
     return (WARP_ENVS_PER_CTA * cells * 2 + 15) & ~15;
 }
 
-// SafeLifeEnv.reset of one env by its warp, inside the step kernel
+inline size_t warp_step_smem_bytes(int cells) {
+    return WARP_SMEM_BAR + WARP_SMEM_STATE + WARP_SMEM_TABLES + 2 * (size_t)warp_slab_stride(cells) +
+           WARP_SMEM_PAD;
+}
+
+__device__ __forceinline__ void load_table(int32_t *table, const int32_t *__restrict__ gtable,
+                                           int lane) {
+    table[lane] = __ldg(gtable + lane);
+    table[lane + 32] = __ldg(gtable + lane + 32);
+    if (lane < 8) table[lane + 64] = __ldg(gtable + lane + 64);
+    __syncwarp();
+}
+
+// SafeLifeEnv.reset of one env by a whole warp, inside the step kernel
 // (safelife_env.py:203-218): next level of the pool into the shared-memory
-// slabs, points recount, update_exit_colors, fresh episode state.  Rare (once
-// per episode), so kept out of line.
-__device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, int e, int level_id,
-                                            int ep_length, float ep_reward, uint16_t *board,
+// slabs, points recount, update_exit_colors, fresh episode state in the
+// shared-memory record.  Rare (once per episode), so kept out of line.
+__device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st, uint16_t *board,
                                             uint16_t *goals, int32_t *table, int lane) {
     const int H = B.H, W = B.W, cells = H * W;
-    const int lvl = (int)(((long long)level_id + B.level_stride) % B.n_levels);
+    const int lvl = (int)(((long long)st->level_id + B.level_stride) % B.n_levels);
     const uint16_t *pb = B.pool_board + (size_t)lvl * cells;
     const uint16_t *pg = B.pool_goals + (size_t)lvl * cells;
     for (int i = lane; i < cells; i += 32) {
         board[i] = pb[i];
         goals[i] = pg[i];
     }
-    const int32_t *gtable = B.pool_table + (size_t)lvl * 72;
-    table[lane] = gtable[lane];
-    table[lane + 32] = gtable[lane + 32];
-    if (lane < 8) table[lane + 64] = gtable[lane + 64];
-    __syncwarp();
+    load_table(table, B.pool_table + (size_t)lvl * 72, lane);
     const bool empty = __any_sync(FULL, lane < 8 && table[lane * 9 + 8] != 0);
     const Torus t = make_torus(H, W, lane);
     RowPlanes p = load_row_planes(board, lane, W, t.wmask);
@@ -365,39 +377,40 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, int e, int leve
         const int32_t *exits = B.pool_exits + (size_t)lvl * B.max_exits;
         int n_exits = 0;
         while (n_exits < B.max_exits && exits[n_exits] >= 0) n_exits++;
-        SlEnvState st;
-        st.level_id = lvl;
-        st.init_points = B.pool_init_points[lvl];
-        st.required = B.pool_required[lvl];
-        st.spawn_thr = B.pool_spawn_thr[lvl];
-        st.empty_points = empty;
-        st.reserved0 = 0;
-        st.n_exits = n_exits;
-        st.exit0 = n_exits > 0 ? exits[0] : -1;
-        st.exit1 = n_exits > 1 ? exits[1] : -1;
+        st->level_id = lvl;
+        st->init_points = B.pool_init_points[lvl];
+        st->required = B.pool_required[lvl];
+        st->spawn_thr = B.pool_spawn_thr[lvl];
+        st->empty_points = empty;
+        st->n_exits = n_exits;
+        st->exit0 = n_exits > 0 ? exits[0] : -1;
+        st->exit1 = n_exits > 1 ? exits[1] : -1;
         bool agent_alive, exited;
         int dmem;
         const int row = B.pool_loc[2 * lvl], col = B.pool_loc[2 * lvl + 1];
-        const int value = exit_update(board, goals, W, row, col, pts, st, exits, table,
+        const int value = exit_update(board, goals, W, row, col, pts, *st, exits, table,
                                       &agent_alive, &exited, &dmem);
-        st.loc_row = row;
-        st.loc_col = col;
-        st.num_steps = 0;
-        st.old_value = value;
-        st.ep_length = ep_length;   // episode totals stay (SL_RESET_KEEP_STATS)
-        st.ep_reward = ep_reward;
-        st.count_points = pts + dmem;
-        st.active = 1;
-        st.static_goals = 0;
-        uint4 *dst = (uint4 *)(B.state + e);
-        const uint4 *src = (const uint4 *)&st;
-#pragma unroll
-        for (int i = 2; i < 6; i++) dst[i] = src[i];
+        st->loc_row = row;
+        st->loc_col = col;
+        st->num_steps = 0;
+        st->old_value = value;
+        st->count_points = pts + dmem;
+        st->active = 1;
+        st->static_goals = 0;   // episode totals stay (SL_RESET_KEEP_STATS)
     }
     __syncwarp();
 }
 
 // SafeLifeEnv.step, one warp per env (safelife_env.py:148-201).
+//
+// A CTA owns 8 consecutive envs.  Their board slabs, goal slabs and state
+// records arrive in shared memory by three bulk asynchronous copies and leave
+// the same way.  Work is split so that scalar per-env code runs once per CTA
+// on 8 lanes instead of once per warp on 1 lane:
+//   phase A  warp w: execute_actions and advance_board of env w on bit planes
+//            (+ goals, points)
+//   phase B  warp 0, lane w: update_exit_colors, reward / done, episode
+//            counters of env w; then auto-reset of finished envs
 __global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, 4)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
                 int bulk_ok, int flags) {
@@ -406,91 +419,82 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int e0 = blockIdx.x * WARP_ENVS_PER_CTA;
     const int nenv = min(WARP_ENVS_PER_CTA, B.n_envs - e0);
-    const int group_bytes = nenv * cells * 2;
+    const int group_bytes = nenv * cells * 2, state_bytes = nenv * 96;
     uint64_t *bar = (uint64_t *)smem_raw;
-    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_HEADER);
-    uint16_t *sgoals = (uint16_t *)(smem_raw + WARP_SMEM_HEADER + warp_slab_stride(cells));
-    int32_t *stable = (int32_t *)(smem_raw + WARP_SMEM_HEADER + 2 * warp_slab_stride(cells) + WARP_SMEM_PAD);
+    SlEnvState *sstate = (SlEnvState *)(smem_raw + WARP_SMEM_BAR);
+    int32_t *stables = (int32_t *)(smem_raw + WARP_SMEM_BAR + WARP_SMEM_STATE);
+    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_BAR + WARP_SMEM_STATE + WARP_SMEM_TABLES);
+    uint16_t *sgoals = sboard + warp_slab_stride(cells) / 2;
     uint16_t *gboard = B.board + (size_t)e0 * cells;
     uint16_t *ggoals = B.goals + (size_t)e0 * cells;
+    SlEnvState *gstate = B.state + e0;
     const bool bulk = bulk_ok && (group_bytes & 15) == 0;
 
     if (bulk) {
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
-            mbar_expect_tx(bar, 2u * group_bytes);
+            mbar_expect_tx(bar, 2u * group_bytes + state_bytes);
+            bulk_load(sstate, gstate, state_bytes, bar);
             bulk_load(sboard, gboard, group_bytes, bar);
             bulk_load(sgoals, ggoals, group_bytes, bar);
         }
     } else {
+        copy_slabs(sstate, gstate, state_bytes);
         copy_slabs(sboard, gboard, group_bytes);
         copy_slabs(sgoals, ggoals, group_bytes);
-    }
-    // per-env record: every lane reads all of it (same address -> one transaction
-    // per 16-byte load) while the slabs are in flight
-    const int e = e0 + warp;
-    const bool have_env = warp < nenv;
-    SlEnvState st;
-    int action = 0;
-    if (have_env) {
-        const uint4 *src = (const uint4 *)(B.state + e);
-        uint4 *dst = (uint4 *)&st;
-#pragma unroll
-        for (int i = 0; i < 6; i++) dst[i] = src[i];
-        action = actions[e];
     }
     __syncthreads();                      // mbarrier init / fallback copy visible
     if (bulk) mbar_wait(bar, 0);
 
+    const bool have_env = warp < nenv;
+    SlEnvState *st = sstate + warp;
+    uint16_t *board = sboard + warp * cells;
+    uint16_t *goals = sgoals + warp * cells;
+
+    // ---- phase A: advance_board on bit planes, env = warp
     bool goals_dirty = false;
     if (have_env) {
-        uint16_t *board = sboard + warp * cells;
-        uint16_t *goals = sgoals + warp * cells;
-        const int lvl = st.level_id;
-        const uint64_t thr = st.spawn_thr;
-        // this level's points table, staged per warp (lookups sit in divergent loops)
-        int32_t *table = stable + warp * 72;
-        {
-            const int32_t *gtable = B.pool_table + (size_t)lvl * 72;
-            table[lane] = __ldg(gtable + lane);
-            table[lane + 32] = __ldg(gtable + lane + 32);
-            if (lane < 8) table[lane + 64] = __ldg(gtable + lane + 64);
-            __syncwarp();
-        }
-        u128 state = {st.rng[0], st.rng[1]};
-        const u128 inc = {st.rng[2], st.rng[3]};
-        int row = st.loc_row, col = st.loc_col;
-        int sg = st.static_goals;
+        const uint64_t thr = st->spawn_thr;
+        u128 state = {st->rng[0], st->rng[1]};
+        const u128 inc = {st->rng[2], st->rng[3]};
+        const uint64_t state_lo0 = state.lo;
+        int sg = st->static_goals;
         int delta = 0;                    // change of sum(table * alive_counts), this lane
+        // points table of the level: looked up in global memory, and only for
+        // cells that changed (dead cells not at all unless its "empty" column counts)
+        const int32_t *table = B.pool_table + (size_t)st->level_id * 72;
+        const bool dead_counts = st->empty_points != 0;
 
-        // ---- execute_actions (advance_board.c:217-300): lane 0 acts; lanes 0-3
-        //      account for the (at most four) cells it can touch
+        // execute_actions (advance_board.c:217-300): lane 0 acts, lanes 0-3 account
+        // for the (at most four) cells it can touch
+        const int action = actions[e0 + warp];
+        int row = st->loc_row, col = st->loc_col;
         if (row >= 0 && action != 0) {
             const ActionCells ac = action_cells(H, W, row, col, action);
             const int idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
-            uint32_t before = lane < 4 ? board[idx] : 0u;
+            const uint32_t before = lane < 4 ? board[idx] : 0u;
             __syncwarp();
-            if (lane == 0) agent_action_at(board, ac, row, col, action);
+            if (lane == 0) {
+                agent_action_at(board, ac, row, col, action);
+                st->loc_row = row;
+                st->loc_col = col;
+            }
             __syncwarp();
-            row = __shfl_sync(FULL, row, 0);
-            col = __shfl_sync(FULL, col, 0);
             if (lane < 4 && !(lane == 3 && ac.i3 == ac.i2)) {
-                uint32_t after = board[idx];
+                const uint32_t after = board[idx];
                 if (after != before) {
-                    uint32_t g = goals[idx];
-                    delta += cell_points(after, g, table) - cell_points(before, g, table);
+                    const uint32_t g = goals[idx];
+                    delta += cell_points(after, g, table, dead_counts) -
+                             cell_points(before, g, table, dead_counts);
                 }
             }
         }
 
-        // ---- advance_board on bit planes
         const Torus t = make_torus(H, W, lane);
         RowPlanes p = load_row_planes(board, lane, W, t.wmask);
         RowDelta d = stencil_row(t, p);
         uint32_t spawned = warp_spawn_draws(state, inc, thr, d.cand, lane);
-        apply_row(p, d, spawned, board, lane, W, goals, table, &delta);
-
-        int pts;
+        apply_row(p, d, spawned, board, lane, W, goals, table, &delta, dead_counts);
         if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
             RowPlanes gp = load_row_planes(goals, lane, W, t.wmask);
             RowDelta gd = stencil_row(t, gp);
@@ -500,64 +504,75 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
             goals_dirty = true;
             __syncwarp();
         }
+        int pts;
         if (sg == 1) {
-            pts = st.count_points + __reduce_add_sync(FULL, delta);
-        } else {
-            pts = warp_points(p, goals, lane, W, t.wmask, table, st.empty_points != 0);
+            pts = st->count_points + __reduce_add_sync(FULL, delta);
+        } else {   // dynamic goals: recount (planes re-read: the board slab is final here)
+            RowPlanes q = load_row_planes(board, lane, W, t.wmask);
+            pts = warp_points(q, goals, lane, W, t.wmask, table, dead_counts);
         }
-
-        bool done = false;
         if (lane == 0) {
-            bool agent_alive, exited;
-            int dmem;
-            int value = exit_update(board, goals, W, row, col, pts, st,
-                                    B.pool_exits + (size_t)lvl * B.max_exits, table,
-                                    &agent_alive, &exited, &dmem);
-            const bool drew = state.hi != st.rng[0] || state.lo != st.rng[1];
-            st.rng[0] = state.hi;
-            st.rng[1] = state.lo;
-            done = finish_step(B, e, st, row, col, value, agent_alive, exited, sg, pts + dmem);
-            uint4 *dst = (uint4 *)(B.state + e);
-            const uint4 *src = (const uint4 *)&st;
-            if (drew) dst[0] = src[0];
-            dst[2] = src[2];
-            dst[3] = src[3];
-            dst[5] = src[5];
-        }
-        if (flags & SL_STEP_AUTO_RESET) {
-            if (__shfl_sync(FULL, (int)done, 0)) {
-                __syncwarp();
-                warp_reset_env(B, e, st.level_id, __shfl_sync(FULL, st.ep_length, 0),
-                               __shfl_sync(FULL, st.ep_reward, 0), board, goals, table, lane);
-                goals_dirty = true;
+            st->count_points = pts;
+            st->static_goals = (uint8_t)sg;
+            if (state.lo != state_lo0) {   // the LCG is a bijection: lo changes iff draws happened
+                st->rng[0] = state.hi;
+                st->rng[1] = state.lo;
             }
         }
     }
+    fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
+    int any_goals_dirty = __syncthreads_or(goals_dirty);
+    if (warp != 0) return;
+
+    // ---- phase B: exit colours, reward / done, counters; env = lane of warp 0
+    bool done = false;
+    if (lane < nenv) {
+        SlEnvState *s0 = sstate + lane;
+        uint16_t *bd = sboard + lane * cells;
+        const uint16_t *gl = sgoals + lane * cells;
+        const int lvl = s0->level_id;
+        bool agent_alive, exited;
+        int dmem;
+        const int row = s0->loc_row, col = s0->loc_col, pts = s0->count_points;
+        const int value = exit_update(bd, gl, W, row, col, pts, *s0,
+                                      B.pool_exits + (size_t)lvl * B.max_exits,
+                                      B.pool_table + (size_t)lvl * 72, &agent_alive, &exited, &dmem);
+        done = finish_step(B, e0 + lane, *s0, row, col, value, agent_alive, exited,
+                           s0->static_goals, pts + dmem);
+    }
+    if (flags & SL_STEP_AUTO_RESET) {
+        uint32_t todo = __ballot_sync(FULL, done);
+        any_goals_dirty |= todo != 0;
+        while (todo != 0) {
+            const int w = __ffs(todo) - 1;
+            todo &= todo - 1;
+            warp_reset_env(B, sstate + w, sboard + w * cells, sgoals + w * cells, stables + w * 72,
+                           lane);
+        }
+    }
+    fence_async_smem();
+    __syncwarp();
     if (bulk) {
-        fence_async_smem();               // generic-proxy writes -> visible to the bulk engine
-        const int any_goals_dirty = __syncthreads_or(goals_dirty);
-        if (threadIdx.x == 0) {
+        if (lane == 0) {
             bulk_store(gboard, sboard, group_bytes);
             if (any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
+            bulk_store(gstate, sstate, state_bytes);
             bulk_commit_and_wait_read();
         }
     } else {
-        const int any_goals_dirty = __syncthreads_or(goals_dirty);
-        copy_slabs(gboard, sboard, group_bytes);
-        if (any_goals_dirty) copy_slabs(ggoals, sgoals, group_bytes);
+        for (int i = lane; i < (group_bytes >> 1); i += 32) gboard[i] = sboard[i];
+        if (any_goals_dirty)
+            for (int i = lane; i < (group_bytes >> 1); i += 32) ggoals[i] = sgoals[i];
+        for (int i = lane; i < (state_bytes >> 1); i += 32)
+            ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
     }
-}
-
-inline size_t warp_step_smem_bytes(int cells) {
-    return WARP_SMEM_HEADER + 2 * (size_t)warp_slab_stride(cells) + WARP_SMEM_PAD +
-           WARP_ENVS_PER_CTA * 72 * sizeof(int32_t);
 }
 
 inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
                                  cudaStream_t st) {
     const int cells = B.H * B.W;
     const int grid = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
-    const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals) & 15) == 0;
+    const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
     k_env_step_warp<<<grid, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(
         B, actions, bulk_ok, flags);
 }
