@@ -51,6 +51,17 @@ def parse_args():
     return ap.parse_args()
 
 
+def measured_traffic(n, H, W):
+    """DRAM bytes per launch of the step kernel from the committed ncu capture, or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            entry = json.load(f)["k_env_step_warp"].get("%dx%dx%d" % (n, H, W))
+        return entry["dram_bytes_read"] + entry["dram_bytes_write"] if entry else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -397,7 +408,8 @@ def run_ours(args, levels):
             "gpu_launches": launches_per_step * K,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "kernel": "env step kernel",
+                "frac": achieved / peak, "traffic": measured_traffic(n, H, W),
+                "kernel": "k_env_step_warp" if fused else "k_env_step_generic",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms": step_ms / K, "dynamic_goal_envs": dyn,
