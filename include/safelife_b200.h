@@ -188,6 +188,13 @@ typedef struct SlEnvBatch {
 int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                 void *stream);
 
+/* sl_env_step followed by a wait for the stream: for host-driven loops.  The
+ * batch's actions / reward / done / success / times_up pointers may be pinned
+ * host memory (device-addressable under UVA); the kernel then reads and writes
+ * them in place and the results are valid on return. */
+int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                     void *stream);
+
 /* SafeLifeEnv.reset (safelife_env.py:203-218) for every env whose mask byte is
  * non-zero (mask NULL = all envs): copy a level from the pool, then
  * update_exit_colors and the episode counters.  The level is new_level[e]

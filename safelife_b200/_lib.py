@@ -97,6 +97,7 @@ PROTOTYPES = {
     "sl_execute_actions_host": [_vp, _vp, _vp, _i, _i, _i, _i, _i],
     "sl_wrapped_label_host": [_vp, _vp, _i, _i, _i],
     "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
+    "sl_env_step_sync": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_reset": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _i, _vp],
     "sl_get_obs": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _i, _i, _vp],
     "sl_side_effect_cells": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _vp],
@@ -109,8 +110,11 @@ def lib():
     """The loaded library (built first if needed)."""
     global _lib
     if _lib is None:
-        build()
-        handle = ctypes.CDLL(LIB_PATH)
+        path = os.environ.get("SAFELIFE_B200_LIB")   # A/B testing of kernel builds
+        if not path:
+            build()
+            path = LIB_PATH
+        handle = ctypes.CDLL(path)
         for name, argtypes in PROTOTYPES.items():
             fn = getattr(handle, name)
             fn.argtypes = argtypes

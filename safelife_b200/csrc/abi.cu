@@ -361,7 +361,13 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
         return fail(SL_ERR_ARG, "warp kernel needs H, W <= %d", sl::WARP_MAX_DIM);
     if (flags & ~SL_STEP_AUTO_RESET) return fail(SL_ERR_ARG, "unknown step flags");
     if (kernel == 2 || (kernel == 0 && warp_ok)) {
-        sl::launch_env_step_warp(*batch, actions, flags, st);
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        size_t smem = sl::pipe_smem_bytes(batch->H * batch->W);
+        rc = prepare_smem(sl::k_env_step_pipe, smem);
+        if (rc) return rc;
+        sl::launch_env_step_warp(*batch, actions, flags, props.sm_count, st);
         return launch_status("k_env_step_warp");
     }
     size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
@@ -371,6 +377,14 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
     rc = launch_status("k_env_step_generic");
     if (rc || !(flags & SL_STEP_AUTO_RESET)) return rc;
     return sl_env_reset(batch, batch->done, nullptr, SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS, stream);
+}
+
+int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                     void *stream) {
+    int rc = sl_env_step(batch, actions, kernel, flags, stream);
+    if (rc) return rc;
+    SL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return SL_OK;
 }
 
 int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *new_level,

@@ -173,14 +173,23 @@ struct ActionCells {
 __device__ inline ActionCells action_cells(int H, int W, int y0, int x0, int action) {
     ActionCells c;
     c.dir = (action - 1) & 3;   // 0 up, 1 right, 2 down, 3 left
-    const int dy = (c.dir == 0) ? -1 : (c.dir == 2 ? 1 : 0);
-    const int dx = (c.dir == 1) ? 1 : (c.dir == 3 ? -1 : 0);
-    c.y1 = wrap_idx(y0 + dy, H);
-    c.x1 = wrap_idx(x0 + dx, W);
+    // all four cells lie on one axis: walk it once
+    const bool vertical = (c.dir & 1) == 0;
+    const int step = (c.dir == 1 || c.dir == 2) ? 1 : -1;
+    const int n = vertical ? H : W, pos = vertical ? y0 : x0;
+    const int stride = vertical ? W : 1, base = vertical ? x0 : y0 * W;
+    int p1 = pos + step;
+    p1 = p1 < 0 ? n - 1 : (p1 == n ? 0 : p1);
+    int p2 = p1 + step;
+    p2 = p2 < 0 ? n - 1 : (p2 == n ? 0 : p2);
+    int p3 = pos - step;
+    p3 = p3 < 0 ? n - 1 : (p3 == n ? 0 : p3);
     c.i0 = y0 * W + x0;
-    c.i1 = c.y1 * W + c.x1;
-    c.i2 = wrap_idx(c.y1 + dy, H) * W + wrap_idx(c.x1 + dx, W);
-    c.i3 = wrap_idx(y0 - dy, H) * W + wrap_idx(x0 - dx, W);
+    c.i1 = base + p1 * stride;
+    c.i2 = base + p2 * stride;
+    c.i3 = base + p3 * stride;
+    c.y1 = vertical ? p1 : y0;
+    c.x1 = vertical ? x0 : p1;
     return c;
 }
 

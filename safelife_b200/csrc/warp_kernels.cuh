@@ -96,6 +96,64 @@ __device__ __forceinline__ RowPlanes load_row_planes(const uint16_t *slab, int r
     return p;
 }
 
+// The common path only needs the planes of the low byte of the cell word
+// (ALIVE, DESTRUCTIBLE, FROZEN, PRESERVING, INHIBITING, SPAWNING); the high
+// byte (EXIT, colours) matters only where a cell may be created.
+struct LowPlanes { uint32_t A, D, F, P, I, S; };
+struct HighPlanes { uint32_t E, R, G, B; };
+
+// 8 words of 4 bytes (cells i, i+8, i+16, i+24) -> 8 plane words (index = bit).
+__device__ __forceinline__ void transpose8(uint32_t (&x)[8]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint32_t a = x[k], b = x[k + 4];
+        x[k] = (a & 0x0f0f0f0fu) | ((b << 4) & 0xf0f0f0f0u);
+        x[k + 4] = ((a >> 4) & 0x0f0f0f0fu) | (b & 0xf0f0f0f0u);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k & 2) continue;
+        uint32_t a = x[k], b = x[k + 2];
+        x[k] = (a & 0x33333333u) | ((b << 2) & 0xccccccccu);
+        x[k + 2] = ((a >> 2) & 0x33333333u) | (b & 0xccccccccu);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+        uint32_t a = x[k], b = x[k + 1];
+        x[k] = (a & 0x55555555u) | ((b << 1) & 0xaaaaaaaau);
+        x[k + 1] = ((a >> 1) & 0x55555555u) | (b & 0xaaaaaaaau);
+    }
+}
+
+// selector 0x6240 gathers the low bytes, 0x7351 the high bytes of 4 cells
+template <unsigned SEL>
+__device__ __forceinline__ void load_row_bytes(const uint16_t *slab, int r, int W,
+                                               uint32_t (&x)[8]) {
+    const uint16_t *row = slab + r * W;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        uint32_t a = __byte_perm(row[k], row[k + 16], 0x5410);
+        uint32_t b = __byte_perm(row[k + 8], row[k + 24], 0x5410);
+        x[k] = __byte_perm(a, b, SEL);
+    }
+}
+
+__device__ __forceinline__ LowPlanes load_row_low(const uint16_t *slab, int r, int W,
+                                                  uint32_t wmask) {
+    uint32_t x[8];
+    load_row_bytes<0x6240>(slab, r, W, x);
+    transpose8(x);
+    return {x[0] & wmask, x[3] & wmask, x[4] & wmask, x[5] & wmask, x[6] & wmask, x[7] & wmask};
+}
+
+__device__ __forceinline__ HighPlanes load_row_high(const uint16_t *slab, int r, int W,
+                                                    uint32_t wmask) {
+    uint32_t x[8];
+    load_row_bytes<0x7351>(slab, r, W, x);
+    transpose8(x);
+    return {x[0] & wmask, x[1] & wmask, x[2] & wmask, x[3] & wmask};
+}
+
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
     return (a & b) | (a & c) | (b & c);
 }
@@ -149,8 +207,10 @@ __device__ __forceinline__ uint32_t two3x3(const Torus &t, uint32_t x) {
     return two | t.north(two) | t.south(two) | maj3(one, on, os);
 }
 
-// advance_board.c:34-125 on bit planes.
-__device__ __forceinline__ RowDelta stencil_row(const Torus &t, const RowPlanes &p) {
+// advance_board.c:34-125 on bit planes.  `slab` is the (unmodified) board the
+// planes came from: the high-byte planes are fetched from it only if needed.
+__device__ __forceinline__ RowDelta stencil_row(const Torus &t, const LowPlanes &p,
+                                                const uint16_t *slab, int r) {
     // n = alive cells in the 3x3 (centre included), as 4 bit planes
     uint32_t w = t.west(p.A), e = t.east(p.A);
     uint32_t s0 = p.A ^ w ^ e, s1 = maj3(p.A, w, e);
@@ -170,10 +230,11 @@ __device__ __forceinline__ RowDelta stencil_row(const Torus &t, const RowPlanes 
     d.cand = open & ~is3 & any_s;
     // colours / destructibility only matter where something may be created
     if (__any_sync(FULL, (d.born | d.cand) != 0)) {
-        d.tR = two3x3(t, p.A & p.R) | any3x3(t, p.S & p.R);
-        d.tG = two3x3(t, p.A & p.G) | any3x3(t, p.S & p.G);
-        d.tB = two3x3(t, p.A & p.B) | any3x3(t, p.S & p.B);
-        d.dn = two3x3(t, p.A & (p.D | p.E));
+        const HighPlanes h = load_row_high(slab, r, t.W, t.wmask);
+        d.tR = two3x3(t, p.A & h.R) | any3x3(t, p.S & h.R);
+        d.tG = two3x3(t, p.A & h.G) | any3x3(t, p.S & h.G);
+        d.tB = two3x3(t, p.A & h.B) | any3x3(t, p.S & h.B);
+        d.dn = two3x3(t, p.A & (p.D | h.E));
     } else {
         d.tR = d.tG = d.tB = d.dn = 0;
     }
@@ -215,33 +276,28 @@ __device__ __forceinline__ uint32_t warp_spawn_draws(u128 &state, const u128 &in
     return spawned;
 }
 
-// Apply a resolved step to the planes and write the changed cells of this row
-// back into the uint16 slab.  Returns the mask of changed cells; when `table`
-// is given, *delta accumulates what the changes add to sum(table * alive_counts)
-// (goal colours read from the goals slab).
-__device__ __forceinline__ uint32_t apply_row(RowPlanes &p, const RowDelta &d, uint32_t spawned,
-                                              uint16_t *slab, int r, int W,
-                                              const uint16_t *goals = nullptr,
+// Write the cells of this row that a resolved step changed back into the
+// uint16 slab: dead ones become 0, new ones ALIVE | inherited colours |
+// DESTRUCTIBLE (advance_board.c:104, 111-118).  Returns the mask of changed
+// cells; when `table` is given, *delta accumulates what the changes add to
+// sum(table * alive_counts) (goal colours read from the goals slab).
+__device__ __forceinline__ uint32_t apply_row(const RowDelta &d, uint32_t spawned, uint16_t *slab,
+                                              int r, int W, const uint16_t *goals = nullptr,
                                               const int32_t *table = nullptr,
                                               int *delta = nullptr, bool dead_counts = true) {
     const uint32_t fresh = d.born | spawned;
     const uint32_t changed = d.die | fresh;
     if (changed == 0) return 0u;
-    const uint32_t keep = ~changed;
-    p.A = (p.A & keep) | fresh;
-    p.D = (p.D & keep) | (d.dn & d.born) | spawned;
-    p.R = (p.R & keep) | (d.tR & fresh);
-    p.G = (p.G & keep) | (d.tG & fresh);
-    p.B = (p.B & keep) | (d.tB & fresh);
-    p.P &= keep; p.I &= keep; p.S &= keep; p.E &= keep;
-    p.PU &= keep; p.PL &= keep; p.AG &= keep;   // (F is already 0 on every changed cell)
+    const uint32_t destr = (d.dn & d.born) | spawned;
     uint16_t *row = slab + r * W;
     uint32_t m = changed;
     while (m != 0) {
         int j = __ffs(m) - 1;
         m &= m - 1;
-        uint32_t v = ((p.A >> j) & 1u) | (((p.D >> j) & 1u) << 3) | (((p.R >> j) & 1u) << 9) |
-                     (((p.G >> j) & 1u) << 10) | (((p.B >> j) & 1u) << 11);
+        uint32_t v = 0;
+        if ((fresh >> j) & 1u)
+            v = ALIVE | (((destr >> j) & 1u) << 3) | (((d.tR >> j) & 1u) << 9) |
+                (((d.tG >> j) & 1u) << 10) | (((d.tB >> j) & 1u) << 11);
         if (table != nullptr) {
             uint32_t g = goals[r * W + j];
             *delta += cell_points(v, g, table, dead_counts) -
@@ -401,23 +457,131 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st,
     __syncwarp();
 }
 
-// SafeLifeEnv.step, one warp per env (safelife_env.py:148-201).
-//
-// A CTA owns 8 consecutive envs.  Their board slabs, goal slabs and state
-// records arrive in shared memory by three bulk asynchronous copies and leave
-// the same way.  Work is split so that scalar per-env code runs once per CTA
-// on 8 lanes instead of once per warp on 1 lane:
+// ---- phase A: execute_actions + advance_board of one env by one warp ----------
+// `st`, `board`, `goals` are the env's record and slabs in shared memory.
+// Returns true if the goals slab was modified.
+__device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st, uint16_t *board,
+                                             uint16_t *goals, int action, int lane) {
+    const int H = B.H, W = B.W;
+    bool goals_dirty = false;
+    const uint64_t thr = st->spawn_thr;
+    u128 state = {st->rng[0], st->rng[1]};
+    const u128 inc = {st->rng[2], st->rng[3]};
+    const uint64_t state_lo0 = state.lo;
+    int sg = st->static_goals;
+    int delta = 0;                    // change of sum(table * alive_counts), this lane
+    // points table of the level: looked up in global memory, and only for
+    // cells that changed (dead cells not at all unless its "empty" column counts)
+    const int32_t *table = B.pool_table + (size_t)st->level_id * 72;
+    const bool dead_counts = st->empty_points != 0;
+
+    // execute_actions (advance_board.c:217-300): lane 0 acts, lanes 0-3 account
+    // for the (at most four) cells it can touch
+    int row = st->loc_row, col = st->loc_col;
+    if (row >= 0 && action != 0) {
+        const ActionCells ac = action_cells(H, W, row, col, action);
+        const int idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
+        const uint32_t before = lane < 4 ? board[idx] : 0u;
+        __syncwarp();
+        if (lane == 0) {
+            agent_action_at(board, ac, row, col, action);
+            st->loc_row = row;
+            st->loc_col = col;
+        }
+        __syncwarp();
+        if (lane < 4 && !(lane == 3 && ac.i3 == ac.i2)) {
+            const uint32_t after = board[idx];
+            if (after != before) {
+                const uint32_t g = goals[idx];
+                delta += cell_points(after, g, table, dead_counts) -
+                         cell_points(before, g, table, dead_counts);
+            }
+        }
+    }
+
+    const Torus t = make_torus(H, W, lane);
+    const LowPlanes p = load_row_low(board, lane, W, t.wmask);
+    const RowDelta d = stencil_row(t, p, board, lane);
+    const uint32_t spawned = warp_spawn_draws(state, inc, thr, d.cand, lane);
+    apply_row(d, spawned, board, lane, W, goals, table, &delta, dead_counts);
+    if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
+        const LowPlanes gp = load_row_low(goals, lane, W, t.wmask);
+        const RowDelta gd = stencil_row(t, gp, goals, lane);
+        const uint32_t gspawned = warp_spawn_draws(state, inc, thr, gd.cand, lane);
+        const uint32_t gchanged = apply_row(gd, gspawned, goals, lane, W);
+        // static iff nothing changed and no spawner is left (safelife_game.py:756-760)
+        if (sg == 0) sg = __any_sync(FULL, (gchanged | (gp.S & ~gchanged)) != 0) ? 2 : 1;
+        goals_dirty = true;
+        __syncwarp();
+    }
+    int pts;
+    if (sg == 1) {
+        pts = st->count_points + __reduce_add_sync(FULL, delta);
+    } else {   // dynamic goals: recount (planes re-read: the board slab is final here)
+        RowPlanes q = load_row_planes(board, lane, W, t.wmask);
+        pts = warp_points(q, goals, lane, W, t.wmask, table, dead_counts);
+    }
+    if (lane == 0) {
+        st->count_points = pts;
+        st->static_goals = (uint8_t)sg;
+        if (state.lo != state_lo0) {   // the LCG is a bijection: lo changes iff draws happened
+            st->rng[0] = state.hi;
+            st->rng[1] = state.lo;
+        }
+    }
+    return goals_dirty;
+}
+
+// ---- phase B: scalar tail of the step for up to 8 envs, lane w = env w --------
+// update_exit_colors, reward / done, counters (safelife_env.py:153-175), then
+// the auto-reset of finished envs by the whole warp.  Returns true if a reset
+// rewrote a goals slab.
+__device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, int e0, int nenv,
+                                             SlEnvState *sstate, uint16_t *sboard,
+                                             uint16_t *sgoals, int32_t *stables, int flags,
+                                             int lane) {
+    const int cells = B.H * B.W;
+    bool done = false;
+    if (lane < nenv) {
+        SlEnvState *s0 = sstate + lane;
+        uint16_t *bd = sboard + lane * cells;
+        const uint16_t *gl = sgoals + lane * cells;
+        const int lvl = s0->level_id;
+        bool agent_alive, exited;
+        int dmem;
+        const int row = s0->loc_row, col = s0->loc_col, pts = s0->count_points;
+        const int value = exit_update(bd, gl, B.W, row, col, pts, *s0,
+                                      B.pool_exits + (size_t)lvl * B.max_exits,
+                                      B.pool_table + (size_t)lvl * 72, &agent_alive, &exited, &dmem);
+        done = finish_step(B, e0 + lane, *s0, row, col, value, agent_alive, exited,
+                           s0->static_goals, pts + dmem);
+    }
+    bool any_reset = false;
+    if (flags & SL_STEP_AUTO_RESET) {
+        uint32_t todo = __ballot_sync(FULL, done);
+        any_reset = todo != 0;
+        while (todo != 0) {
+            const int w = __ffs(todo) - 1;
+            todo &= todo - 1;
+            warp_reset_env(B, sstate + w, sboard + w * cells, sgoals + w * cells, stables + w * 72,
+                           lane);
+        }
+    }
+    return any_reset;
+}
+
+// SafeLifeEnv.step, one warp per env (safelife_env.py:148-201): single-pass
+// variant, one CTA per group of 8 envs.  Used for ragged / unaligned batches
+// (scalar copies instead of bulk copies) and for batches too small to pipeline.
 //   phase A  warp w: execute_actions and advance_board of env w on bit planes
-//            (+ goals, points)
-//   phase B  warp 0, lane w: update_exit_colors, reward / done, episode
-//            counters of env w; then auto-reset of finished envs
-__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, 4)
+//   phase B  warp 0, lane w: exit colours, reward / done, counters, auto-reset
+__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, 5)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
-                int bulk_ok, int flags) {
+                int bulk_ok, int flags, int first_group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int H = B.H, W = B.W, cells = H * W;
+    const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e0 = blockIdx.x * WARP_ENVS_PER_CTA;
+    const int e0 = (first_group + blockIdx.x) * WARP_ENVS_PER_CTA;
     const int nenv = min(WARP_ENVS_PER_CTA, B.n_envs - e0);
     const int group_bytes = nenv * cells * 2, state_bytes = nenv * 96;
     uint64_t *bar = (uint64_t *)smem_raw;
@@ -443,113 +607,19 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
         copy_slabs(sboard, gboard, group_bytes);
         copy_slabs(sgoals, ggoals, group_bytes);
     }
+    const int action = warp < nenv ? actions[e0 + warp] : 0;
     __syncthreads();                      // mbarrier init / fallback copy visible
     if (bulk) mbar_wait(bar, 0);
 
-    const bool have_env = warp < nenv;
-    SlEnvState *st = sstate + warp;
-    uint16_t *board = sboard + warp * cells;
-    uint16_t *goals = sgoals + warp * cells;
-
-    // ---- phase A: advance_board on bit planes, env = warp
     bool goals_dirty = false;
-    if (have_env) {
-        const uint64_t thr = st->spawn_thr;
-        u128 state = {st->rng[0], st->rng[1]};
-        const u128 inc = {st->rng[2], st->rng[3]};
-        const uint64_t state_lo0 = state.lo;
-        int sg = st->static_goals;
-        int delta = 0;                    // change of sum(table * alive_counts), this lane
-        // points table of the level: looked up in global memory, and only for
-        // cells that changed (dead cells not at all unless its "empty" column counts)
-        const int32_t *table = B.pool_table + (size_t)st->level_id * 72;
-        const bool dead_counts = st->empty_points != 0;
-
-        // execute_actions (advance_board.c:217-300): lane 0 acts, lanes 0-3 account
-        // for the (at most four) cells it can touch
-        const int action = actions[e0 + warp];
-        int row = st->loc_row, col = st->loc_col;
-        if (row >= 0 && action != 0) {
-            const ActionCells ac = action_cells(H, W, row, col, action);
-            const int idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
-            const uint32_t before = lane < 4 ? board[idx] : 0u;
-            __syncwarp();
-            if (lane == 0) {
-                agent_action_at(board, ac, row, col, action);
-                st->loc_row = row;
-                st->loc_col = col;
-            }
-            __syncwarp();
-            if (lane < 4 && !(lane == 3 && ac.i3 == ac.i2)) {
-                const uint32_t after = board[idx];
-                if (after != before) {
-                    const uint32_t g = goals[idx];
-                    delta += cell_points(after, g, table, dead_counts) -
-                             cell_points(before, g, table, dead_counts);
-                }
-            }
-        }
-
-        const Torus t = make_torus(H, W, lane);
-        RowPlanes p = load_row_planes(board, lane, W, t.wmask);
-        RowDelta d = stencil_row(t, p);
-        uint32_t spawned = warp_spawn_draws(state, inc, thr, d.cand, lane);
-        apply_row(p, d, spawned, board, lane, W, goals, table, &delta, dead_counts);
-        if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
-            RowPlanes gp = load_row_planes(goals, lane, W, t.wmask);
-            RowDelta gd = stencil_row(t, gp);
-            uint32_t gspawned = warp_spawn_draws(state, inc, thr, gd.cand, lane);
-            uint32_t gchanged = apply_row(gp, gd, gspawned, goals, lane, W);
-            if (sg == 0) sg = __any_sync(FULL, (gchanged | gp.S) != 0) ? 2 : 1;
-            goals_dirty = true;
-            __syncwarp();
-        }
-        int pts;
-        if (sg == 1) {
-            pts = st->count_points + __reduce_add_sync(FULL, delta);
-        } else {   // dynamic goals: recount (planes re-read: the board slab is final here)
-            RowPlanes q = load_row_planes(board, lane, W, t.wmask);
-            pts = warp_points(q, goals, lane, W, t.wmask, table, dead_counts);
-        }
-        if (lane == 0) {
-            st->count_points = pts;
-            st->static_goals = (uint8_t)sg;
-            if (state.lo != state_lo0) {   // the LCG is a bijection: lo changes iff draws happened
-                st->rng[0] = state.hi;
-                st->rng[1] = state.lo;
-            }
-        }
-    }
+    if (warp < nenv)
+        goals_dirty = step_phase_a(B, sstate + warp, sboard + warp * cells, sgoals + warp * cells,
+                                   action, lane);
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
     int any_goals_dirty = __syncthreads_or(goals_dirty);
     if (warp != 0) return;
 
-    // ---- phase B: exit colours, reward / done, counters; env = lane of warp 0
-    bool done = false;
-    if (lane < nenv) {
-        SlEnvState *s0 = sstate + lane;
-        uint16_t *bd = sboard + lane * cells;
-        const uint16_t *gl = sgoals + lane * cells;
-        const int lvl = s0->level_id;
-        bool agent_alive, exited;
-        int dmem;
-        const int row = s0->loc_row, col = s0->loc_col, pts = s0->count_points;
-        const int value = exit_update(bd, gl, W, row, col, pts, *s0,
-                                      B.pool_exits + (size_t)lvl * B.max_exits,
-                                      B.pool_table + (size_t)lvl * 72, &agent_alive, &exited, &dmem);
-        done = finish_step(B, e0 + lane, *s0, row, col, value, agent_alive, exited,
-                           s0->static_goals, pts + dmem);
-    }
-    if (flags & SL_STEP_AUTO_RESET) {
-        uint32_t todo = __ballot_sync(FULL, done);
-        any_goals_dirty |= todo != 0;
-        while (todo != 0) {
-            const int w = __ffs(todo) - 1;
-            todo &= todo - 1;
-            warp_reset_env(B, sstate + w, sboard + w * cells, sgoals + w * cells, stables + w * 72,
-                           lane);
-        }
-    }
+    any_goals_dirty |= step_phase_b(B, e0, nenv, sstate, sboard, sgoals, stables, flags, lane);
     fence_async_smem();
     __syncwarp();
     if (bulk) {
@@ -568,13 +638,127 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     }
 }
 
-inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
-                                 cudaStream_t st) {
+// ---- persistent, warp-specialised, double-buffered variant ----------------------
+// One CTA per SM slot loops over groups of 8 envs (group g, g + grid, ...).
+// Warps 0-7 are stencil warps (phase A of env w of the current group); warp 8
+// is the scalar warp: it issues the bulk loads two groups ahead, waits for the
+// 8 stencil warps of a group on an mbarrier, runs phase B for the group's 8
+// envs on 8 lanes, and issues the bulk stores.  Stencil warps never wait for
+// each other: the TMA head and the scalar tail of one group overlap the
+// stencil work of the next.
+constexpr int PIPE_STAGES = 2;
+constexpr int PIPE_THREADS = (WARP_ENVS_PER_CTA + 1) * 32;
+constexpr int PIPE_SMEM_HEAD = 64;    // full[2], done[2] mbarriers + dirty flags
+
+__host__ __device__ inline int pipe_stage_bytes(int cells) {
+    return WARP_SMEM_STATE + 2 * warp_slab_stride(cells);
+}
+
+inline size_t pipe_smem_bytes(int cells) {
+    return PIPE_SMEM_HEAD + WARP_SMEM_TABLES + PIPE_STAGES * (size_t)pipe_stage_bytes(cells) +
+           WARP_SMEM_PAD;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(PIPE_THREADS, 4)
+k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
+                int flags, int n_groups) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
-    const int grid = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group_bytes = WARP_ENVS_PER_CTA * cells * 2;
+    uint64_t *full = (uint64_t *)smem_raw;            // [2] loads of a stage landed
+    uint64_t *fin = full + PIPE_STAGES;               // [2] the 8 stencil warps are through
+    volatile uint8_t *dirty = (volatile uint8_t *)(fin + PIPE_STAGES);   // [2][8] goals rewritten
+    int32_t *stables = (int32_t *)(smem_raw + PIPE_SMEM_HEAD);
+    unsigned char *stages = smem_raw + PIPE_SMEM_HEAD + WARP_SMEM_TABLES;
+    const int stage_bytes = pipe_stage_bytes(cells);
+    auto stage_state = [&](int s) { return (SlEnvState *)(stages + s * stage_bytes); };
+    auto stage_board = [&](int s) { return (uint16_t *)(stages + s * stage_bytes + WARP_SMEM_STATE); };
+    auto stage_goals = [&](int s) {
+        return (uint16_t *)(stages + s * stage_bytes + WARP_SMEM_STATE + warp_slab_stride(cells));
+    };
+    auto issue_load = [&](int s, int g) {
+        const size_t e0 = (size_t)g * WARP_ENVS_PER_CTA;
+        mbar_expect_tx(full + s, 2u * group_bytes + WARP_SMEM_STATE);
+        bulk_load(stage_state(s), B.state + e0, WARP_SMEM_STATE, full + s);
+        bulk_load(stage_board(s), B.board + e0 * cells, group_bytes, full + s);
+        bulk_load(stage_goals(s), B.goals + e0 * cells, group_bytes, full + s);
+    };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PIPE_STAGES; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(fin + s, WARP_ENVS_PER_CTA);
+        }
+    }
+    __syncthreads();
+    const int first = blockIdx.x, stride = gridDim.x;
+
+    if (warp == WARP_ENVS_PER_CTA) {
+        // ---- scalar warp: loads, phase B, stores
+        if (lane == 0)
+            for (int s = 0; s < PIPE_STAGES; s++)
+                if (first + s * stride < n_groups) issue_load(s, first + s * stride);
+        int it = 0;
+        for (int g = first; g < n_groups; g += stride, it++) {
+            const int s = it & 1, parity = (it >> 1) & 1;
+            mbar_wait(fin + s, parity);
+            const int e0 = g * WARP_ENVS_PER_CTA;
+            bool goals_dirty = lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
+            goals_dirty |= step_phase_b(B, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
+                                        stage_goals(s), stables, flags, lane);
+            const bool any_dirty = __any_sync(FULL, goals_dirty);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(B.board + (size_t)e0 * cells, stage_board(s), group_bytes);
+                if (any_dirty) bulk_store(B.goals + (size_t)e0 * cells, stage_goals(s), group_bytes);
+                bulk_store(B.state + e0, stage_state(s), WARP_SMEM_STATE);
+                bulk_commit_and_wait_read();       // the stage may be overwritten after this
+                const int gn = g + PIPE_STAGES * stride;
+                if (gn < n_groups) issue_load(s, gn);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- stencil warp w: phase A of env w of every group of this CTA
+        int it = 0;
+        for (int g = first; g < n_groups; g += stride, it++) {
+            const int s = it & 1, parity = (it >> 1) & 1;
+            const int action = actions[g * WARP_ENVS_PER_CTA + warp];
+            mbar_wait(full + s, parity);
+            const bool gd = step_phase_a(B, stage_state(s) + warp, stage_board(s) + warp * cells,
+                                         stage_goals(s) + warp * cells, action, lane);
+            if (lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fin + s);
+        }
+    }
+}
+
+inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
+                                 int sm_count, cudaStream_t st) {
+    const int cells = B.H * B.W;
+    const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
+    const int full_groups = B.n_envs / WARP_ENVS_PER_CTA;
     const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
-    k_env_step_warp<<<grid, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(
-        B, actions, bulk_ok, flags);
+    // pipelining pays once a CTA slot sees more than one group
+    const int slots = sm_count * 4;
+    int piped = 0;
+    if (bulk_ok && full_groups > slots) {
+        piped = full_groups;
+        const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
+        const int grid = (full_groups + per_cta - 1) / per_cta;
+        k_env_step_pipe<<<grid, PIPE_THREADS, pipe_smem_bytes(cells), st>>>(B, actions, flags, piped);
+    }
+    if (groups > piped)
+        k_env_step_warp<<<groups - piped, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(
+            B, actions, bulk_ok, flags, piped);
 }
 
 inline bool warp_advance_supports(int H, int W) {

@@ -245,6 +245,49 @@ class BatchedSafeLifeEnv(object):
                 self._batch_ref, self._actions.data_ptr(), self.kernel,
                 _lib.SL_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
 
+    def enable_host_io(self):
+        """
+        Allocate pinned host buffers that the step kernel reads / writes in place
+        (zero-copy over PCIe: pinned memory is device-addressable under UVA), for
+        callers whose policy lives on the host: see step_host().
+        """
+        n = self.num_envs
+        self._host = {
+            "actions": torch.zeros(n, dtype=torch.uint8).pin_memory(),
+            "reward": torch.zeros(n, dtype=torch.float32).pin_memory(),
+            "done": torch.zeros(n, dtype=torch.uint8).pin_memory(),
+            "success": torch.zeros(n, dtype=torch.uint8).pin_memory(),
+            "times_up": torch.zeros(n, dtype=torch.uint8).pin_memory(),
+        }
+        fields = {name: getattr(self._batch, name) for name, _ in _lib.SlEnvBatch._fields_}
+        for k in ("reward", "done", "success", "times_up"):
+            fields[k] = self._host[k].data_ptr()
+        self._batch_host = _lib.SlEnvBatch(**fields)
+        self._batch_host_ref = ctypes.byref(self._batch_host)
+        self._host_np = {k: v.numpy() for k, v in self._host.items()}
+        self._host_actions_ptr = self._host["actions"].data_ptr()
+        return self._host_np
+
+    def step_host(self, actions, auto_reset=None):
+        """
+        One step with HOST buffers end to end: `actions` (array-like [N], values
+        0..8) are placed in the pinned action buffer, the kernel reads them and
+        writes reward / done / success / times_up straight into pinned host memory,
+        and the call returns after the step has completed.  Returns numpy views
+        (reward float32[N], done uint8[N]) that the next call overwrites.
+        """
+        if getattr(self, "_host", None) is None:
+            self.enable_host_io()
+        h = self._host_np
+        if actions is not h["actions"]:
+            np.copyto(h["actions"], actions, casting="unsafe")
+        auto = self.auto_reset if auto_reset is None else auto_reset
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_env_step_sync(
+                self._batch_host_ref, self._host_actions_ptr, self.kernel,
+                _lib.SL_STEP_AUTO_RESET if auto else 0, self._stream()))
+        return h["reward"], h["done"]
+
     def step(self, actions):
         assert self._has_reset, "Game state is not initialized."
         self.step_physics(actions, self.auto_reset)

@@ -210,3 +210,62 @@ def test_full_size_properties(kernel):
         tot += r
     assert np.array_equal(ora.board, b_all[idx])
     assert np.array_equal(tot, r_all[idx])
+
+
+def test_step_host_zero_copy_matches_device_path():
+    levels = gu.levels_of(gu.load_traj("procgen25spawn"))
+    from safelife_b200.env import BatchedSafeLifeEnv
+    n = len(levels)
+    rng = np.stack([orc.rng_from_seed(i) for i in range(n)])
+    a = BatchedSafeLifeEnv(levels, n, auto_reset=True, time_limit=25)
+    b = BatchedSafeLifeEnv(levels, n, auto_reset=True, time_limit=25)
+    a.set_rng_state(rng)
+    b.set_rng_state(rng)
+    a.reset()
+    b.reset()
+    acts = np.random.default_rng(9).integers(0, 9, (60, n))
+    for t in range(60):
+        a.step_physics(acts[t], auto_reset=True)
+        r, d = b.step_host(acts[t])
+        assert np.array_equal(r, a._t["reward"].cpu().numpy())
+        assert np.array_equal(d, a._t["done"].cpu().numpy())
+        assert np.array_equal(a.board.cpu().numpy(), b.board.cpu().numpy())
+    assert d.dtype == np.uint8 and r.dtype == np.float32
+
+
+@pytest.mark.parametrize("n", [592 * 8 + 8, 592 * 8 * 2 + 13, 20011])
+def test_pipelined_kernel_large_batches_vs_oracle(n):
+    """Batches large enough for the persistent pipelined kernel (plus a ragged tail)."""
+    rs = np.random.default_rng(n)
+    base = _random_levels(rs, 64, 25, 25)
+    levels = [base[i % 64] for i in range(n)]
+    rng = np.stack([orc.rng_from_seed(i % 997) for i in range(n)])
+    from safelife_b200.env import BatchedSafeLifeEnv
+    env = BatchedSafeLifeEnv(base, n, time_limit=9, auto_reset=True, kernel=2)
+    env.set_rng_state(rng)
+    env.reset()
+    idx = np.unique(np.concatenate([np.arange(0, n, 211), [n - 1, n - 2, n - 9, 4735, 4736, 4744]]))
+    idx = idx[idx < n]
+    ora = orc.OracleEnv([levels[i] for i in idx], list(rng[idx]), time_limit=9)
+    live = np.ones(len(idx), dtype=bool)     # the oracle has no auto-reset: follow an env
+    for t in range(9):                        # until its first done
+        a = rs.integers(0, 9, n)
+        r0, d0 = ora.step(a[idx].astype(np.int64))
+        env.step_physics(a, auto_reset=True)
+        assert np.array_equal(env._t["reward"].cpu().numpy()[idx][live], r0[live]), t
+        assert np.array_equal(env._t["done"].cpu().numpy()[idx].astype(bool)[live], d0[live]), t
+        cont = live & ~d0
+        assert np.array_equal(env.board.cpu().numpy()[idx][cont], ora.board[cont]), t
+        assert np.array_equal(env.goals.cpu().numpy()[idx][cont], ora.goals[cont]), t
+        assert np.array_equal(env.rng_state[idx][cont], ora.rng[cont]), t
+        if t < 8:
+            live = cont
+    assert live.sum() > len(idx) // 2 and d0[live].all()
+    # envs that ran the full episode were auto-reset once: next level, fresh state
+    lvl = env._t["level_id"].cpu().numpy()
+    sel = idx[live]
+    assert np.array_equal(lvl[sel], (sel % 64 + n) % 64)
+    fresh = orc.OracleEnv([base[l] for l in lvl[sel]], list(rng[sel]), time_limit=9)
+    assert np.array_equal(env.board.cpu().numpy()[sel], fresh.board)
+    assert np.array_equal(env.goals.cpu().numpy()[sel], fresh.goals)
+    assert env._t["num_steps"].cpu().numpy()[sel].max() == 0
