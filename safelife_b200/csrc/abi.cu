@@ -108,8 +108,11 @@ int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int 
     if (n == 0) return SL_OK;
     if (counts == nullptr && out == nullptr) return fail(SL_ERR_ARG, "null output pointer");
     if (sl::warp_advance_supports(H, W)) {
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
         sl::launch_advance_warp(in, out, counts, n, H, W, spawn_threshold(spawn_prob), n_steps,
-                                rng, st);
+                                rng, props.sm_count, st);
         return launch_status("k_advance_warp");
     }
     size_t smem = sl::generic_smem_bytes(H * W);

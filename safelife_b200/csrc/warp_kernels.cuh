@@ -22,6 +22,7 @@
 // integer pipes.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "cells.cuh"
 #include "generic_kernels.cuh"
 #include "../../include/safelife_b200.h"
@@ -207,10 +208,10 @@ __device__ __forceinline__ uint32_t two3x3(const Torus &t, uint32_t x) {
     return two | t.north(two) | t.south(two) | maj3(one, on, os);
 }
 
-// advance_board.c:34-125 on bit planes.  `slab` is the (unmodified) board the
-// planes came from: the high-byte planes are fetched from it only if needed.
-__device__ __forceinline__ RowDelta stencil_row(const Torus &t, const LowPlanes &p,
-                                                const uint16_t *slab, int r) {
+// advance_board.c:34-125 on bit planes.  `high()` supplies the high-byte planes
+// and is only called if some cell of the board may be created.
+template <class HighFn>
+__device__ __forceinline__ RowDelta stencil_planes(const Torus &t, const LowPlanes &p, HighFn high) {
     // n = alive cells in the 3x3 (centre included), as 4 bit planes
     uint32_t w = t.west(p.A), e = t.east(p.A);
     uint32_t s0 = p.A ^ w ^ e, s1 = maj3(p.A, w, e);
@@ -230,7 +231,7 @@ __device__ __forceinline__ RowDelta stencil_row(const Torus &t, const LowPlanes 
     d.cand = open & ~is3 & any_s;
     // colours / destructibility only matter where something may be created
     if (__any_sync(FULL, (d.born | d.cand) != 0)) {
-        const HighPlanes h = load_row_high(slab, r, t.W, t.wmask);
+        const HighPlanes h = high();
         d.tR = two3x3(t, p.A & h.R) | any3x3(t, p.S & h.R);
         d.tG = two3x3(t, p.A & h.G) | any3x3(t, p.S & h.G);
         d.tB = two3x3(t, p.A & h.B) | any3x3(t, p.S & h.B);
@@ -239,6 +240,13 @@ __device__ __forceinline__ RowDelta stencil_row(const Torus &t, const LowPlanes 
         d.tR = d.tG = d.tB = d.dn = 0;
     }
     return d;
+}
+
+// `slab` is the (unmodified) board the planes came from: the high-byte planes
+// are fetched from it only if needed.
+__device__ __forceinline__ RowDelta stencil_row(const Torus &t, const LowPlanes &p,
+                                                const uint16_t *slab, int r) {
+    return stencil_planes(t, p, [&] { return load_row_high(slab, r, t.W, t.wmask); });
 }
 
 // Resolve the spawn draws of one board: lane r holds its candidate mask; on
@@ -748,7 +756,12 @@ inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, in
     const int full_groups = B.n_envs / WARP_ENVS_PER_CTA;
     const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
     // pipelining pays once a CTA slot sees more than one group
-    const int slots = sm_count * 4;
+    static const int slots_per_sm = [] {
+        const char *v = getenv("SAFELIFE_B200_PIPE_SLOTS");   // tuning knob, default 4
+        int k = v ? atoi(v) : 4;
+        return k >= 1 && k <= 4 ? k : 4;
+    }();
+    const int slots = sm_count * slots_per_sm;
     int piped = 0;
     if (bulk_ok && full_groups > slots) {
         piped = full_groups;
@@ -761,12 +774,137 @@ inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, in
             B, actions, bulk_ok, flags, piped);
 }
 
-inline bool warp_advance_supports(int H, int W) {
-    (void)H; (void)W;
-    return false;   // multi-step bit-plane kernel: see k_advance_warp (to come)
+// ------------------------------------------------------------------------
+// n-step advance / life occupancy, one warp per board, the whole loop in
+// registers: advance_board_nstep (advance_board.c:128-149) and life_occupancy
+// (:153-189).  The planes live in registers for all n_steps; occupancy counts
+// are bit-sliced counters (one 10-bit vertical counter per colour and cell),
+// spilled into the int32 output every 1023 steps.  Nothing touches memory
+// inside the step loop.
+// ------------------------------------------------------------------------
+constexpr int ADV_WARPS = 4;
+constexpr int ADV_SLAB_CELLS = 32 * 32 + 32;     // one padded board per warp
+constexpr int OCC_BITS = 10;
+
+inline bool warp_advance_supports(int H, int W) { return warp_kernel_supports(H, W); }
+
+__global__ void __launch_bounds__(ADV_WARPS * 32)
+k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, int n, int H,
+               int W, uint64_t thr, int n_steps, uint64_t *__restrict__ rng) {
+    __shared__ uint16_t slabs[ADV_WARPS][ADV_SLAB_CELLS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = H * W;
+    uint16_t *slab = slabs[warp];
+    const Torus t = make_torus(H, W, lane);
+    for (int b = blockIdx.x * ADV_WARPS + warp; b < n; b += gridDim.x * ADV_WARPS) {
+        const uint16_t *src = in + (size_t)b * cells;
+        for (int i = lane; i < cells; i += 32) slab[i] = src[i];
+        __syncwarp();
+        RowPlanes p = load_row_planes(slab, lane, W, t.wmask);
+        uint32_t kept = t.wmask;              // cells that never changed keep their word
+        u128 state = {0, 0}, inc = {0, 0};
+        if (rng != nullptr) {
+            state = {rng[4 * (size_t)b], rng[4 * (size_t)b + 1]};
+            inc = {rng[4 * (size_t)b + 2], rng[4 * (size_t)b + 3]};
+        }
+        uint32_t cnt[8][OCC_BITS];
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
+        int pending = 0;
+
+        auto flush_counts = [&]() {
+            // bit-sliced counters -> counts[b][row][col][colour] (+=)
+            if (lane < H) {
+                int32_t *dst = counts + ((size_t)b * cells + (size_t)lane * W) * 8;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    uint32_t nz = 0;
+#pragma unroll
+                    for (int k = 0; k < OCC_BITS; k++) nz |= cnt[c][k];
+                    while (nz != 0) {
+                        const int j = __ffs(nz) - 1;
+                        nz &= nz - 1;
+                        int v = 0;
+#pragma unroll
+                        for (int k = 0; k < OCC_BITS; k++) v |= ((cnt[c][k] >> j) & 1u) << k;
+                        dst[j * 8 + c] += v;
+                    }
+#pragma unroll
+                    for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
+                }
+            }
+            pending = 0;
+        };
+
+        for (int s = 0; s < n_steps; s++) {
+            const LowPlanes lp = {p.A, p.D, p.F, p.P, p.I, p.S};
+            const RowDelta d = stencil_planes(t, lp, [&] { return HighPlanes{p.E, p.R, p.G, p.B}; });
+            const uint32_t spawned =
+                rng != nullptr ? warp_spawn_draws(state, inc, thr, d.cand, lane) : 0u;
+            const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
+            p.A = (p.A & keep) | fresh;
+            p.D = (p.D & keep) | (d.dn & d.born) | spawned;
+            p.R = (p.R & keep) | (d.tR & fresh);
+            p.G = (p.G & keep) | (d.tG & fresh);
+            p.B = (p.B & keep) | (d.tB & fresh);
+            p.P &= keep; p.I &= keep; p.S &= keep; p.E &= keep; p.AG &= keep;
+            p.PU &= keep; p.PL &= keep;
+            kept &= keep;
+            if (counts != nullptr) {
+                // +1 for cells ALIVE and none of AGENT | EXIT | FROZEN, by colour (:153-162)
+                const uint32_t occ = p.A & ~(p.AG | p.E | p.F);
+                if (__any_sync(FULL, occ != 0)) {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) {
+                        uint32_t carry = occ & ((c & 1) ? p.R : ~p.R) & ((c & 2) ? p.G : ~p.G) &
+                                         ((c & 4) ? p.B : ~p.B);
+                        if (__any_sync(FULL, carry != 0)) {
+#pragma unroll
+                            for (int k = 0; k < OCC_BITS; k++) {
+                                const uint32_t tmp = cnt[c][k] & carry;
+                                cnt[c][k] ^= carry;
+                                carry = tmp;
+                            }
+                        }
+                    }
+                }
+                if (++pending == (1 << OCC_BITS) - 1) flush_counts();
+            }
+        }
+        if (counts != nullptr) {
+            if (pending) flush_counts();
+        } else {
+            // cells that changed at least once are fully described by the planes
+            uint16_t *row = slab + lane * W;
+            uint32_t m = t.wmask & ~kept;
+            while (m != 0) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                row[j] = (uint16_t)(((p.A >> j) & 1u) | (((p.D >> j) & 1u) << 3) |
+                                    (((p.R >> j) & 1u) << 9) | (((p.G >> j) & 1u) << 10) |
+                                    (((p.B >> j) & 1u) << 11));
+            }
+            __syncwarp();
+            uint16_t *dst = out + (size_t)b * cells;
+            for (int i = lane; i < cells; i += 32) dst[i] = slab[i];
+        }
+        if (rng != nullptr && lane == 0) {
+            rng[4 * (size_t)b] = state.hi;
+            rng[4 * (size_t)b + 1] = state.lo;
+        }
+        __syncwarp();
+    }
 }
 
-inline void launch_advance_warp(const uint16_t *, uint16_t *, int32_t *, int, int, int, uint64_t,
-                                int, uint64_t *, cudaStream_t) {}
+inline void launch_advance_warp(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int H,
+                                int W, uint64_t thr, int n_steps, uint64_t *rng, int sm_count,
+                                cudaStream_t st) {
+    int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
+    const int cap = sm_count * 8;
+    if (grid > cap) grid = cap;
+    k_advance_warp<<<grid, ADV_WARPS * 32, 0, st>>>(in, out, counts, n, H, W, thr, n_steps, rng);
+}
 
 }  // namespace sl

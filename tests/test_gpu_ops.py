@@ -194,3 +194,32 @@ def test_error_conventions(sp):
         sp.execute_actions(np.zeros((5, 5), np.uint16), np.zeros((3, 2), np.int64), [1, 2])
     with pytest.raises(ValueError):
         sp.advance_board(np.zeros((5, 5), dtype=np.uint16), 0.3, 0)
+
+
+@pytest.mark.parametrize("shape,steps", [((25, 25), 1100), ((7, 9), 2050), ((32, 32), 300),
+                                         ((40, 33), 60)])
+def test_life_occupancy_long_runs_vs_oracle(sp, shape, steps):
+    """More steps than a 10-bit occupancy counter holds (flush path) and a generic-size board."""
+    H, W = shape
+    rs = np.random.default_rng(steps)
+    n = 6
+    boards = (rs.integers(0, 65536, (n, H, W)) & rs.integers(0, 65536, (n, H, W))).astype(np.uint16)
+    boards[0] = 0
+    boards[0, 1, 1:4] = 9 | (3 << 9)          # a blinker that lives forever
+    rng = np.stack([orc.rng_from_seed(50 + i) for i in range(n)])
+    want_rng = rng.copy()
+    want = np.stack([orc.life_occupancy(boards[i], 0.3, steps, want_rng[i]) for i in range(n)])
+    got = sp.life_occupancy_batch(boards, 0.3, steps, rng)
+    assert np.array_equal(got, want)
+    assert np.array_equal(rng, want_rng)
+    assert got[0, 1, 2, 3] == steps           # the blinker's centre is alive after every step
+
+
+def test_advance_board_many_steps_vs_oracle(sp):
+    rs = np.random.default_rng(77)
+    boards = (rs.integers(0, 65536, (10, 26, 26)) & rs.integers(0, 65536, (10, 26, 26))).astype(np.uint16)
+    rng = np.stack([orc.rng_from_seed(i) for i in range(10)])
+    want_rng = rng.copy()
+    want = np.stack([orc.advance_board(boards[i], 0.3, 150, want_rng[i]) for i in range(10)])
+    got = sp.advance_board_batch(boards, 0.3, 150, rng)
+    assert np.array_equal(got, want) and np.array_equal(rng, want_rng)
