@@ -148,6 +148,7 @@ class BatchedSafeLifeEnv(object):
                 "level_id": state[:, 10], "num_steps": state[:, 11], "old_value": state[:, 12],
                 "ep_length": state[:, 13], "ep_reward": state[:, 14:15].view(torch.float32)[:, 0],
                 "active": flags[:, 0], "static_goals": flags[:, 1],
+                "init_points": state[:, 18], "required": state[:, 19],
                 "count_points": state[:, 20],
             }
             self._views["level_id"].copy_((torch.arange(N, dtype=torch.int64) % len(p)).to(torch.int32))
@@ -300,6 +301,30 @@ class BatchedSafeLifeEnv(object):
         }
         info["board"], info["goals"], info["agent_locs"] = self.board, self.goals, self.agent_locs
         return self.get_obs(), reward, done, info
+
+    def reset_done(self, mask=None):
+        """
+        Reset the envs whose mask byte is set (default: the `done` flags of the last
+        step) onto their next level, as BaseAlgo.act_on_envs does after a done
+        (training/base_algo.py:231-236).  Episode totals stay readable.  Returns obs.
+        """
+        mask = self._t["done"] if mask is None else mask.to(torch.uint8)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_env_reset(
+                self._batch_ref, mask.data_ptr(), None,
+                _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS, self._stream()))
+        return self.get_obs()
+
+    def side_effect_cells(self, baseline):
+        """
+        SimpleSideEffectPenalty's cell count against `baseline` (uint16/int16 [N,H,W]
+        device tensor): env_wrappers.py:177-213 with ignore_reward_cells=False.
+        """
+        out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_side_effect_cells(
+                self._batch_ref, baseline.data_ptr(), out.data_ptr(), self._stream()))
+        return out
 
     def render(self, mode="ansi"):
         raise NotImplementedError("rendering is out of scope (SURVEY.md section 2)")

@@ -106,6 +106,63 @@ def run_episode(game, seed, time_limit, view_shape, channels, action_seed):
     return rec, log, env.game
 
 
+def run_wrapped_episode(game, seed, time_limit, action_seed, se_penalty, exit_difficulty):
+    """One episode through the training wrapper stack of training/env_factory.py:274-283."""
+    from safelife import env_wrappers
+    game.seed = seed
+    env = SafeLifeEnv(iter([game]), time_limit=time_limit, view_shape=(5, 5),
+                      output_channels=None, should_calculate_side_effects=False)
+    env = env_wrappers.MovementBonusWrapper(env, as_penalty=True)
+    env = env_wrappers.ExtraExitBonus(env)
+    env = env_wrappers.SimpleSideEffectPenalty(env, baseline="starting-state",
+                                               penalty_coef=se_penalty)
+    env = env_wrappers.MinPerformanceScheduler(env, min_performance_fraction=exit_difficulty)
+    rec = level_record(game)        # before reset: the scheduler rescales min_performance
+    env.reset()
+    rec["rng_init"] = orc.rng_from_generator(game.rng)
+    arng = np.random.default_rng(action_seed)
+    log = {"action": [], "reward": [], "done": []}
+    for t in range(time_limit):
+        a = int(arng.integers(0, 9))
+        obs, reward, done, info = env.step(a)
+        log["action"].append(a)
+        log["reward"].append(np.float64(reward))
+        log["done"].append(bool(done))
+        if done:
+            break
+    return rec, log
+
+
+def group_wrapped(name, paths, limit, time_limit, seed0, se_penalty, exit_difficulty,
+                  min_performance=None):
+    recs, logs = [], []
+    ss = np.random.SeedSequence(seed0)
+    for path in paths:
+        for fname, data in static_games(path, limit):
+            game = SafeLifeGame.loaddata(data, auto_cls=False)
+            if min_performance is not None:
+                game.min_performance = min_performance
+                game._init_data = game.serialize()
+            rec, log = run_wrapped_episode(game, ss.spawn(1)[0], time_limit,
+                                           len(recs) + 1000 * seed0, se_penalty, exit_difficulty)
+            recs.append(rec)
+            logs.append(log)
+    L, T = len(recs), max(len(lg["action"]) for lg in logs)
+    out = {k: np.stack([r[k] for r in recs]) for k in recs[0]}
+    out["length"] = np.array([len(lg["action"]) for lg in logs], dtype=np.int32)
+    for key, dtype in (("action", np.uint8), ("reward", np.float64), ("done", np.uint8)):
+        arr = np.zeros((L, T), dtype=dtype)
+        for i, lg in enumerate(logs):
+            arr[i, :len(lg[key])] = np.asarray(lg[key], dtype=dtype)
+        out[key] = arr
+    out["time_limit"] = np.int32(time_limit)
+    out["se_penalty"] = np.float64(se_penalty)
+    out["exit_difficulty"] = np.float64(exit_difficulty)
+    path = os.path.join(HERE, "wrapped_%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print("wrote", path, "levels", L, "max steps", T, os.path.getsize(path) // 1024, "KiB")
+
+
 def save_group(name, recs, logs, time_limit, view_shape, channels):
     L = len(recs)
     T = max(len(lg["action"]) for lg in logs)
@@ -334,6 +391,10 @@ def main():
     if want("navtrain"):
         group_static("navtrain", ["training/navigation.npz"], 8, 150, (25, 25),
                      TRAIN_CHANNELS, seed0=14)
+    if want("wrapped"):
+        group_wrapped("v1.0", v10[:6], 3, 120, seed0=21, se_penalty=0.7, exit_difficulty=0.5)
+        group_wrapped("mazes", ["mazes/*.npz"], None, 600, seed0=22, se_penalty=0.25,
+                      exit_difficulty=1.0, min_performance=0.0)
     if want("procgen25"):
         # BASELINE config 1: 25x25 append-still-easy, SeedSequence(0).spawn(1)[0], 1000 steps
         group_procgen("procgen25", "random/append-still-easy", (25, 25), 1, 1000, (25, 25),

@@ -269,3 +269,53 @@ def test_pipelined_kernel_large_batches_vs_oracle(n):
     assert np.array_equal(env.board.cpu().numpy()[sel], fresh.board)
     assert np.array_equal(env.goals.cpu().numpy()[sel], fresh.goals)
     assert env._t["num_steps"].cpu().numpy()[sel].max() == 0
+
+
+# BASELINE.json configs 2-5 as parity cases: procgen pools generated by the
+# reference (tests/golden/make_pools.py), a strided subset replayed through the
+# oracle with RNG state compared every step.
+CONFIGS = [
+    ("append-still-25", 4096, 40),
+    ("prune-still-25", 16384, 25),
+    ("append-spawn-25", 8192, 40),
+    ("append-still-26", 2048, 30),
+    ("navigation-50", 512, 25),
+]
+
+
+@pytest.mark.parametrize("pool,n,steps", CONFIGS)
+def test_baseline_configs_vs_oracle(pool, n, steps):
+    path = os.path.join(gu.GOLDEN, "pools", pool + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("pool fixture missing")
+    from safelife_b200.env import BatchedSafeLifeEnv, seed_rng_states
+    from safelife_b200.levels import load_levels
+    levels = load_levels(path)
+    L = len(levels)
+    env = BatchedSafeLifeEnv(levels, n, auto_reset=False, time_limit=1000)
+    rng = seed_rng_states(4, n)
+    env.set_rng_state(rng)
+    env.reset()
+    idx = np.arange(0, n, max(1, n // 256))[:256]
+    ora = orc.OracleEnv([levels[i % L] for i in idx], list(rng[idx]), time_limit=1000)
+    acts = np.random.default_rng(2).integers(0, 9, (steps, n)).astype(np.uint8)
+    draws = 0
+    for t in range(steps):
+        before = ora.rng.copy()
+        r0, d0 = ora.step(acts[t, idx].astype(np.int64))
+        draws += int((before[:, 1] != ora.rng[:, 1]).sum())
+        env.step_physics(acts[t])
+        where = (pool, t)
+        assert np.array_equal(env._t["reward"].cpu().numpy()[idx], r0), where
+        assert np.array_equal(env._t["done"].cpu().numpy()[idx].astype(bool), d0), where
+        assert np.array_equal(env.rng_state[idx], ora.rng), where
+        assert np.array_equal(env.agent_locs.cpu().numpy()[idx, 0], ora.loc), where
+        if t % 5 == 4 or t == steps - 1:
+            assert np.array_equal(env.board.cpu().numpy()[idx], ora.board), where
+            assert np.array_equal(env.goals.cpu().numpy()[idx], ora.goals), where
+    sg = env._t["static_goals"].cpu().numpy()
+    assert np.array_equal(sg[idx], ora.static_goals)
+    if "spawn" in pool or "navigation" in pool:
+        assert draws > 0                      # the stochastic path was exercised
+    if "navigation" in pool:
+        assert (sg == 2).any()                # dynamic goals: two stencils per step

@@ -1,0 +1,61 @@
+"""
+Batched training wrappers (safelife_b200/wrappers.py) against rewards recorded
+from the reference's wrapper stack (env_wrappers.py via
+tests/golden/make_golden.py wrapped).  Rewards are float64 sums of exactly
+representable terms in both implementations: compared with rtol 1e-12.
+"""
+import numpy as np
+import pytest
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["v1.0", "mazes"])
+def test_training_stack_matches_reference(name):
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200 import wrappers
+    d = gu.load_npz("wrapped_%s.npz" % name)
+    levels = gu.levels_of(d)
+    L = len(levels)
+    base = BatchedSafeLifeEnv(levels, L, auto_reset=False, time_limit=int(d["time_limit"]),
+                              view_shape=(5, 5), output_channels=None)
+    base.set_rng_state(d["rng_init"])
+    env = wrappers.training_stack(base, exit_difficulty=float(d["exit_difficulty"]),
+                                  se_penalty=float(d["se_penalty"]))
+    env.reset()
+    exits = 0
+    for t in range(d["action"].shape[1]):
+        obs, reward, done, info = env.step(d["action"][:, t])
+        reward, done = reward.cpu().numpy(), done.cpu().numpy()
+        assert reward.dtype == np.float64
+        for i in np.flatnonzero(t < d["length"]):
+            assert done[i] == bool(d["done"][i, t]), (name, i, t)
+            assert np.isclose(reward[i], d["reward"][i, t], rtol=1e-12, atol=1e-12), \
+                (name, i, t, reward[i], d["reward"][i, t])
+            exits += int(done[i] and not info["times_up"][i].item())
+    if name == "mazes":
+        assert exits > 0          # ExtraExitBonus was exercised
+
+
+def test_reset_done_restarts_wrapper_state():
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200 import wrappers
+    levels = gu.levels_of(gu.load_npz("wrapped_mazes.npz"))
+    n = 6
+    base = BatchedSafeLifeEnv(levels, n, auto_reset=False, time_limit=5, view_shape=(5, 5))
+    env = wrappers.training_stack(base, se_penalty=1.0)
+    env.reset()
+    for t in range(5):
+        obs, reward, done, info = env.step(np.full(n, 6))      # toggle: creates side effects
+    assert done.all()
+    assert (env.env.last_side_effect > 0).any()
+    obs = env.reset_done()
+    assert obs.shape[0] == n
+    assert base._t["num_steps"].tolist() == [0] * n
+    assert base._t["level_id"].tolist() == [(i + n) % len(levels) for i in range(n)]
+    assert env.env.last_side_effect.tolist() == [0] * n
+    assert (env.env.baseline_board == base._t["board"]).all()
+    with pytest.raises(ValueError):
+        wrappers.MovementBonusWrapper(BatchedSafeLifeEnv(levels, 2, auto_reset=True))
