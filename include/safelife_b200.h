@@ -178,7 +178,7 @@ typedef struct SlEnvBatch {
  * update_exit_colors -> reward / done / episode counters.  actions is
  * uint8[n_envs] (device), values as the reference's Discrete(9).
  * kernel: 0 = pick automatically, 1 = generic CTA-per-env kernel,
- * 2 = warp-per-env bit-plane kernel (requires H, W <= 32).
+ * 2 = warp-per-env bit-plane kernel (requires H, W <= 64).
  * flags: SL_STEP_AUTO_RESET resets every env that finished in this step in
  * the same call, exactly as sl_env_reset(batch, done, NULL,
  * SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS) would (the batched form of

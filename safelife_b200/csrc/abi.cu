@@ -361,14 +361,22 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
     cudaStream_t st = (cudaStream_t)stream;
     bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
     if (kernel == 2 && !warp_ok)
-        return fail(SL_ERR_ARG, "warp kernel needs H, W <= %d", sl::WARP_MAX_DIM);
+        return fail(SL_ERR_ARG, "warp kernel needs 3 <= H, W <= %d", sl::WARP_MAX_DIM);
     if (flags & ~SL_STEP_AUTO_RESET) return fail(SL_ERR_ARG, "unknown step flags");
     if (kernel == 2 || (kernel == 0 && warp_ok)) {
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
-        size_t smem = sl::pipe_smem_bytes(batch->H * batch->W);
-        rc = prepare_smem(sl::k_env_step_pipe, smem);
+        const int cells = batch->H * batch->W;
+        if (sl::warp_kernel_is_narrow(batch->H, batch->W)) {
+            rc = prepare_smem(sl::k_env_step_pipe, sl::pipe_smem_bytes(cells));
+            if (rc) return rc;
+            rc = prepare_smem(sl::k_env_step_warp<sl::Narrow>,
+                              sl::warp_step_smem_bytes<sl::Narrow>(cells));
+        } else {
+            rc = prepare_smem(sl::k_env_step_warp<sl::Wide>,
+                              sl::warp_step_smem_bytes<sl::Wide>(cells));
+        }
         if (rc) return rc;
         sl::launch_env_step_warp(*batch, actions, flags, props.sm_count, st);
         return launch_status("k_env_step_warp");

@@ -1,25 +1,31 @@
-// warp_kernels.cuh -- warp-per-env bit-plane kernels (boards up to 32x32).
+// warp_kernels.cuh -- warp-per-env bit-plane kernels.
 //
-// The fast path for the BASELINE shapes (25x25, 26x26).  One warp owns one
-// env; lane r owns board row r.  A CTA of 8 warps stages the 8 consecutive env
-// slabs it owns ([8][H][W] uint16, 16-byte aligned as a group for any H, W)
-// from HBM into shared memory with 128-bit loads, and writes them back the
-// same way.  Inside the warp:
+// The fast path.  One warp owns one env; a CTA of 8 warps stages the 8
+// consecutive env slabs it owns ([8][H][W] uint16, 16-byte aligned as a group
+// for any H, W) and their 8 state records from HBM into shared memory with
+// bulk asynchronous copies (TMA) and writes them back the same way.  Inside
+// the warp:
 //
-//   1. lane r reads its row (W uint16) and transposes it in registers into 16
-//      bit-plane words (bit j of plane p = bit p of cell j) with a 4-stage
-//      butterfly: one byte-permute stage and three masked shift stages;
+//   1. each lane reads the rows it owns and transposes them in registers into
+//      bit-plane words (bit j of plane p = bit p of cell j): one byte-permute
+//      stage and three masked shift stages per 32 cells;
 //   2. the 3x3 toroidal neighbourhood aggregate of advance_board.c:34-125 is
 //      evaluated on whole rows at once with bitwise adders: horizontal
 //      neighbours are 1-bit rotations of the row word, vertical neighbours come
-//      from lanes r-1 / r+1 by warp shuffle;
+//      from neighbouring lanes by warp shuffle;
 //   3. the spawn draws of the reference (one PCG64 double per qualifying cell
 //      in raster order, advance_board.c:115) are produced 32 at a time by
 //      leapfrogging the LCG across lanes and handed to the rows by prefix sum;
-//   4. only cells that changed are written back into the uint16 slab.
+//   4. only cells that changed are written back into the uint16 slab, and the
+//      points sum is updated incrementally from those cells.
 //
-// No tensor cores: the path is integer / bitwise and bound by HBM and the
-// integer pipes.
+// Two geometries share all of that code through templates:
+//   Narrow  H, W <= 32: lane r owns row r, a row is one 32-bit word
+//           (the BASELINE shapes 25x25 / 26x26);
+//   Wide    H, W <= 64: lane r owns rows r and r + 32, a row is a 64-bit word
+//           (50x50 navigation boards).
+//
+// No tensor cores: the path is integer / bitwise.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -29,12 +35,16 @@
 
 namespace sl {
 
-constexpr int WARP_MAX_DIM = 32;
+constexpr int WARP_MAX_DIM = 64;
+constexpr int WARP_NARROW_DIM = 32;
 constexpr int WARP_ENVS_PER_CTA = 8;
 constexpr unsigned FULL = 0xffffffffu;
 
 inline bool warp_kernel_supports(int H, int W) {
     return H >= 3 && W >= 3 && H <= WARP_MAX_DIM && W <= WARP_MAX_DIM;
+}
+inline bool warp_kernel_is_narrow(int H, int W) {
+    return H <= WARP_NARROW_DIM && W <= WARP_NARROW_DIM;
 }
 
 // Per-lane leapfrog constants (A^(l+1), G_(l+1)); global memory so that each
@@ -42,13 +52,35 @@ inline bool warp_kernel_supports(int H, int W) {
 __device__ const uint64_t d_lane_a[32][2] = SL_PCG_LANE_A;
 __device__ const uint64_t d_lane_g[32][2] = SL_PCG_LANE_G;
 
-// Bit planes of one board row that the physics reads or rewrites.
-struct RowPlanes {
-    uint32_t A, D, F, P, I, S, E, R, G, B;   // stencil inputs
-    uint32_t PU, PL, AG;                      // pushable, pullable, agent
+// ------------------------------------------------------------------ planes
+// A plane is "one bit per cell for the rows this lane owns": uint32_t in the
+// narrow geometry, P2 (two 64-bit rows) in the wide one.
+struct P2 {
+    uint64_t a, b;   // row `lane`, row `lane + 32`
+};
+__device__ __forceinline__ P2 operator&(P2 x, P2 y) { return {x.a & y.a, x.b & y.b}; }
+__device__ __forceinline__ P2 operator|(P2 x, P2 y) { return {x.a | y.a, x.b | y.b}; }
+__device__ __forceinline__ P2 operator^(P2 x, P2 y) { return {x.a ^ y.a, x.b ^ y.b}; }
+__device__ __forceinline__ P2 operator~(P2 x) { return {~x.a, ~x.b}; }
+__device__ __forceinline__ bool nonzero(uint32_t x) { return x != 0; }
+__device__ __forceinline__ bool nonzero(P2 x) { return (x.a | x.b) != 0; }
+__device__ __forceinline__ int popc(uint32_t x) { return __popc(x); }
+__device__ __forceinline__ int popc(uint64_t x) { return __popcll(x); }
+__device__ __forceinline__ int lowest(uint32_t x) { return __ffs(x) - 1; }
+__device__ __forceinline__ int lowest(uint64_t x) { return __ffsll((long long)x) - 1; }
+
+template <class P> struct LowPlanesT { P A, D, F, P_, I, S; };   // bits 0, 3, 4, 5, 6, 7
+template <class P> struct HighPlanesT { P E, R, G, B; };         // bits 8, 9, 10, 11
+template <class P> struct RowDeltaT {
+    P die;          // alive cells that die
+    P born;         // dead cells that come alive through n == 3
+    P cand;         // dead cells that take a spawn draw
+    P tR, tG, tB;   // inherited colour bits of a new cell
+    P dn;           // births that are DESTRUCTIBLE
 };
 
-// 16 cells-pairs words -> 16 plane words.  x[k] = cell(k) | cell(k+16) << 16.
+// ------------------------------------------------------ 32-cell transposes
+// 16 cell-pair words -> 16 plane words.  x[k] = cell(k) | cell(k+16) << 16.
 __device__ __forceinline__ void transpose16(uint32_t (&x)[16]) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {            // bytes: cell bit 3 <-> plane bit 3
@@ -78,31 +110,6 @@ __device__ __forceinline__ void transpose16(uint32_t (&x)[16]) {
     }
 }
 
-// Row r of a slab (shared memory) -> plane words.  Reads 32 cells starting at
-// the row (the slab is padded so that this never leaves shared memory) and
-// masks the planes to the W valid columns; lanes past the last row get zeros
-// through their empty wmask.
-__device__ __forceinline__ RowPlanes load_row_planes(const uint16_t *slab, int r, int W,
-                                                     uint32_t wmask) {
-    uint32_t x[16];
-    const uint16_t *row = slab + r * W;
-#pragma unroll
-    for (int k = 0; k < 16; k++) x[k] = __byte_perm(row[k], row[k + 16], 0x5410);
-    transpose16(x);
-    RowPlanes p;
-    p.A = x[0] & wmask; p.AG = x[1] & wmask; p.PU = x[2] & wmask; p.D = x[3] & wmask;
-    p.F = x[4] & wmask; p.P = x[5] & wmask; p.I = x[6] & wmask; p.S = x[7] & wmask;
-    p.E = x[8] & wmask; p.R = x[9] & wmask; p.G = x[10] & wmask; p.B = x[11] & wmask;
-    p.PL = x[15] & wmask;
-    return p;
-}
-
-// The common path only needs the planes of the low byte of the cell word
-// (ALIVE, DESTRUCTIBLE, FROZEN, PRESERVING, INHIBITING, SPAWNING); the high
-// byte (EXIT, colours) matters only where a cell may be created.
-struct LowPlanes { uint32_t A, D, F, P, I, S; };
-struct HighPlanes { uint32_t E, R, G, B; };
-
 // 8 words of 4 bytes (cells i, i+8, i+16, i+24) -> 8 plane words (index = bit).
 __device__ __forceinline__ void transpose8(uint32_t (&x)[8]) {
 #pragma unroll
@@ -126,232 +133,340 @@ __device__ __forceinline__ void transpose8(uint32_t (&x)[8]) {
     }
 }
 
-// selector 0x6240 gathers the low bytes, 0x7351 the high bytes of 4 cells
+// Planes of the low (SEL 0x6240) or high (SEL 0x7351) byte of 32 consecutive
+// cells starting at `cells` (shared memory; callers pad their slabs so that the
+// read never leaves it).  x[p] = plane of bit p (low) / bit 8 + p (high).
 template <unsigned SEL>
-__device__ __forceinline__ void load_row_bytes(const uint16_t *slab, int r, int W,
-                                               uint32_t (&x)[8]) {
-    const uint16_t *row = slab + r * W;
+__device__ __forceinline__ void planes32(const uint16_t *cells, uint32_t (&x)[8]) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        uint32_t a = __byte_perm(row[k], row[k + 16], 0x5410);
-        uint32_t b = __byte_perm(row[k + 8], row[k + 24], 0x5410);
+        uint32_t a = __byte_perm(cells[k], cells[k + 16], 0x5410);
+        uint32_t b = __byte_perm(cells[k + 8], cells[k + 24], 0x5410);
         x[k] = __byte_perm(a, b, SEL);
     }
-}
-
-__device__ __forceinline__ LowPlanes load_row_low(const uint16_t *slab, int r, int W,
-                                                  uint32_t wmask) {
-    uint32_t x[8];
-    load_row_bytes<0x6240>(slab, r, W, x);
     transpose8(x);
-    return {x[0] & wmask, x[3] & wmask, x[4] & wmask, x[5] & wmask, x[6] & wmask, x[7] & wmask};
 }
 
-__device__ __forceinline__ HighPlanes load_row_high(const uint16_t *slab, int r, int W,
-                                                    uint32_t wmask) {
-    uint32_t x[8];
-    load_row_bytes<0x7351>(slab, r, W, x);
-    transpose8(x);
-    return {x[0] & wmask, x[1] & wmask, x[2] & wmask, x[3] & wmask};
-}
+// ------------------------------------------------------------- geometries
+// Narrow: lane r owns row r (r < H <= 32), a row is a 32-bit word.
+struct Narrow {
+    typedef uint32_t P;
+    typedef uint32_t RowMask;
+    static constexpr int ROWS = 1;
+    static constexpr int PAD_CELLS = 32 * 32 + 32;   // row over-read past the last slab
+    int H, W, lane, up, down;
+    uint32_t wmask;
 
-__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) {
+    __device__ __forceinline__ Narrow(int H_, int W_, int lane_) : H(H_), W(W_), lane(lane_) {
+        int r = lane < H ? lane : 0;
+        up = r == 0 ? H - 1 : r - 1;
+        down = r == H - 1 ? 0 : r + 1;
+        // lanes past the last row carry an empty mask: they never create, kill or draw
+        wmask = lane < H ? (W == 32 ? FULL : ((1u << W) - 1u)) : 0u;
+    }
+    __device__ __forceinline__ P mask() const { return wmask; }
+    __device__ __forceinline__ P west(P x) const { return ((x << 1) | (x >> (W - 1))) & wmask; }
+    __device__ __forceinline__ P east(P x) const { return ((x >> 1) | (x << (W - 1))) & wmask; }
+    __device__ __forceinline__ P north(P x) const { return __shfl_sync(FULL, x, up); }
+    __device__ __forceinline__ P south(P x) const { return __shfl_sync(FULL, x, down); }
+    __device__ __forceinline__ int row_of(int) const { return lane; }
+    __device__ __forceinline__ RowMask row(P x, int) const { return x; }
+    __device__ __forceinline__ void set_row(P &x, int, RowMask v) const { x = v; }
+
+    __device__ __forceinline__ LowPlanesT<P> load_low(const uint16_t *slab) const {
+        uint32_t x[8];
+        planes32<0x6240>(slab + lane * W, x);
+        return {x[0] & wmask, x[3] & wmask, x[4] & wmask, x[5] & wmask, x[6] & wmask, x[7] & wmask};
+    }
+    __device__ __forceinline__ HighPlanesT<P> load_high(const uint16_t *slab) const {
+        uint32_t x[8];
+        planes32<0x7351>(slab + lane * W, x);
+        return {x[0] & wmask, x[1] & wmask, x[2] & wmask, x[3] & wmask};
+    }
+};
+
+// Wide: lane r owns rows r and r + 32 (H <= 64), a row is a 64-bit word (W <= 64).
+struct Wide {
+    typedef P2 P;
+    typedef uint64_t RowMask;
+    static constexpr int ROWS = 2;
+    static constexpr int PAD_CELLS = 64 * 64 + 64;
+    int H, W, lane;
+    uint64_t mask_a, mask_b;
+    int n_src_b, s_src_a;      // shuffle sources that depend on the lane
+    bool b_is_last;            // row lane + 32 is the last row of the board
+
+    __device__ __forceinline__ Wide(int H_, int W_, int lane_) : H(H_), W(W_), lane(lane_) {
+        const uint64_t full = W == 64 ? ~0ull : ((1ull << W) - 1ull);
+        mask_a = lane < H ? full : 0ull;
+        mask_b = lane + 32 < H ? full : 0ull;
+        // north of row 0 is row H-1: slot b of lane H-33 when H > 32
+        n_src_b = lane == 0 ? (H > 32 ? H - 33 : 0) : lane - 1;
+        // south of row lane: row 0 if it is the last row, else slot a of the next lane
+        s_src_a = lane == H - 1 ? 0 : ((lane + 1) & 31);
+        b_is_last = lane + 32 == H - 1;
+    }
+    __device__ __forceinline__ P mask() const { return {mask_a, mask_b}; }
+    __device__ __forceinline__ uint64_t rotl(uint64_t x, uint64_t m) const {
+        return ((x << 1) | (x >> (W - 1))) & m;
+    }
+    __device__ __forceinline__ uint64_t rotr(uint64_t x, uint64_t m) const {
+        return ((x >> 1) | (x << (W - 1))) & m;
+    }
+    __device__ __forceinline__ P west(P x) const { return {rotl(x.a, mask_a), rotl(x.b, mask_b)}; }
+    __device__ __forceinline__ P east(P x) const { return {rotr(x.a, mask_a), rotr(x.b, mask_b)}; }
+    __device__ __forceinline__ P north(P x) const {
+        if (H <= 32) {
+            const int src = lane == 0 ? H - 1 : (lane < H ? lane - 1 : 0);
+            return {__shfl_sync(FULL, x.a, src), 0ull};
+        }
+        const uint64_t u = __shfl_sync(FULL, x.a, (lane + 31) & 31);   // slot a of the previous lane
+        const uint64_t v = __shfl_sync(FULL, x.b, n_src_b);
+        return {lane == 0 ? v : u, lane == 0 ? u : v};
+    }
+    __device__ __forceinline__ P south(P x) const {
+        const uint64_t u = __shfl_sync(FULL, x.a, s_src_a);
+        if (H <= 32) return {u, 0ull};
+        const uint64_t v = __shfl_sync(FULL, x.b, (lane + 1) & 31);    // slot b of the next lane
+        const uint64_t row0 = __shfl_sync(FULL, x.a, 0);
+        return {lane == 31 ? v : u, b_is_last ? row0 : v};
+    }
+    __device__ __forceinline__ int row_of(int slot) const { return lane + 32 * slot; }
+    __device__ __forceinline__ RowMask row(P x, int slot) const { return slot ? x.b : x.a; }
+    __device__ __forceinline__ void set_row(P &x, int slot, RowMask v) const {
+        if (slot) x.b = v; else x.a = v;
+    }
+
+    template <unsigned SEL>
+    __device__ __forceinline__ void load_bytes(const uint16_t *slab, uint64_t (&pa)[8],
+                                               uint64_t (&pb)[8]) const {
+        uint32_t lo[8], hi[8];
+        planes32<SEL>(slab + lane * W, lo);
+        planes32<SEL>(slab + lane * W + 32, hi);
+#pragma unroll
+        for (int k = 0; k < 8; k++) pa[k] = ((uint64_t)lo[k] | ((uint64_t)hi[k] << 32)) & mask_a;
+        planes32<SEL>(slab + (lane + 32) * W, lo);
+        planes32<SEL>(slab + (lane + 32) * W + 32, hi);
+#pragma unroll
+        for (int k = 0; k < 8; k++) pb[k] = ((uint64_t)lo[k] | ((uint64_t)hi[k] << 32)) & mask_b;
+    }
+    __device__ __forceinline__ LowPlanesT<P> load_low(const uint16_t *slab) const {
+        uint64_t a[8], b[8];
+        load_bytes<0x6240>(slab, a, b);
+        return {{a[0], b[0]}, {a[3], b[3]}, {a[4], b[4]}, {a[5], b[5]}, {a[6], b[6]}, {a[7], b[7]}};
+    }
+    __device__ __forceinline__ HighPlanesT<P> load_high(const uint16_t *slab) const {
+        uint64_t a[8], b[8];
+        load_bytes<0x7351>(slab, a, b);
+        return {{a[0], b[0]}, {a[1], b[1]}, {a[2], b[2]}, {a[3], b[3]}};
+    }
+};
+
+// ------------------------------------------------------------------ stencil
+template <class P>
+__device__ __forceinline__ P maj3(P a, P b, P c) {
     return (a & b) | (a & c) | (b & c);
 }
 
-// What one stencil step does to a row (before the spawn draws are resolved).
-struct RowDelta {
-    uint32_t die;      // alive cells that die
-    uint32_t born;     // dead cells that come alive through n == 3
-    uint32_t cand;     // dead cells that take a spawn draw
-    uint32_t tR, tG, tB;   // inherited colour bits of a new cell
-    uint32_t dn;       // births that are DESTRUCTIBLE
-};
-
-struct Torus {
-    int H, W, up, down;   // source lanes of the rows above / below
-    uint32_t wmask;
-    __device__ __forceinline__ uint32_t west(uint32_t x) const {   // bit j <- cell j-1
-        return ((x << 1) | (x >> (W - 1))) & wmask;
-    }
-    __device__ __forceinline__ uint32_t east(uint32_t x) const {   // bit j <- cell j+1
-        return ((x >> 1) | (x << (W - 1))) & wmask;
-    }
-    __device__ __forceinline__ uint32_t north(uint32_t x) const { return __shfl_sync(FULL, x, up); }
-    __device__ __forceinline__ uint32_t south(uint32_t x) const { return __shfl_sync(FULL, x, down); }
-};
-
-__device__ __forceinline__ Torus make_torus(int H, int W, int lane) {
-    Torus t;
-    t.H = H; t.W = W;
-    int r = lane < H ? lane : 0;
-    t.up = r == 0 ? H - 1 : r - 1;
-    t.down = r == H - 1 ? 0 : r + 1;
-    // lanes past the last row carry an empty mask so that they never create,
-    // kill or draw anything
-    t.wmask = lane < H ? (W == 32 ? FULL : ((1u << W) - 1u)) : 0u;
-    return t;
-}
-
 // "at least one" / "at least two" of a plane over the 3x3 neighbourhood.
-struct Any2 { uint32_t one, two; };
-
-__device__ __forceinline__ uint32_t any3x3(const Torus &t, uint32_t x) {
-    uint32_t h = x | t.west(x) | t.east(x);
+template <class G>
+__device__ __forceinline__ typename G::P any3x3(const G &t, typename G::P x) {
+    typename G::P h = x | t.west(x) | t.east(x);
     return h | t.north(h) | t.south(h);
 }
 
-__device__ __forceinline__ uint32_t two3x3(const Torus &t, uint32_t x) {
-    uint32_t w = t.west(x), e = t.east(x);
-    uint32_t one = x | w | e, two = maj3(x, w, e);
-    uint32_t on = t.north(one), os = t.south(one);
+template <class G>
+__device__ __forceinline__ typename G::P two3x3(const G &t, typename G::P x) {
+    typedef typename G::P P;
+    P w = t.west(x), e = t.east(x);
+    P one = x | w | e, two = maj3(x, w, e);
+    P on = t.north(one), os = t.south(one);
     return two | t.north(two) | t.south(two) | maj3(one, on, os);
 }
 
 // advance_board.c:34-125 on bit planes.  `high()` supplies the high-byte planes
 // and is only called if some cell of the board may be created.
-template <class HighFn>
-__device__ __forceinline__ RowDelta stencil_planes(const Torus &t, const LowPlanes &p, HighFn high) {
+template <class G, class HighFn>
+__device__ __forceinline__ RowDeltaT<typename G::P> stencil_planes(
+    const G &t, const LowPlanesT<typename G::P> &p, HighFn high) {
+    typedef typename G::P P;
     // n = alive cells in the 3x3 (centre included), as 4 bit planes
-    uint32_t w = t.west(p.A), e = t.east(p.A);
-    uint32_t s0 = p.A ^ w ^ e, s1 = maj3(p.A, w, e);
-    uint32_t s0n = t.north(s0), s0s = t.south(s0), s1n = t.north(s1), s1s = t.south(s1);
-    uint32_t n0 = s0 ^ s0n ^ s0s, c0 = maj3(s0, s0n, s0s);
-    uint32_t a = s1 ^ s1n ^ s1s, b = maj3(s1, s1n, s1s);
-    uint32_t n1 = a ^ c0, c1 = a & c0;
-    uint32_t n2 = b ^ c1, n3 = b & c1;
-    uint32_t is3 = n0 & n1 & ~n2 & ~n3;
-    uint32_t is4 = ~n0 & ~n1 & n2 & ~n3;
+    P w = t.west(p.A), e = t.east(p.A);
+    P s0 = p.A ^ w ^ e, s1 = maj3(p.A, w, e);
+    P s0n = t.north(s0), s0s = t.south(s0), s1n = t.north(s1), s1s = t.south(s1);
+    P n0 = s0 ^ s0n ^ s0s, c0 = maj3(s0, s0n, s0s);
+    P a = s1 ^ s1n ^ s1s, b = maj3(s1, s1n, s1s);
+    P n1 = a ^ c0, c1 = a & c0;
+    P n2 = b ^ c1, n3 = b & c1;
+    P is3 = n0 & n1 & ~n2 & ~n3;
+    P is4 = ~n0 & ~n1 & n2 & ~n3;
 
-    uint32_t any_p = any3x3(t, p.P), any_i = any3x3(t, p.I), any_s = any3x3(t, p.S);
-    RowDelta d;
+    P any_p = any3x3(t, p.P_), any_i = any3x3(t, p.I), any_s = any3x3(t, p.S);
+    RowDeltaT<P> d;
     d.die = p.A & ~(p.F | any_p | is3 | is4);
-    uint32_t open = ~p.A & ~p.F & ~any_i & t.wmask;   // dead, not frozen, not inhibited
+    P open = ~p.A & ~p.F & ~any_i & t.mask();   // dead, not frozen, not inhibited
     d.born = open & is3;
     d.cand = open & ~is3 & any_s;
     // colours / destructibility only matter where something may be created
-    if (__any_sync(FULL, (d.born | d.cand) != 0)) {
-        const HighPlanes h = high();
+    if (__any_sync(FULL, nonzero(d.born | d.cand))) {
+        const HighPlanesT<P> h = high();
         d.tR = two3x3(t, p.A & h.R) | any3x3(t, p.S & h.R);
         d.tG = two3x3(t, p.A & h.G) | any3x3(t, p.S & h.G);
         d.tB = two3x3(t, p.A & h.B) | any3x3(t, p.S & h.B);
         d.dn = two3x3(t, p.A & (p.D | h.E));
     } else {
-        d.tR = d.tG = d.tB = d.dn = 0;
+        d.tR = d.tG = d.tB = d.dn = d.die & ~d.die;   // zero
     }
     return d;
 }
 
-// `slab` is the (unmodified) board the planes came from: the high-byte planes
-// are fetched from it only if needed.
-__device__ __forceinline__ RowDelta stencil_row(const Torus &t, const LowPlanes &p,
-                                                const uint16_t *slab, int r) {
-    return stencil_planes(t, p, [&] { return load_row_high(slab, r, t.W, t.wmask); });
-}
-
-// Resolve the spawn draws of one board: lane r holds its candidate mask; on
-// return `spawned` is the subset whose draw was below thr and the (uniform)
-// state has advanced by the total number of candidates.  Raster order = row
-// order, then bit order within the row.
-__device__ __forceinline__ uint32_t warp_spawn_draws(u128 &state, const u128 &inc, uint64_t thr,
-                                                     uint32_t cand, int lane) {
-    if (!__any_sync(FULL, cand != 0)) return 0u;
-    int cnt = __popc(cand), incl = cnt;
+// Resolve the spawn draws of one board: each lane holds the candidate masks of
+// its rows; returns the subset whose draw was below thr; the (uniform) state
+// advances by the total number of candidates.  Raster order = row order (all
+// rows of slot 0 come before those of slot 1), then bit order within the row.
+template <class G>
+__device__ __forceinline__ typename G::P warp_spawn_draws(const G &t, u128 &state, const u128 &inc,
+                                                          uint64_t thr, typename G::P cand) {
+    typedef typename G::P P;
+    typedef typename G::RowMask M;
+    P spawned = cand & ~cand;
+    if (!__any_sync(FULL, nonzero(cand))) return spawned;
+    const int lane = t.lane;
+    M todo[G::ROWS];
+    int next[G::ROWS];      // index of the next draw of each row
+    int total = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int v = __shfl_up_sync(FULL, incl, d);
-        if (lane >= d) incl += v;
+    for (int s = 0; s < G::ROWS; s++) {
+        todo[s] = t.row(cand, s);
+        int cnt = popc(todo[s]), incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int v = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += v;
+        }
+        next[s] = total + incl - cnt;
+        total += __shfl_sync(FULL, incl, 31);
     }
-    const int total = __shfl_sync(FULL, incl, 31);
-    int k = incl - cnt;                      // index of this lane's first draw
     const u128 la = {__ldg(&d_lane_a[lane][0]), __ldg(&d_lane_a[lane][1])};
     const u128 lg = {__ldg(&d_lane_g[lane][0]), __ldg(&d_lane_g[lane][1])};
     const u128 ginc = mul128(lg, inc);
-    uint32_t spawned = 0, todo = cand;
+    M got[G::ROWS];
+#pragma unroll
+    for (int s = 0; s < G::ROWS; s++) got[s] = 0;
     for (int base = 0; base < total; base += 32) {
-        u128 s = add128(mul128(la, state), ginc);          // state after lane+1 more steps
-        uint32_t ok = __ballot_sync(FULL, (pcg_output(s) >> 11) < thr);
-        while (todo != 0 && k < base + 32) {
-            int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            spawned |= ((ok >> (k - base)) & 1u) << j;
-            k++;
+        u128 sn = add128(mul128(la, state), ginc);          // state after lane+1 more steps
+        uint32_t ok = __ballot_sync(FULL, (pcg_output(sn) >> 11) < thr);
+#pragma unroll
+        for (int s = 0; s < G::ROWS; s++) {
+            while (todo[s] != 0 && next[s] < base + 32) {
+                int j = lowest(todo[s]);
+                todo[s] &= todo[s] - 1;
+                got[s] |= (M)((ok >> (next[s] - base)) & 1u) << j;
+                next[s]++;
+            }
         }
         int last = min(31, total - base - 1);
-        state.hi = __shfl_sync(FULL, s.hi, last);
-        state.lo = __shfl_sync(FULL, s.lo, last);
+        state.hi = __shfl_sync(FULL, sn.hi, last);
+        state.lo = __shfl_sync(FULL, sn.lo, last);
     }
+#pragma unroll
+    for (int s = 0; s < G::ROWS; s++) t.set_row(spawned, s, got[s]);
     return spawned;
 }
 
-// Write the cells of this row that a resolved step changed back into the
-// uint16 slab: dead ones become 0, new ones ALIVE | inherited colours |
-// DESTRUCTIBLE (advance_board.c:104, 111-118).  Returns the mask of changed
-// cells; when `table` is given, *delta accumulates what the changes add to
-// sum(table * alive_counts) (goal colours read from the goals slab).
-__device__ __forceinline__ uint32_t apply_row(const RowDelta &d, uint32_t spawned, uint16_t *slab,
-                                              int r, int W, const uint16_t *goals = nullptr,
-                                              const int32_t *table = nullptr,
-                                              int *delta = nullptr, bool dead_counts = true) {
-    const uint32_t fresh = d.born | spawned;
-    const uint32_t changed = d.die | fresh;
-    if (changed == 0) return 0u;
-    const uint32_t destr = (d.dn & d.born) | spawned;
-    uint16_t *row = slab + r * W;
-    uint32_t m = changed;
-    while (m != 0) {
-        int j = __ffs(m) - 1;
-        m &= m - 1;
-        uint32_t v = 0;
-        if ((fresh >> j) & 1u)
-            v = ALIVE | (((destr >> j) & 1u) << 3) | (((d.tR >> j) & 1u) << 9) |
-                (((d.tG >> j) & 1u) << 10) | (((d.tB >> j) & 1u) << 11);
-        if (table != nullptr) {
-            uint32_t g = goals[r * W + j];
-            *delta += cell_points(v, g, table, dead_counts) -
-                      cell_points(row[j], g, table, dead_counts);
+// New value of a changed cell: 0 if it died, else ALIVE | inherited colours |
+// DESTRUCTIBLE (advance_board.c:104, 111-118).
+template <class M>
+__device__ __forceinline__ uint32_t fresh_cell(M f, M de, M r, M g, M b, int j) {
+    if (!((f >> j) & 1)) return 0u;
+    return ALIVE | ((uint32_t)((de >> j) & 1) << 3) | ((uint32_t)((r >> j) & 1) << 9) |
+           ((uint32_t)((g >> j) & 1) << 10) | ((uint32_t)((b >> j) & 1) << 11);
+}
+
+// Write the board cells that a resolved step changed back into the uint16
+// slab.  *delta accumulates what the changes add to sum(table * alive_counts),
+// priced with the goals as they are in `goals`.
+template <class G>
+__device__ __forceinline__ void apply_board(const G &t, const RowDeltaT<typename G::P> &d,
+                                            typename G::P spawned, uint16_t *board,
+                                            const uint16_t *goals, const int32_t *table,
+                                            bool dead_counts, int *delta) {
+    typedef typename G::P P;
+    typedef typename G::RowMask M;
+    const P fresh = d.born | spawned;
+    const P changed = d.die | fresh;
+    if (!nonzero(changed)) return;
+    const P destr = (d.dn & d.born) | spawned;
+#pragma unroll
+    for (int s = 0; s < G::ROWS; s++) {
+        M m = t.row(changed, s);
+        const M f = t.row(fresh, s), de = t.row(destr, s);
+        const M r = t.row(d.tR, s), g = t.row(d.tG, s), b = t.row(d.tB, s);
+        const int base = t.row_of(s) * t.W;
+        while (m != 0) {
+            const int j = lowest(m);
+            m &= m - 1;
+            const uint32_t v = fresh_cell(f, de, r, g, b, j);
+            const uint32_t gl = goals[base + j];
+            *delta += cell_points(v, gl, table, dead_counts) -
+                      cell_points(board[base + j], gl, table, dead_counts);
+            board[base + j] = (uint16_t)v;
         }
-        row[j] = (uint16_t)v;
+    }
+}
+
+// The same for the goals plane; a goal cell whose colour changes re-prices the
+// board cell on top of it (`board` is already the new board).  Returns the
+// mask of changed goal cells.
+template <class G>
+__device__ __forceinline__ typename G::P apply_goals(const G &t, const RowDeltaT<typename G::P> &d,
+                                                     typename G::P spawned, uint16_t *goals,
+                                                     const uint16_t *board, const int32_t *table,
+                                                     bool dead_counts, int *delta) {
+    typedef typename G::P P;
+    typedef typename G::RowMask M;
+    const P fresh = d.born | spawned;
+    const P changed = d.die | fresh;
+    if (!nonzero(changed)) return changed;
+    const P destr = (d.dn & d.born) | spawned;
+#pragma unroll
+    for (int s = 0; s < G::ROWS; s++) {
+        M m = t.row(changed, s);
+        const M f = t.row(fresh, s), de = t.row(destr, s);
+        const M r = t.row(d.tR, s), g = t.row(d.tG, s), b = t.row(d.tB, s);
+        const int base = t.row_of(s) * t.W;
+        while (m != 0) {
+            const int j = lowest(m);
+            m &= m - 1;
+            const uint32_t v = fresh_cell(f, de, r, g, b, j);
+            const uint32_t old = goals[base + j];
+            if ((old ^ v) & COLORS) {
+                const uint32_t cell = board[base + j];
+                *delta += cell_points(cell, v, table, dead_counts) -
+                          cell_points(cell, old, table, dead_counts);
+            }
+            goals[base + j] = (uint16_t)v;
+        }
     }
     return changed;
 }
 
-// sum(table * alive_counts) of a board given its planes and the goals slab
+// sum(table * alive_counts) of a board / goals pair in shared memory, any size
 // (advance_board.c:192-207 + safelife_game.py:684-687), reduced over the warp.
-__device__ __forceinline__ int warp_points(const RowPlanes &p, const uint16_t *goals, int r, int W,
-                                           uint32_t wmask, const int32_t *table,
-                                           bool empty_column) {
-    const uint32_t countable = ((p.D | p.PU | p.PL) | ~p.F) & wmask;
-    const uint16_t *grow = goals + r * W;
+// Only used by the in-kernel reset.
+__device__ __forceinline__ int warp_points_slab(const uint16_t *board, const uint16_t *goals,
+                                                int cells, const int32_t *table, int lane) {
     int pts = 0;
-    uint32_t m = p.A & countable;
-    while (m != 0) {
-        int j = __ffs(m) - 1;
-        m &= m - 1;
-        int col = ((p.R >> j) & 1) | (((p.G >> j) & 1) << 1) | (((p.B >> j) & 1) << 2);
-        int g = (grow[j] >> COLOR_SHIFT) & 7;
-        pts += table[g * 9 + col];
-    }
-    if (empty_column) {
-        m = ~p.A & countable;
-        while (m != 0) {
-            int j = __ffs(m) - 1;
-            m &= m - 1;
-            pts += table[((grow[j] >> COLOR_SHIFT) & 7) * 9 + 8];
-        }
-    }
+    for (int i = lane; i < cells; i += 32) pts += cell_points(board[i], goals[i], table, true);
     return __reduce_add_sync(FULL, pts);
 }
 
-// Cooperative copy between a CTA's group of env slabs in global memory and
-// shared memory (fallback when the group is not 16-byte sized / aligned).
+// ---- bulk asynchronous copies (TMA, 1-D) and their mbarrier -----------------
 __device__ __forceinline__ void copy_slabs(void *dst, const void *src, int bytes) {
     const uint16_t *s2 = (const uint16_t *)src;
     uint16_t *d2 = (uint16_t *)dst;
     for (int i = threadIdx.x; i < (bytes >> 1); i += blockDim.x) d2[i] = s2[i];
 }
-
-// ---- bulk asynchronous copies (TMA, 1-D) and their mbarrier -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
@@ -363,6 +478,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
                  "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
@@ -398,24 +516,14 @@ __device__ __forceinline__ void fence_async_smem() {
 // Shared memory of one CTA of the step kernel.
 constexpr int WARP_SMEM_BAR = 16;                                   // mbarrier
 constexpr int WARP_SMEM_STATE = WARP_ENVS_PER_CTA * 96;             // SlEnvState[8]
-constexpr int WARP_SMEM_TABLES = WARP_ENVS_PER_CTA * 72 * 4;        // points tables
-constexpr int WARP_SMEM_PAD = 2 * (32 * 32 + 32);                   // row over-read of the last warp
 
 __host__ __device__ inline int warp_slab_stride(int cells) {
     return (WARP_ENVS_PER_CTA * cells * 2 + 15) & ~15;
 }
 
+template <class G>
 inline size_t warp_step_smem_bytes(int cells) {
-    return WARP_SMEM_BAR + WARP_SMEM_STATE + WARP_SMEM_TABLES + 2 * (size_t)warp_slab_stride(cells) +
-           WARP_SMEM_PAD;
-}
-
-__device__ __forceinline__ void load_table(int32_t *table, const int32_t *__restrict__ gtable,
-                                           int lane) {
-    table[lane] = __ldg(gtable + lane);
-    table[lane + 32] = __ldg(gtable + lane + 32);
-    if (lane < 8) table[lane + 64] = __ldg(gtable + lane + 64);
-    __syncwarp();
+    return WARP_SMEM_BAR + WARP_SMEM_STATE + 2 * (size_t)warp_slab_stride(cells) + 2 * G::PAD_CELLS;
 }
 
 // SafeLifeEnv.reset of one env by a whole warp, inside the step kernel
@@ -423,7 +531,7 @@ __device__ __forceinline__ void load_table(int32_t *table, const int32_t *__rest
 // slabs, points recount, update_exit_colors, fresh episode state in the
 // shared-memory record.  Rare (once per episode), so kept out of line.
 __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st, uint16_t *board,
-                                            uint16_t *goals, int32_t *table, int lane) {
+                                            uint16_t *goals, int lane) {
     const int H = B.H, W = B.W, cells = H * W;
     const int lvl = (int)(((long long)st->level_id + B.level_stride) % B.n_levels);
     const uint16_t *pb = B.pool_board + (size_t)lvl * cells;
@@ -432,11 +540,10 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st,
         board[i] = pb[i];
         goals[i] = pg[i];
     }
-    load_table(table, B.pool_table + (size_t)lvl * 72, lane);
+    const int32_t *table = B.pool_table + (size_t)lvl * 72;
+    __syncwarp();
     const bool empty = __any_sync(FULL, lane < 8 && table[lane * 9 + 8] != 0);
-    const Torus t = make_torus(H, W, lane);
-    RowPlanes p = load_row_planes(board, lane, W, t.wmask);
-    const int pts = warp_points(p, goals, lane, W, t.wmask, table, empty);
+    const int pts = warp_points_slab(board, goals, cells, table, lane);
     if (lane == 0) {
         const int32_t *exits = B.pool_exits + (size_t)lvl * B.max_exits;
         int n_exits = 0;
@@ -468,8 +575,10 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st,
 // ---- phase A: execute_actions + advance_board of one env by one warp ----------
 // `st`, `board`, `goals` are the env's record and slabs in shared memory.
 // Returns true if the goals slab was modified.
+template <class G>
 __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st, uint16_t *board,
                                              uint16_t *goals, int action, int lane) {
+    typedef typename G::P P;
     const int H = B.H, W = B.W;
     bool goals_dirty = false;
     const uint64_t thr = st->spawn_thr;
@@ -507,28 +616,24 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st
         }
     }
 
-    const Torus t = make_torus(H, W, lane);
-    const LowPlanes p = load_row_low(board, lane, W, t.wmask);
-    const RowDelta d = stencil_row(t, p, board, lane);
-    const uint32_t spawned = warp_spawn_draws(state, inc, thr, d.cand, lane);
-    apply_row(d, spawned, board, lane, W, goals, table, &delta, dead_counts);
+    const G t(H, W, lane);
+    {
+        const LowPlanesT<P> p = t.load_low(board);
+        const RowDeltaT<P> d = stencil_planes(t, p, [&] { return t.load_high(board); });
+        const P spawned = warp_spawn_draws(t, state, inc, thr, d.cand);
+        apply_board(t, d, spawned, board, goals, table, dead_counts, &delta);
+    }
     if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
-        const LowPlanes gp = load_row_low(goals, lane, W, t.wmask);
-        const RowDelta gd = stencil_row(t, gp, goals, lane);
-        const uint32_t gspawned = warp_spawn_draws(state, inc, thr, gd.cand, lane);
-        const uint32_t gchanged = apply_row(gd, gspawned, goals, lane, W);
-        // static iff nothing changed and no spawner is left (safelife_game.py:756-760)
-        if (sg == 0) sg = __any_sync(FULL, (gchanged | (gp.S & ~gchanged)) != 0) ? 2 : 1;
-        goals_dirty = true;
         __syncwarp();
+        const LowPlanesT<P> gp = t.load_low(goals);
+        const RowDeltaT<P> gd = stencil_planes(t, gp, [&] { return t.load_high(goals); });
+        const P gspawned = warp_spawn_draws(t, state, inc, thr, gd.cand);
+        const P gchanged = apply_goals(t, gd, gspawned, goals, board, table, dead_counts, &delta);
+        // static iff nothing changed and no spawner is left (safelife_game.py:756-760)
+        if (sg == 0) sg = __any_sync(FULL, nonzero(gchanged | (gp.S & ~gchanged))) ? 2 : 1;
+        goals_dirty = true;
     }
-    int pts;
-    if (sg == 1) {
-        pts = st->count_points + __reduce_add_sync(FULL, delta);
-    } else {   // dynamic goals: recount (planes re-read: the board slab is final here)
-        RowPlanes q = load_row_planes(board, lane, W, t.wmask);
-        pts = warp_points(q, goals, lane, W, t.wmask, table, dead_counts);
-    }
+    const int pts = st->count_points + __reduce_add_sync(FULL, delta);
     if (lane == 0) {
         st->count_points = pts;
         st->static_goals = (uint8_t)sg;
@@ -546,8 +651,7 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st
 // rewrote a goals slab.
 __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, int e0, int nenv,
                                              SlEnvState *sstate, uint16_t *sboard,
-                                             uint16_t *sgoals, int32_t *stables, int flags,
-                                             int lane) {
+                                             uint16_t *sgoals, int flags, int lane) {
     const int cells = B.H * B.W;
     bool done = false;
     if (lane < nenv) {
@@ -571,19 +675,19 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, int e0, int ne
         while (todo != 0) {
             const int w = __ffs(todo) - 1;
             todo &= todo - 1;
-            warp_reset_env(B, sstate + w, sboard + w * cells, sgoals + w * cells, stables + w * 72,
-                           lane);
+            warp_reset_env(B, sstate + w, sboard + w * cells, sgoals + w * cells, lane);
         }
     }
     return any_reset;
 }
 
 // SafeLifeEnv.step, one warp per env (safelife_env.py:148-201): single-pass
-// variant, one CTA per group of 8 envs.  Used for ragged / unaligned batches
-// (scalar copies instead of bulk copies) and for batches too small to pipeline.
+// variant, one CTA per group of 8 envs.
 //   phase A  warp w: execute_actions and advance_board of env w on bit planes
 //   phase B  warp 0, lane w: exit colours, reward / done, counters, auto-reset
-__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, 5)
+// Ragged / unaligned batches fall back to scalar copies instead of bulk copies.
+template <class G>
+__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 5 : 2)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
                 int bulk_ok, int flags, int first_group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -594,8 +698,7 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     const int group_bytes = nenv * cells * 2, state_bytes = nenv * 96;
     uint64_t *bar = (uint64_t *)smem_raw;
     SlEnvState *sstate = (SlEnvState *)(smem_raw + WARP_SMEM_BAR);
-    int32_t *stables = (int32_t *)(smem_raw + WARP_SMEM_BAR + WARP_SMEM_STATE);
-    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_BAR + WARP_SMEM_STATE + WARP_SMEM_TABLES);
+    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_BAR + WARP_SMEM_STATE);
     uint16_t *sgoals = sboard + warp_slab_stride(cells) / 2;
     uint16_t *gboard = B.board + (size_t)e0 * cells;
     uint16_t *ggoals = B.goals + (size_t)e0 * cells;
@@ -621,13 +724,13 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
 
     bool goals_dirty = false;
     if (warp < nenv)
-        goals_dirty = step_phase_a(B, sstate + warp, sboard + warp * cells, sgoals + warp * cells,
-                                   action, lane);
+        goals_dirty = step_phase_a<G>(B, sstate + warp, sboard + warp * cells,
+                                      sgoals + warp * cells, action, lane);
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
     int any_goals_dirty = __syncthreads_or(goals_dirty);
     if (warp != 0) return;
 
-    any_goals_dirty |= step_phase_b(B, e0, nenv, sstate, sboard, sgoals, stables, flags, lane);
+    any_goals_dirty |= step_phase_b(B, e0, nenv, sstate, sboard, sgoals, flags, lane);
     fence_async_smem();
     __syncwarp();
     if (bulk) {
@@ -646,7 +749,7 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     }
 }
 
-// ---- persistent, warp-specialised, double-buffered variant ----------------------
+// ---- persistent, warp-specialised, double-buffered variant (narrow boards) ------
 // One CTA per SM slot loops over groups of 8 envs (group g, g + grid, ...).
 // Warps 0-7 are stencil warps (phase A of env w of the current group); warp 8
 // is the scalar warp: it issues the bulk loads two groups ahead, waits for the
@@ -656,19 +759,14 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
 // stencil work of the next.
 constexpr int PIPE_STAGES = 2;
 constexpr int PIPE_THREADS = (WARP_ENVS_PER_CTA + 1) * 32;
-constexpr int PIPE_SMEM_HEAD = 64;    // full[2], done[2] mbarriers + dirty flags
+constexpr int PIPE_SMEM_HEAD = 64;    // full[2], fin[2] mbarriers + dirty flags
 
 __host__ __device__ inline int pipe_stage_bytes(int cells) {
     return WARP_SMEM_STATE + 2 * warp_slab_stride(cells);
 }
 
 inline size_t pipe_smem_bytes(int cells) {
-    return PIPE_SMEM_HEAD + WARP_SMEM_TABLES + PIPE_STAGES * (size_t)pipe_stage_bytes(cells) +
-           WARP_SMEM_PAD;
-}
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    return PIPE_SMEM_HEAD + PIPE_STAGES * (size_t)pipe_stage_bytes(cells) + 2 * Narrow::PAD_CELLS;
 }
 
 __global__ void __launch_bounds__(PIPE_THREADS, 4)
@@ -681,8 +779,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     uint64_t *full = (uint64_t *)smem_raw;            // [2] loads of a stage landed
     uint64_t *fin = full + PIPE_STAGES;               // [2] the 8 stencil warps are through
     volatile uint8_t *dirty = (volatile uint8_t *)(fin + PIPE_STAGES);   // [2][8] goals rewritten
-    int32_t *stables = (int32_t *)(smem_raw + PIPE_SMEM_HEAD);
-    unsigned char *stages = smem_raw + PIPE_SMEM_HEAD + WARP_SMEM_TABLES;
+    unsigned char *stages = smem_raw + PIPE_SMEM_HEAD;
     const int stage_bytes = pipe_stage_bytes(cells);
     auto stage_state = [&](int s) { return (SlEnvState *)(stages + s * stage_bytes); };
     auto stage_board = [&](int s) { return (uint16_t *)(stages + s * stage_bytes + WARP_SMEM_STATE); };
@@ -718,7 +815,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
             const int e0 = g * WARP_ENVS_PER_CTA;
             bool goals_dirty = lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
             goals_dirty |= step_phase_b(B, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
-                                        stage_goals(s), stables, flags, lane);
+                                        stage_goals(s), flags, lane);
             const bool any_dirty = __any_sync(FULL, goals_dirty);
             fence_async_smem();
             __syncwarp();
@@ -739,8 +836,9 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
             const int s = it & 1, parity = (it >> 1) & 1;
             const int action = actions[g * WARP_ENVS_PER_CTA + warp];
             mbar_wait(full + s, parity);
-            const bool gd = step_phase_a(B, stage_state(s) + warp, stage_board(s) + warp * cells,
-                                         stage_goals(s) + warp * cells, action, lane);
+            const bool gd = step_phase_a<Narrow>(B, stage_state(s) + warp,
+                                                 stage_board(s) + warp * cells,
+                                                 stage_goals(s) + warp * cells, action, lane);
             if (lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
             fence_async_smem();
             __syncwarp();
@@ -755,6 +853,11 @@ inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, in
     const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
     const int full_groups = B.n_envs / WARP_ENVS_PER_CTA;
     const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
+    if (!warp_kernel_is_narrow(B.H, B.W)) {
+        k_env_step_warp<Wide><<<groups, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes<Wide>(cells), st>>>(
+            B, actions, bulk_ok, flags, 0);
+        return;
+    }
     // pipelining pays once a CTA slot sees more than one group
     static const int slots_per_sm = [] {
         const char *v = getenv("SAFELIFE_B200_PIPE_SLOTS");   // tuning knob, default 4
@@ -770,23 +873,26 @@ inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, in
         k_env_step_pipe<<<grid, PIPE_THREADS, pipe_smem_bytes(cells), st>>>(B, actions, flags, piped);
     }
     if (groups > piped)
-        k_env_step_warp<<<groups - piped, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes(cells), st>>>(
+        k_env_step_warp<Narrow><<<groups - piped, WARP_ENVS_PER_CTA * 32,
+                                  warp_step_smem_bytes<Narrow>(cells), st>>>(
             B, actions, bulk_ok, flags, piped);
 }
 
 // ------------------------------------------------------------------------
-// n-step advance / life occupancy, one warp per board, the whole loop in
-// registers: advance_board_nstep (advance_board.c:128-149) and life_occupancy
-// (:153-189).  The planes live in registers for all n_steps; occupancy counts
-// are bit-sliced counters (one 10-bit vertical counter per colour and cell),
-// spilled into the int32 output every 1023 steps.  Nothing touches memory
-// inside the step loop.
+// n-step advance / life occupancy, one warp per board (H, W <= 32), the whole
+// loop in registers: advance_board_nstep (advance_board.c:128-149) and
+// life_occupancy (:153-189).  The planes live in registers for all n_steps;
+// occupancy counts are bit-sliced counters (one 10-bit vertical counter per
+// colour and cell), spilled into the int32 output every 1023 steps.  Nothing
+// touches memory inside the step loop.
 // ------------------------------------------------------------------------
 constexpr int ADV_WARPS = 4;
 constexpr int ADV_SLAB_CELLS = 32 * 32 + 32;     // one padded board per warp
 constexpr int OCC_BITS = 10;
 
-inline bool warp_advance_supports(int H, int W) { return warp_kernel_supports(H, W); }
+inline bool warp_advance_supports(int H, int W) {
+    return warp_kernel_supports(H, W) && warp_kernel_is_narrow(H, W);
+}
 
 __global__ void __launch_bounds__(ADV_WARPS * 32)
 k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, int n, int H,
@@ -795,12 +901,23 @@ k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cells = H * W;
     uint16_t *slab = slabs[warp];
-    const Torus t = make_torus(H, W, lane);
+    const Narrow t(H, W, lane);
     for (int b = blockIdx.x * ADV_WARPS + warp; b < n; b += gridDim.x * ADV_WARPS) {
         const uint16_t *src = in + (size_t)b * cells;
         for (int i = lane; i < cells; i += 32) slab[i] = src[i];
         __syncwarp();
-        RowPlanes p = load_row_planes(slab, lane, W, t.wmask);
+        uint32_t x[16];
+        {
+            const uint16_t *row = slab + lane * W;
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] = __byte_perm(row[k], row[k + 16], 0x5410);
+            transpose16(x);
+#pragma unroll
+            for (int k = 0; k < 16; k++) x[k] &= t.wmask;
+        }
+        LowPlanesT<uint32_t> lp = {x[0], x[3], x[4], x[5], x[6], x[7]};
+        HighPlanesT<uint32_t> hp = {x[8], x[9], x[10], x[11]};
+        uint32_t agent = x[1];
         uint32_t kept = t.wmask;              // cells that never changed keep their word
         u128 state = {0, 0}, inc = {0, 0};
         if (rng != nullptr) {
@@ -839,27 +956,25 @@ k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, 
         };
 
         for (int s = 0; s < n_steps; s++) {
-            const LowPlanes lp = {p.A, p.D, p.F, p.P, p.I, p.S};
-            const RowDelta d = stencil_planes(t, lp, [&] { return HighPlanes{p.E, p.R, p.G, p.B}; });
+            const RowDeltaT<uint32_t> d = stencil_planes(t, lp, [&] { return hp; });
             const uint32_t spawned =
-                rng != nullptr ? warp_spawn_draws(state, inc, thr, d.cand, lane) : 0u;
+                rng != nullptr ? warp_spawn_draws(t, state, inc, thr, d.cand) : 0u;
             const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
-            p.A = (p.A & keep) | fresh;
-            p.D = (p.D & keep) | (d.dn & d.born) | spawned;
-            p.R = (p.R & keep) | (d.tR & fresh);
-            p.G = (p.G & keep) | (d.tG & fresh);
-            p.B = (p.B & keep) | (d.tB & fresh);
-            p.P &= keep; p.I &= keep; p.S &= keep; p.E &= keep; p.AG &= keep;
-            p.PU &= keep; p.PL &= keep;
-            kept &= keep;
+            lp.A = (lp.A & keep) | fresh;
+            lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
+            hp.R = (hp.R & keep) | (d.tR & fresh);
+            hp.G = (hp.G & keep) | (d.tG & fresh);
+            hp.B = (hp.B & keep) | (d.tB & fresh);
+            lp.P_ &= keep; lp.I &= keep; lp.S &= keep; hp.E &= keep; agent &= keep;
+            kept &= keep;                     // (F is already 0 on every changed cell)
             if (counts != nullptr) {
                 // +1 for cells ALIVE and none of AGENT | EXIT | FROZEN, by colour (:153-162)
-                const uint32_t occ = p.A & ~(p.AG | p.E | p.F);
+                const uint32_t occ = lp.A & ~(agent | hp.E | lp.F);
                 if (__any_sync(FULL, occ != 0)) {
 #pragma unroll
                     for (int c = 0; c < 8; c++) {
-                        uint32_t carry = occ & ((c & 1) ? p.R : ~p.R) & ((c & 2) ? p.G : ~p.G) &
-                                         ((c & 4) ? p.B : ~p.B);
+                        uint32_t carry = occ & ((c & 1) ? hp.R : ~hp.R) & ((c & 2) ? hp.G : ~hp.G) &
+                                         ((c & 4) ? hp.B : ~hp.B);
                         if (__any_sync(FULL, carry != 0)) {
 #pragma unroll
                             for (int k = 0; k < OCC_BITS; k++) {
@@ -882,9 +997,9 @@ k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, 
             while (m != 0) {
                 const int j = __ffs(m) - 1;
                 m &= m - 1;
-                row[j] = (uint16_t)(((p.A >> j) & 1u) | (((p.D >> j) & 1u) << 3) |
-                                    (((p.R >> j) & 1u) << 9) | (((p.G >> j) & 1u) << 10) |
-                                    (((p.B >> j) & 1u) << 11));
+                row[j] = (uint16_t)(((lp.A >> j) & 1u) | (((lp.D >> j) & 1u) << 3) |
+                                    (((hp.R >> j) & 1u) << 9) | (((hp.G >> j) & 1u) << 10) |
+                                    (((hp.B >> j) & 1u) << 11));
             }
             __syncwarp();
             uint16_t *dst = out + (size_t)b * cells;

@@ -90,7 +90,8 @@ def _random_levels(rs, n, H, W, spawners=True):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("shape", [(3, 3), (5, 9), (16, 16), (25, 25), (26, 26), (32, 32), (50, 50)])
+@pytest.mark.parametrize("shape", [(3, 3), (5, 9), (16, 16), (25, 25), (26, 26), (32, 32), (50, 50),
+                                   (33, 40), (20, 50), (47, 21), (64, 64), (33, 33), (70, 30)])
 def test_env_random_levels_vs_oracle(shape, kernel):
     H, W = shape
     rs = np.random.default_rng(1000 * H + W)

@@ -59,3 +59,36 @@ def test_reset_done_restarts_wrapper_state():
     assert (env.env.baseline_board == base._t["board"]).all()
     with pytest.raises(ValueError):
         wrappers.MovementBonusWrapper(BatchedSafeLifeEnv(levels, 2, auto_reset=True))
+
+
+def test_batched_rollout_follows_act_on_envs():
+    import torch
+    from oracle import oracle as orc
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200.rollout import BatchedRollout
+    levels = gu.levels_of(gu.load_traj("mazes"))
+    L, n, T = len(levels), 7, 4
+    env = BatchedSafeLifeEnv(levels, n, auto_reset=False, time_limit=T, view_shape=(9, 9),
+                             output_channels=None)
+    runner = BatchedRollout(env)
+    obs0, ids0 = runner.obs_for_envs()
+    assert ids0.tolist() == [[i, 0, 0] for i in range(n)]
+    ora = orc.OracleEnv([levels[i % L] for i in range(n)], [orc.rng_from_seed(0)] * n, time_limit=T)
+    rs = np.random.default_rng(0)
+    for t in range(T):
+        a = rs.integers(0, 9, n)
+        obs, ids = runner.obs_for_envs()
+        nxt, reward, done = runner.act_on_envs(a)
+        r0, d0 = ora.step(a.astype(np.int64))
+        assert np.array_equal(reward.cpu().numpy(), r0) and np.array_equal(done.cpu().numpy(), d0)
+        for i in range(n):     # next_obs is the observation of the step, before any reset
+            want = orc.get_obs(ora.board[i], ora.goals[i], ora.loc[i], ora.exits[i], (9, 9), None)
+            assert np.array_equal(nxt[i].cpu().numpy(), want)
+    assert done.all()
+    obs, ids = runner.obs_for_envs()
+    assert ids.tolist() == [[i, 1, 0] for i in range(n)]
+    fresh = orc.OracleEnv([levels[(i + n) % L] for i in range(n)], [orc.rng_from_seed(0)] * n)
+    for i in range(n):
+        want = orc.get_obs(fresh.board[i], fresh.goals[i], fresh.loc[i], fresh.exits[i], (9, 9), None)
+        assert np.array_equal(obs[i].cpu().numpy(), want)
+    assert not torch.equal(obs, nxt)
