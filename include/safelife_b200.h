@@ -72,6 +72,23 @@ int sl_advance_board(const uint16_t *in, uint16_t *out, int n, int H, int W,
 int sl_life_occupancy(const uint16_t *board, int32_t *counts, int n, int H, int W,
                       float spawn_prob, int n_steps, uint64_t *rng, void *stream);
 
+/* The simulation part of side_effects.side_effect_score for n finished
+ * episodes at once (side_effects.py:101-111, num_runs = 1):
+ *     b1 = advance_board(init_board[b], spawn_prob, num_steps[b])
+ *     counts[b][0] += life_occupancy(b1, spawn_prob, num_samples)
+ *     counts[b][1] += life_occupancy(final_board[b], spawn_prob, num_samples)
+ * with the three calls drawing from rng[b] in this order (what the reference
+ * does under `with set_rng(...)`).  counts is int32[n][2][H][W][8], added to;
+ * spawn_thr[b] = ceil((double)(float)spawn_prob * 2^53) (SlEnvState.spawn_thr);
+ * num_steps[b] >= 0 is GameState.num_steps of the episode (0 leaves the initial
+ * board as it is; the reference's n_step = 0 quirk, advance_board.c:128-149,
+ * is not reproduced).  The earth-mover distance over these histograms stays on
+ * the host (sl_emd_host). */
+int sl_side_effect_occupancy(const uint16_t *init_board, const uint16_t *final_board,
+                             int32_t *counts, int n, int H, int W,
+                             const uint64_t *spawn_thr, const int32_t *num_steps,
+                             int num_samples, uint64_t *rng, void *stream);
+
 /* out[b][goal_colour][cell_colour | 8=empty] histogram, int64[n][8][9],
  * overwritten.  Replaces speedups.alive_counts (module.c:99-132 ->
  * advance_board.c:192-207). */
@@ -106,6 +123,15 @@ int sl_alive_counts_host(const uint16_t *board, const uint16_t *goals, int64_t *
 int sl_execute_actions_host(uint16_t *board, int64_t *locations, const int64_t *actions,
                             int n, int H, int W, int n_agents, int action_stride);
 int sl_wrapped_label_host(int32_t *data, int32_t *num_labels, int n, int H, int W);
+
+/* Earth mover's distance between two histograms over the same k points, host
+ * memory, no GPU involved: *out = min-cost flow of min(sum a, sum b) mass under
+ * dist[k][k] + extra_mass_penalty * |sum a - sum b| (extra_mass_penalty < 0:
+ * max(dist)).  Stands in for pyemd.emd as called by
+ * side_effects.earth_mover_distance (side_effects.py:57); exact in double
+ * precision, where pyemd/FastEMD quantises to 1e-6 of the maxima. */
+int sl_emd_host(const double *a, const double *b, const double *dist, int k,
+                double extra_mass_penalty, double *out);
 
 /* ---- batched environment (SafeLifeEnv.step / reset) ------------------- */
 

@@ -88,6 +88,8 @@ PROTOTYPES = {
     "sl_warp_kernel_supported": [_i, _i],
     "sl_advance_board": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
     "sl_life_occupancy": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
+    "sl_side_effect_occupancy": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
+    "sl_emd_host": [_vp, _vp, _vp, _i, ctypes.c_double, _vp],
     "sl_alive_counts": [_vp, _vp, _vp, _i, _i, _vp],
     "sl_execute_actions": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "sl_wrapped_label": [_vp, _vp, _i, _i, _i, _vp],

@@ -11,6 +11,7 @@
 
 #include "../../include/safelife_b200.h"
 #include "cells.cuh"
+#include "emd_host.h"
 #include "generic_kernels.cuh"
 #include "warp_kernels.cuh"
 
@@ -164,6 +165,14 @@ int sl_device_info(int *sm_count, int *l2_bytes, int *cc_major, int *cc_minor) {
     return SL_OK;
 }
 
+#ifdef SL_TRACE
+/* diagnostic builds only (tools/trace_step.py): device buffer uint64[grid][8] or NULL */
+int sl_debug_trace(void *buf) {
+    SL_CUDA(cudaMemcpyToSymbol(sl::sl_trace_buf, &buf, sizeof buf));
+    return SL_OK;
+}
+#endif
+
 int sl_warp_kernel_supported(int H, int W) { return sl::warp_kernel_supports(H, W) ? 1 : 0; }
 
 int sl_advance_board(const uint16_t *in, uint16_t *out, int n, int H, int W, float spawn_prob,
@@ -176,6 +185,32 @@ int sl_life_occupancy(const uint16_t *board, int32_t *counts, int n, int H, int 
     if (n > 0 && counts == nullptr) return fail(SL_ERR_ARG, "null counts pointer");
     return advance_impl(board, nullptr, counts, n, H, W, spawn_prob, n_steps, rng,
                         (cudaStream_t)stream);
+}
+
+int sl_side_effect_occupancy(const uint16_t *init_board, const uint16_t *final_board,
+                             int32_t *counts, int n, int H, int W, const uint64_t *spawn_thr,
+                             const int32_t *num_steps, int num_samples, uint64_t *rng,
+                             void *stream) {
+    int rc = check_board_args(init_board, n, H, W);
+    if (rc) return rc;
+    if (num_samples < 1) return fail(SL_ERR_ARG, "num_samples must be >= 1");
+    if (n == 0) return SL_OK;
+    if (!final_board || !counts || !spawn_thr || !num_steps) return fail(SL_ERR_ARG, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sl::warp_advance_supports(H, W)) {
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        sl::launch_side_effect_warp(init_board, final_board, counts, n, H, W, spawn_thr, num_steps,
+                                    num_samples, rng, props.sm_count, st);
+        return launch_status("k_side_effect_warp");
+    }
+    size_t smem = sl::generic_smem_bytes(H * W);
+    rc = prepare_smem(sl::k_side_effect_generic, smem);
+    if (rc) return rc;
+    sl::k_side_effect_generic<<<grid_for(n), sl::GENERIC_THREADS, smem, st>>>(
+        init_board, final_board, counts, n, H, W, spawn_thr, num_steps, num_samples, rng);
+    return launch_status("k_side_effect_generic");
 }
 
 int sl_alive_counts(const uint16_t *board, const uint16_t *goals, int64_t *out, int n, int cells,
@@ -330,6 +365,16 @@ int sl_wrapped_label_host(int32_t *data, int32_t *num_labels, int n, int H, int 
     SL_CUDA(cudaMemcpyAsync(data, d_data, dbytes, cudaMemcpyDeviceToHost, 0));
     SL_CUDA(cudaMemcpyAsync(num_labels, d_num, nbytes, cudaMemcpyDeviceToHost, 0));
     SL_CUDA(cudaStreamSynchronize(0));
+    return SL_OK;
+}
+
+int sl_emd_host(const double *a, const double *b, const double *dist, int k,
+                double extra_mass_penalty, double *out) {
+    if (k < 0) return fail(SL_ERR_ARG, "k must be >= 0");
+    if (!out || (k > 0 && (!a || !b || !dist))) return fail(SL_ERR_ARG, "null pointer");
+    for (int i = 0; i < k; i++)
+        if (!(a[i] >= 0.0) || !(b[i] >= 0.0)) return fail(SL_ERR_ARG, "histograms must be >= 0");
+    *out = k == 0 ? 0.0 : sl::emd_hat(a, b, dist, k, extra_mass_penalty);
     return SL_OK;
 }
 

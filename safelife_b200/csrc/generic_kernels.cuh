@@ -171,6 +171,48 @@ k_advance_generic(const uint16_t *in, uint16_t *out,   // may alias
     }
 }
 
+// Device part of side_effects.side_effect_score (side_effects.py:101-111), one
+// CTA per board, any size: inaction board = init advanced num_steps[b] times;
+// then num_samples more steps of it and of the final board with occupancy
+// counted into counts[b][0] / counts[b][1]; all draws from rng[b] in that order.
+__global__ void __launch_bounds__(GENERIC_THREADS)
+k_side_effect_generic(const uint16_t *__restrict__ init_board,
+                      const uint16_t *__restrict__ final_board, int32_t *__restrict__ counts,
+                      int n, int H, int W, const uint64_t *__restrict__ thr,
+                      const int32_t *__restrict__ num_steps, int num_samples,
+                      uint64_t *__restrict__ rng) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cells = H * W;
+    GenericSmem sm(smem_raw, cells);
+    for (int b = blockIdx.x; b < n; b += gridDim.x) {
+        if (rng != nullptr && threadIdx.x < 4) sm.rng[threadIdx.x] = rng[4 * (size_t)b + threadIdx.x];
+        const uint64_t th = thr[b];
+        for (int run = 0; run < 2; run++) {
+            const uint16_t *src = (run == 0 ? init_board : final_board) + (size_t)b * cells;
+            __syncthreads();
+            for (int i = threadIdx.x; i < cells; i += blockDim.x) sm.a[i] = src[i];
+            __syncthreads();
+            uint16_t *cur = sm.a, *nxt = sm.b;
+            const int lead = run == 0 ? num_steps[b] : 0;
+            int32_t *cnt = counts + ((size_t)b * 2 + run) * cells * 8;
+            for (int s = 0; s < lead + num_samples; s++) {
+                block_advance(cur, nxt, H, W, th, rng ? sm.rng : nullptr, sm.scratch);
+                if (s >= lead) {
+                    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+                        uint32_t c = nxt[i];
+                        if ((c & ALIVE) && !(c & (AGENT | EXIT | FROZEN)))
+                            cnt[8 * i + ((c & COLORS) >> COLOR_SHIFT)] += 1;
+                    }
+                }
+                uint16_t *t = cur; cur = nxt; nxt = t;
+            }
+        }
+        __syncthreads();
+        if (rng != nullptr && threadIdx.x < 2) rng[4 * (size_t)b + threadIdx.x] = sm.rng[threadIdx.x];
+        __syncthreads();
+    }
+}
+
 // out[b][72] histogram (advance_board.c:192-207).
 __global__ void __launch_bounds__(GENERIC_THREADS)
 k_alive_counts(const uint16_t *__restrict__ board, const uint16_t *__restrict__ goals,

@@ -513,6 +513,22 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// Optional per-CTA timeline for tools/trace_step.py (compiled in with -DSL_TRACE
+// into a separate diagnostic library, never into libsafelife_b200.so proper).
+#ifdef SL_TRACE
+__device__ unsigned long long *sl_trace_buf = nullptr;   // [grid][8] globaltimer ns
+__device__ __forceinline__ void trace_mark(int slot) {
+    if (sl_trace_buf != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        sl_trace_buf[(size_t)blockIdx.x * 8 + slot] = t;
+    }
+}
+#define SL_TRACE_MARK(cond, slot) do { if (cond) trace_mark(slot); } while (0)
+#else
+#define SL_TRACE_MARK(cond, slot) do { } while (0)
+#endif
+
 // Shared memory of one CTA of the step kernel.
 constexpr int WARP_SMEM_BAR = 16;                                   // mbarrier
 constexpr int WARP_SMEM_STATE = WARP_ENVS_PER_CTA * 96;             // SlEnvState[8]
@@ -704,6 +720,7 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     uint16_t *ggoals = B.goals + (size_t)e0 * cells;
     SlEnvState *gstate = B.state + e0;
     const bool bulk = bulk_ok && (group_bytes & 15) == 0;
+    SL_TRACE_MARK(threadIdx.x == 0, 0);
 
     if (bulk) {
         if (threadIdx.x == 0) {
@@ -721,18 +738,22 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     const int action = warp < nenv ? actions[e0 + warp] : 0;
     __syncthreads();                      // mbarrier init / fallback copy visible
     if (bulk) mbar_wait(bar, 0);
+    SL_TRACE_MARK(threadIdx.x == 0, 1);
 
     bool goals_dirty = false;
     if (warp < nenv)
         goals_dirty = step_phase_a<G>(B, sstate + warp, sboard + warp * cells,
                                       sgoals + warp * cells, action, lane);
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
+    SL_TRACE_MARK(threadIdx.x == 0, 2);
     int any_goals_dirty = __syncthreads_or(goals_dirty);
     if (warp != 0) return;
+    SL_TRACE_MARK(threadIdx.x == 0, 3);
 
     any_goals_dirty |= step_phase_b(B, e0, nenv, sstate, sboard, sgoals, flags, lane);
     fence_async_smem();
     __syncwarp();
+    SL_TRACE_MARK(threadIdx.x == 0, 4);
     if (bulk) {
         if (lane == 0) {
             bulk_store(gboard, sboard, group_bytes);
@@ -747,6 +768,7 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
         for (int i = lane; i < (state_bytes >> 1); i += 32)
             ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
     }
+    SL_TRACE_MARK(threadIdx.x == 0, 5);
 }
 
 // ---- persistent, warp-specialised, double-buffered variant (narrow boards) ------
@@ -894,6 +916,121 @@ inline bool warp_advance_supports(int H, int W) {
     return warp_kernel_supports(H, W) && warp_kernel_is_narrow(H, W);
 }
 
+// Register image of one board (H, W <= 32) for the multi-step loops: the ten
+// planes the rule reads or writes, the AGENT plane (occupancy mask) and the
+// mask of cells that have not changed since the board was loaded.
+struct AdvBoard {
+    LowPlanesT<uint32_t> lp;
+    HighPlanesT<uint32_t> hp;
+    uint32_t agent, kept;
+};
+
+// slab: this lane's padded copy of the board in shared memory.
+__device__ __forceinline__ AdvBoard adv_load(const Narrow &t, const uint16_t *slab) {
+    uint32_t x[16];
+    const uint16_t *row = slab + t.lane * t.W;
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] = __byte_perm(row[k], row[k + 16], 0x5410);
+    transpose16(x);
+#pragma unroll
+    for (int k = 0; k < 16; k++) x[k] &= t.wmask;
+    AdvBoard b;
+    b.lp = {x[0], x[3], x[4], x[5], x[6], x[7]};
+    b.hp = {x[8], x[9], x[10], x[11]};
+    b.agent = x[1];
+    b.kept = t.wmask;              // cells that never changed keep their word
+    return b;
+}
+
+// One advance_board step (advance_board.c:34-125) on the register image.
+__device__ __forceinline__ void adv_step(const Narrow &t, AdvBoard &b, u128 &state, const u128 &inc,
+                                         uint64_t thr, bool draws) {
+    LowPlanesT<uint32_t> &lp = b.lp;
+    HighPlanesT<uint32_t> &hp = b.hp;
+    const RowDeltaT<uint32_t> d = stencil_planes(t, lp, [&] { return hp; });
+    const uint32_t spawned = draws ? warp_spawn_draws(t, state, inc, thr, d.cand) : 0u;
+    const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
+    lp.A = (lp.A & keep) | fresh;
+    lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
+    hp.R = (hp.R & keep) | (d.tR & fresh);
+    hp.G = (hp.G & keep) | (d.tG & fresh);
+    hp.B = (hp.B & keep) | (d.tB & fresh);
+    lp.P_ &= keep; lp.I &= keep; lp.S &= keep; hp.E &= keep; b.agent &= keep;
+    b.kept &= keep;                     // (F is already 0 on every changed cell)
+}
+
+// Cells that changed at least once are fully described by the planes: patch
+// them into the lane's row of the slab.
+__device__ __forceinline__ void adv_store(const Narrow &t, const AdvBoard &b, uint16_t *slab) {
+    uint16_t *row = slab + t.lane * t.W;
+    uint32_t m = t.wmask & ~b.kept;
+    while (m != 0) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        row[j] = (uint16_t)(((b.lp.A >> j) & 1u) | (((b.lp.D >> j) & 1u) << 3) |
+                            (((b.hp.R >> j) & 1u) << 9) | (((b.hp.G >> j) & 1u) << 10) |
+                            (((b.hp.B >> j) & 1u) << 11));
+    }
+}
+
+// Bit-sliced occupancy counters of one board row: a 10-bit vertical counter
+// per colour and cell (advance_board.c:153-162 adds one per step).
+struct OccCounters {
+    uint32_t cnt[8][OCC_BITS];
+    int pending;
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
+        pending = 0;
+    }
+    // counters -> dst[row][col][colour] (+=), dst = counts of this board
+    __device__ __forceinline__ void flush(const Narrow &t, int32_t *board_counts) {
+        if (t.lane < t.H) {
+            int32_t *dst = board_counts + (size_t)t.lane * t.W * 8;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t nz = 0;
+#pragma unroll
+                for (int k = 0; k < OCC_BITS; k++) nz |= cnt[c][k];
+                while (nz != 0) {
+                    const int j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    int v = 0;
+#pragma unroll
+                    for (int k = 0; k < OCC_BITS; k++) v |= ((cnt[c][k] >> j) & 1u) << k;
+                    dst[j * 8 + c] += v;
+                }
+#pragma unroll
+                for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
+            }
+        }
+        pending = 0;
+    }
+    // +1 for cells ALIVE and none of AGENT | EXIT | FROZEN, by colour (:153-162)
+    __device__ __forceinline__ void add(const Narrow &t, const AdvBoard &b, int32_t *board_counts) {
+        const uint32_t occ = b.lp.A & ~(b.agent | b.hp.E | b.lp.F);
+        if (__any_sync(FULL, occ != 0)) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t carry = occ & ((c & 1) ? b.hp.R : ~b.hp.R) & ((c & 2) ? b.hp.G : ~b.hp.G) &
+                                 ((c & 4) ? b.hp.B : ~b.hp.B);
+                if (__any_sync(FULL, carry != 0)) {
+#pragma unroll
+                    for (int k = 0; k < OCC_BITS; k++) {
+                        const uint32_t tmp = cnt[c][k] & carry;
+                        cnt[c][k] ^= carry;
+                        carry = tmp;
+                    }
+                }
+            }
+        }
+        if (++pending == (1 << OCC_BITS) - 1) flush(t, board_counts);
+    }
+};
+
 __global__ void __launch_bounds__(ADV_WARPS * 32)
 k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, int n, int H,
                int W, uint64_t thr, int n_steps, uint64_t *__restrict__ rng) {
@@ -906,101 +1043,24 @@ k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, 
         const uint16_t *src = in + (size_t)b * cells;
         for (int i = lane; i < cells; i += 32) slab[i] = src[i];
         __syncwarp();
-        uint32_t x[16];
-        {
-            const uint16_t *row = slab + lane * W;
-#pragma unroll
-            for (int k = 0; k < 16; k++) x[k] = __byte_perm(row[k], row[k + 16], 0x5410);
-            transpose16(x);
-#pragma unroll
-            for (int k = 0; k < 16; k++) x[k] &= t.wmask;
-        }
-        LowPlanesT<uint32_t> lp = {x[0], x[3], x[4], x[5], x[6], x[7]};
-        HighPlanesT<uint32_t> hp = {x[8], x[9], x[10], x[11]};
-        uint32_t agent = x[1];
-        uint32_t kept = t.wmask;              // cells that never changed keep their word
+        AdvBoard bd = adv_load(t, slab);
         u128 state = {0, 0}, inc = {0, 0};
         if (rng != nullptr) {
             state = {rng[4 * (size_t)b], rng[4 * (size_t)b + 1]};
             inc = {rng[4 * (size_t)b + 2], rng[4 * (size_t)b + 3]};
         }
-        uint32_t cnt[8][OCC_BITS];
-#pragma unroll
-        for (int c = 0; c < 8; c++)
-#pragma unroll
-            for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
-        int pending = 0;
-
-        auto flush_counts = [&]() {
-            // bit-sliced counters -> counts[b][row][col][colour] (+=)
-            if (lane < H) {
-                int32_t *dst = counts + ((size_t)b * cells + (size_t)lane * W) * 8;
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    uint32_t nz = 0;
-#pragma unroll
-                    for (int k = 0; k < OCC_BITS; k++) nz |= cnt[c][k];
-                    while (nz != 0) {
-                        const int j = __ffs(nz) - 1;
-                        nz &= nz - 1;
-                        int v = 0;
-#pragma unroll
-                        for (int k = 0; k < OCC_BITS; k++) v |= ((cnt[c][k] >> j) & 1u) << k;
-                        dst[j * 8 + c] += v;
-                    }
-#pragma unroll
-                    for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
-                }
-            }
-            pending = 0;
-        };
-
-        for (int s = 0; s < n_steps; s++) {
-            const RowDeltaT<uint32_t> d = stencil_planes(t, lp, [&] { return hp; });
-            const uint32_t spawned =
-                rng != nullptr ? warp_spawn_draws(t, state, inc, thr, d.cand) : 0u;
-            const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
-            lp.A = (lp.A & keep) | fresh;
-            lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
-            hp.R = (hp.R & keep) | (d.tR & fresh);
-            hp.G = (hp.G & keep) | (d.tG & fresh);
-            hp.B = (hp.B & keep) | (d.tB & fresh);
-            lp.P_ &= keep; lp.I &= keep; lp.S &= keep; hp.E &= keep; agent &= keep;
-            kept &= keep;                     // (F is already 0 on every changed cell)
-            if (counts != nullptr) {
-                // +1 for cells ALIVE and none of AGENT | EXIT | FROZEN, by colour (:153-162)
-                const uint32_t occ = lp.A & ~(agent | hp.E | lp.F);
-                if (__any_sync(FULL, occ != 0)) {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        uint32_t carry = occ & ((c & 1) ? hp.R : ~hp.R) & ((c & 2) ? hp.G : ~hp.G) &
-                                         ((c & 4) ? hp.B : ~hp.B);
-                        if (__any_sync(FULL, carry != 0)) {
-#pragma unroll
-                            for (int k = 0; k < OCC_BITS; k++) {
-                                const uint32_t tmp = cnt[c][k] & carry;
-                                cnt[c][k] ^= carry;
-                                carry = tmp;
-                            }
-                        }
-                    }
-                }
-                if (++pending == (1 << OCC_BITS) - 1) flush_counts();
-            }
-        }
         if (counts != nullptr) {
-            if (pending) flush_counts();
-        } else {
-            // cells that changed at least once are fully described by the planes
-            uint16_t *row = slab + lane * W;
-            uint32_t m = t.wmask & ~kept;
-            while (m != 0) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1;
-                row[j] = (uint16_t)(((lp.A >> j) & 1u) | (((lp.D >> j) & 1u) << 3) |
-                                    (((hp.R >> j) & 1u) << 9) | (((hp.G >> j) & 1u) << 10) |
-                                    (((hp.B >> j) & 1u) << 11));
+            int32_t *dst = counts + (size_t)b * cells * 8;
+            OccCounters occ;
+            occ.clear();
+            for (int s = 0; s < n_steps; s++) {
+                adv_step(t, bd, state, inc, thr, rng != nullptr);
+                occ.add(t, bd, dst);
             }
+            if (occ.pending) occ.flush(t, dst);
+        } else {
+            for (int s = 0; s < n_steps; s++) adv_step(t, bd, state, inc, thr, rng != nullptr);
+            adv_store(t, bd, slab);
             __syncwarp();
             uint16_t *dst = out + (size_t)b * cells;
             for (int i = lane; i < cells; i += 32) dst[i] = slab[i];
@@ -1013,13 +1073,73 @@ k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, 
     }
 }
 
+// Device part of side_effects.side_effect_score for one board per warp
+// (side_effects.py:101-111): the inaction board is the initial board advanced
+// num_steps[b] times, then both it and the final board run num_samples more
+// steps with their occupancy counted; the three runs draw from rng[b] in that
+// order.  counts: int32[n][2][H][W][8], added to.
+__global__ void __launch_bounds__(ADV_WARPS * 32)
+k_side_effect_warp(const uint16_t *__restrict__ init_board, const uint16_t *__restrict__ final_board,
+                   int32_t *__restrict__ counts, int n, int H, int W,
+                   const uint64_t *__restrict__ thr, const int32_t *__restrict__ num_steps,
+                   int num_samples, uint64_t *__restrict__ rng) {
+    __shared__ uint16_t slabs[ADV_WARPS][ADV_SLAB_CELLS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = H * W;
+    uint16_t *slab = slabs[warp];
+    const Narrow t(H, W, lane);
+    for (int b = blockIdx.x * ADV_WARPS + warp; b < n; b += gridDim.x * ADV_WARPS) {
+        u128 state = {0, 0}, inc = {0, 0};
+        if (rng != nullptr) {
+            state = {rng[4 * (size_t)b], rng[4 * (size_t)b + 1]};
+            inc = {rng[4 * (size_t)b + 2], rng[4 * (size_t)b + 3]};
+        }
+        const uint64_t th = thr[b];
+        const bool draws = rng != nullptr;
+        OccCounters occ;
+        for (int run = 0; run < 2; run++) {
+            const uint16_t *src = (run == 0 ? init_board : final_board) + (size_t)b * cells;
+            __syncwarp();
+            for (int i = lane; i < cells; i += 32) slab[i] = src[i];
+            __syncwarp();
+            AdvBoard bd = adv_load(t, slab);
+            if (run == 0) {
+                const int ns = num_steps[b];
+                for (int s = 0; s < ns; s++) adv_step(t, bd, state, inc, th, draws);
+            }
+            int32_t *dst = counts + ((size_t)b * 2 + run) * cells * 8;
+            occ.clear();
+            for (int s = 0; s < num_samples; s++) {
+                adv_step(t, bd, state, inc, th, draws);
+                occ.add(t, bd, dst);
+            }
+            if (occ.pending) occ.flush(t, dst);
+        }
+        if (rng != nullptr && lane == 0) {
+            rng[4 * (size_t)b] = state.hi;
+            rng[4 * (size_t)b + 1] = state.lo;
+        }
+    }
+}
+
+inline int advance_warp_grid(int n, int sm_count) {
+    const int grid = (n + ADV_WARPS - 1) / ADV_WARPS, cap = sm_count * 8;
+    return grid > cap ? cap : grid;
+}
+
 inline void launch_advance_warp(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int H,
                                 int W, uint64_t thr, int n_steps, uint64_t *rng, int sm_count,
                                 cudaStream_t st) {
-    int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
-    const int cap = sm_count * 8;
-    if (grid > cap) grid = cap;
-    k_advance_warp<<<grid, ADV_WARPS * 32, 0, st>>>(in, out, counts, n, H, W, thr, n_steps, rng);
+    k_advance_warp<<<advance_warp_grid(n, sm_count), ADV_WARPS * 32, 0, st>>>(
+        in, out, counts, n, H, W, thr, n_steps, rng);
+}
+
+inline void launch_side_effect_warp(const uint16_t *init_board, const uint16_t *final_board,
+                                    int32_t *counts, int n, int H, int W, const uint64_t *thr,
+                                    const int32_t *num_steps, int num_samples, uint64_t *rng,
+                                    int sm_count, cudaStream_t st) {
+    k_side_effect_warp<<<advance_warp_grid(n, sm_count), ADV_WARPS * 32, 0, st>>>(
+        init_board, final_board, counts, n, H, W, thr, num_steps, num_samples, rng);
 }
 
 }  // namespace sl

@@ -92,6 +92,7 @@ class BatchedSafeLifeEnv(object):
     output_channels = tuple(range(16)) + (25, 26, 27)
     side_effect_weights = None
     should_calculate_side_effects = False
+    side_effect_samples = 1000     # side_effect_score's num_samples default (side_effects.py:60)
 
     def __init__(self, levels, num_envs, device=None, seed=None, auto_reset=True,
                  min_performance_fraction=1.0, kernel=0, **kwargs):
@@ -291,7 +292,10 @@ class BatchedSafeLifeEnv(object):
 
     def step(self, actions):
         assert self._has_reset, "Game state is not initialized."
-        self.step_physics(actions, self.auto_reset)
+        # side effects are scored on the final board, so the reset of finished
+        # envs waits until after the score (safelife_env.py:176-187)
+        score = bool(self.should_calculate_side_effects)
+        self.step_physics(actions, self.auto_reset and not score)
         t = self._t
         reward, done = t["reward"], t["done"].bool()
         info = {
@@ -299,8 +303,31 @@ class BatchedSafeLifeEnv(object):
             "episode": {"length": t["ep_length"], "reward": t["ep_reward"],
                         "success": t["success"].bool()},
         }
+        if score:
+            side_effects = self._episode_side_effects()
+            if side_effects:
+                info["episode"]["side_effects"] = side_effects
+            if self.auto_reset:
+                self.reset_done()
         info["board"], info["goals"], info["agent_locs"] = self.board, self.goals, self.agent_locs
         return self.get_obs(), reward, done, info
+
+    def _episode_side_effects(self):
+        """
+        {env index: side_effect_score(..., strkeys=True)} for the envs that finished in
+        the last step, with the weighted 'total' entry of safelife_env.py:178-184.
+        """
+        from .side_effects import side_effect_score_batch
+        if not bool(self._t["done"].any()):
+            return {}
+        out = side_effect_score_batch(self, num_samples=int(self.side_effect_samples), strkeys=True)
+        if self.side_effect_weights is not None:
+            for scores in out.values():
+                total = np.zeros(2)
+                for key, weight in self.side_effect_weights.items():
+                    total += weight * np.array(scores.get(key, 0))
+                scores["total"] = total.tolist()
+        return out
 
     def reset_done(self, mask=None):
         """

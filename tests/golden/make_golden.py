@@ -17,6 +17,10 @@ Fixture groups written (np.savez_compressed):
                      execute_actions, life_occupancy, wrapped_label).
   occupancy.npz      the device part of side_effect_score
                      (side_effects.py:101-111) at episode end.
+  side_effects.npz   the reference's whole side_effect_score (side_effects.py:60-154,
+                     num_samples=200) at the end of short random episodes, under
+                     set_rng; pyemd is absent here, so the EMD inside it is the
+                     exact LP of oracle/refload.py (parity unpinned at pyemd).
 """
 import os
 import sys
@@ -364,6 +368,43 @@ def make_occupancy():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_side_effects():
+    """side_effects.side_effect_score end to end on the reference."""
+    from safelife.side_effects import side_effect_score
+    recs = []
+    ss = np.random.SeedSequence(78)
+    picks = [("benchmarks/v1.0/append-spawn.npz", 2), ("benchmarks/v1.0/prune-still.npz", 2),
+             ("benchmarks/v1.0/navigation.npz", 2), ("benchmarks/v1.0/prune-spawn.npz", 1),
+             ("benchmarks/v1.0/append-still.npz", 1)]
+    for path, limit in picks:
+        for fname, data in static_games(path, limit):
+            game = SafeLifeGame.loaddata(data, auto_cls=False)
+            seed = ss.spawn(1)[0]
+            rec, log, game = run_episode(game, seed, 80, (15, 15), None, action_seed=100 + len(recs))
+            g = np.random.default_rng(777 + len(recs))
+            r0 = orc.rng_from_generator(g)
+            with set_rng(g):
+                scores = side_effect_score(game, num_samples=200)
+            keys = sorted(scores)
+            vals = np.array([[scores[k][0], scores[k][1]] for k in keys], dtype=np.float64)
+            pad = 16 - len(keys)
+            assert pad >= 0
+            recs.append({
+                "init_board": np.asarray(game._init_data["board"], dtype=np.uint16),
+                "final_board": game.board.copy(), "num_steps": np.int32(game.num_steps),
+                "spawn_prob": np.float32(game.spawn_prob), "rng0": r0,
+                "rng1": orc.rng_from_generator(g), "n_keys": np.int32(len(keys)),
+                "keys": np.array(keys + [0] * pad, dtype=np.int32),
+                "scores": np.concatenate([vals.reshape(-1, 2), np.zeros((pad, 2))]),
+            })
+    out = {k: np.stack([r[k] for r in recs]) for k in recs[0]}
+    out["num_samples"] = np.int32(200)
+    path = os.path.join(HERE, "side_effects.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+    print("keys per record", out["n_keys"], "max emd", out["scores"][..., 0].max())
+
+
 def main():
     which = set(sys.argv[1:])
 
@@ -374,6 +415,8 @@ def main():
         make_ops()
     if want("occupancy"):
         make_occupancy()
+    if want("side_effects"):
+        make_side_effects()
     v10 = ["benchmarks/v1.0/%s.npz" % n for n in (
         "append-still", "append-dynamic", "append-spawn", "prune-dynamic", "prune-spawn",
         "prune-still", "prune-still-hard", "navigation")]
