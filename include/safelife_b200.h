@@ -165,6 +165,19 @@ typedef struct SlEnvState {
                               keep the full list in pool_exits */
 } SlEnvState;
 
+/* Promises a caller may make about its level pool; they only select faster
+ * kernels and never change results.
+ * SL_POOL_UNIFORM_TABLE  every level's points table equals pool_table[0]: the
+ *     step kernels keep it in shared memory.
+ * SL_POOL_STATIC_GOALS   every level's goals are a fixed point of advance_board
+ *     and hold no SPAWNING cell, so GameWithGoals._static_goals becomes True on
+ *     the first step of every episode (safelife_game.py:753-761; true of the
+ *     append / prune -still and -spawn tasks): the step kernels leave the goal
+ *     planes in HBM and read only the goal cells under changed board cells.
+ *     If a level breaks the promise its envs still step correctly, slowly. */
+#define SL_POOL_UNIFORM_TABLE 1
+#define SL_POOL_STATIC_GOALS  2
+
 /*
  * Device-resident state of n_envs single-agent SafeLife environments plus the
  * read-only level pool they reset from.  All pointers are device pointers
@@ -176,6 +189,7 @@ typedef struct SlEnvBatch {
     int32_t time_limit;    /* SafeLifeEnv.time_limit, safelife_env.py:65 */
     int32_t n_levels;
     int32_t level_stride;  /* auto-reset rule: level_id <- (level_id + level_stride) % n_levels */
+    int32_t pool_flags;    /* SL_POOL_* promises about the level pool (0 is always valid) */
 
     /* per-env state */
     uint16_t   *board;     /* [n_envs][H][W]  SafeLifeGame.board */

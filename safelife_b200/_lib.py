@@ -19,6 +19,7 @@ _SRC = os.path.join(_PKG, "csrc")
 SL_OK, SL_ERR_ARG, SL_ERR_CUDA, SL_ERR_NO_DEVICE = 0, 1, 2, 3
 SL_RESET_NEXT_LEVEL, SL_RESET_KEEP_STATS = 1, 2
 SL_STEP_AUTO_RESET = 1
+SL_POOL_UNIFORM_TABLE, SL_POOL_STATIC_GOALS = 1, 2
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -58,7 +59,7 @@ def build(force=False, verbose=False):
 class SlEnvBatch(ctypes.Structure):
     """Mirror of struct SlEnvBatch (include/safelife_b200.h)."""
     _fields_ = [(n, ctypes.c_int32) for n in
-                ("n_envs", "H", "W", "max_exits", "time_limit", "n_levels", "level_stride")] + \
+                ("n_envs", "H", "W", "max_exits", "time_limit", "n_levels", "level_stride", "pool_flags")] + \
                [(n, ctypes.c_void_p) for n in (
                    "board", "goals", "state", "reward", "done", "success", "times_up",
                    "pool_board", "pool_goals", "pool_loc", "pool_table", "pool_exits",

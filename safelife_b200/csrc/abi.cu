@@ -54,7 +54,7 @@ uint64_t spawn_threshold(float spawn_prob) {
 }
 
 struct DeviceProps {
-    int sm_count = 0, l2_bytes = 0, major = 0, minor = 0, max_smem_optin = 0;
+    int sm_count = 0, l2_bytes = 0, major = 0, minor = 0, max_smem_optin = 0, smem_per_sm = 0;
     bool ok = false;
 };
 
@@ -70,6 +70,7 @@ int device_props(DeviceProps *out) {
         SL_CUDA(cudaDeviceGetAttribute(&p.major, cudaDevAttrComputeCapabilityMajor, dev));
         SL_CUDA(cudaDeviceGetAttribute(&p.minor, cudaDevAttrComputeCapabilityMinor, dev));
         SL_CUDA(cudaDeviceGetAttribute(&p.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        SL_CUDA(cudaDeviceGetAttribute(&p.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
         p.ok = true;
         cached = p;
         cached_dev = dev;
@@ -414,16 +415,27 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
         if (rc) return rc;
         const int cells = batch->H * batch->W;
         if (sl::warp_kernel_is_narrow(batch->H, batch->W)) {
-            rc = prepare_smem(sl::k_env_step_pipe, sl::pipe_smem_bytes(cells));
+#define SL_PREP_SHAPE(S, C, R)                                                                   \
+            if (sl::pipe_smem_bytes(cells, S, R) <= (size_t)props.max_smem_optin) {              \
+                rc = prepare_smem(sl::k_env_step_pipe<S, C, R>, sl::pipe_smem_bytes(cells, S, R)); \
+                if (rc) return rc;                                                               \
+            }
+            SL_PIPE_SHAPES(SL_PREP_SHAPE)
+#undef SL_PREP_SHAPE
+            rc = prepare_smem(sl::k_env_step_warp<sl::Narrow, true>,
+                              sl::warp_step_smem_bytes<sl::Narrow>(cells, true));
             if (rc) return rc;
-            rc = prepare_smem(sl::k_env_step_warp<sl::Narrow>,
-                              sl::warp_step_smem_bytes<sl::Narrow>(cells));
+            rc = prepare_smem(sl::k_env_step_warp<sl::Narrow, false>,
+                              sl::warp_step_smem_bytes<sl::Narrow>(cells, false));
         } else {
-            rc = prepare_smem(sl::k_env_step_warp<sl::Wide>,
-                              sl::warp_step_smem_bytes<sl::Wide>(cells));
+            rc = prepare_smem(sl::k_env_step_warp<sl::Wide, true>,
+                              sl::warp_step_smem_bytes<sl::Wide>(cells, true));
+            if (rc) return rc;
+            rc = prepare_smem(sl::k_env_step_warp<sl::Wide, false>,
+                              sl::warp_step_smem_bytes<sl::Wide>(cells, false));
         }
         if (rc) return rc;
-        sl::launch_env_step_warp(*batch, actions, flags, props.sm_count, st);
+        sl::launch_env_step_warp(*batch, actions, flags, props.sm_count, props.smem_per_sm, st);
         return launch_status("k_env_step_warp");
     }
     size_t smem = sl::generic_smem_bytes(batch->H * batch->W);

@@ -493,6 +493,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// The same with a suspend-time hint: a waiting warp is parked by the hardware for
+// up to `ns` instead of re-issuing the test, so the waits of the pipelined
+// kernel do not compete for issue slots with the warps that have work.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3; "
+            "selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+            : "memory");
+    } while (!ok);
+}
 __device__ __forceinline__ void bulk_load(void *dst_smem, const void *src_gmem, uint32_t bytes,
                                           uint64_t *bar) {
     asm volatile(
@@ -529,23 +543,47 @@ __device__ __forceinline__ void trace_mark(int slot) {
 #define SL_TRACE_MARK(cond, slot) do { } while (0)
 #endif
 
-// Shared memory of one CTA of the step kernel.
-constexpr int WARP_SMEM_BAR = 16;                                   // mbarrier
+// ---- shared memory of the step kernels ----------------------------------------
+// How a step kernel sees the goals of its envs:
+//   resident (GR = true)   the goal slabs of the group travel through shared
+//                          memory with the boards (any pool);
+//   in place (GR = false)  the caller promised SL_POOL_STATIC_GOALS: goal slabs
+//                          stay in HBM, the few goal cells that price a changed
+//                          board cell are read from there, and a goals plane
+//                          that is not (yet) known to be static -- the first
+//                          step of every episode, safelife_game.py:753-761 --
+//                          is advanced through one scratch slab per CTA.  A
+//                          broken promise costs time, not correctness.
+constexpr int WARP_SMEM_HEAD = 32;                                  // mbarrier, scratch lock
+constexpr int WARP_SMEM_TABLE = 72 * 4;                             // the pool's points table
 constexpr int WARP_SMEM_STATE = WARP_ENVS_PER_CTA * 96;             // SlEnvState[8]
 
 __host__ __device__ inline int warp_slab_stride(int cells) {
     return (WARP_ENVS_PER_CTA * cells * 2 + 15) & ~15;
 }
+__host__ __device__ inline int warp_scratch_bytes(int cells) { return (cells * 2 + 15) & ~15; }
 
 template <class G>
-inline size_t warp_step_smem_bytes(int cells) {
-    return WARP_SMEM_BAR + WARP_SMEM_STATE + 2 * (size_t)warp_slab_stride(cells) + 2 * G::PAD_CELLS;
+inline size_t warp_step_smem_bytes(int cells, bool goals_resident) {
+    return WARP_SMEM_HEAD + WARP_SMEM_TABLE + WARP_SMEM_STATE +
+           (goals_resident ? 2 * (size_t)warp_slab_stride(cells)
+                           : (size_t)warp_slab_stride(cells) + warp_scratch_bytes(cells)) +
+           2 * G::PAD_CELLS;
+}
+
+// The points table of the pool in shared memory when every level shares one
+// (SL_POOL_UNIFORM_TABLE): pricing a changed cell then never leaves the SM.
+__device__ __forceinline__ const int32_t *stage_table(const SlEnvBatch &B, int32_t *smem_table) {
+    if (!(B.pool_flags & SL_POOL_UNIFORM_TABLE)) return nullptr;
+    if (threadIdx.x < 72) smem_table[threadIdx.x] = __ldg(B.pool_table + threadIdx.x);
+    return smem_table;     // visible after the caller's next CTA barrier
 }
 
 // SafeLifeEnv.reset of one env by a whole warp, inside the step kernel
-// (safelife_env.py:203-218): next level of the pool into the shared-memory
-// slabs, points recount, update_exit_colors, fresh episode state in the
-// shared-memory record.  Rare (once per episode), so kept out of line.
+// (safelife_env.py:203-218): next level of the pool into the board slab (shared
+// memory) and the goals slab (shared memory or, in place, HBM), points recount,
+// update_exit_colors, fresh episode state in the shared-memory record.  Rare
+// (once per episode), so kept out of line.
 __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st, uint16_t *board,
                                             uint16_t *goals, int lane) {
     const int H = B.H, W = B.W, cells = H * W;
@@ -559,7 +597,7 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st,
     const int32_t *table = B.pool_table + (size_t)lvl * 72;
     __syncwarp();
     const bool empty = __any_sync(FULL, lane < 8 && table[lane * 9 + 8] != 0);
-    const int pts = warp_points_slab(board, goals, cells, table, lane);
+    const int pts = warp_points_slab(board, pg, cells, table, lane);
     if (lane == 0) {
         const int32_t *exits = B.pool_exits + (size_t)lvl * B.max_exits;
         int n_exits = 0;
@@ -575,7 +613,7 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st,
         bool agent_alive, exited;
         int dmem;
         const int row = B.pool_loc[2 * lvl], col = B.pool_loc[2 * lvl + 1];
-        const int value = exit_update(board, goals, W, row, col, pts, *st, exits, table,
+        const int value = exit_update(board, pg, W, row, col, pts, *st, exits, table,
                                       &agent_alive, &exited, &dmem);
         st->loc_row = row;
         st->loc_col = col;
@@ -588,12 +626,21 @@ __device__ __noinline__ void warp_reset_env(const SlEnvBatch &B, SlEnvState *st,
     __syncwarp();
 }
 
+// What the warps of one CTA share besides the stage buffers.
+struct CtaShared {
+    const int32_t *table;   // points table in shared memory, or nullptr: per level, in HBM
+    uint16_t *scratch;      // in-place goals only: the one scratch slab of the CTA
+    int *lock;              //                      and its lock
+};
+
 // ---- phase A: execute_actions + advance_board of one env by one warp ----------
-// `st`, `board`, `goals` are the env's record and slabs in shared memory.
-// Returns true if the goals slab was modified.
-template <class G>
-__device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st, uint16_t *board,
-                                             uint16_t *goals, int action, int lane) {
+// `st`, `board` are the env's record and board slab in shared memory; `goals` is
+// its goals slab in shared memory (GR) or in HBM (in place).  Returns true if a
+// shared-memory goals slab was modified.
+template <class G, bool GR>
+__device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShared &cs,
+                                             SlEnvState *st, uint16_t *board, uint16_t *goals,
+                                             uint64_t *goals_bar, int action, int lane) {
     typedef typename G::P P;
     const int H = B.H, W = B.W;
     bool goals_dirty = false;
@@ -603,18 +650,28 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st
     const uint64_t state_lo0 = state.lo;
     int sg = st->static_goals;
     int delta = 0;                    // change of sum(table * alive_counts), this lane
-    // points table of the level: looked up in global memory, and only for
-    // cells that changed (dead cells not at all unless its "empty" column counts)
-    const int32_t *table = B.pool_table + (size_t)st->level_id * 72;
+    // points table: shared memory if the pool has one table, else the level's in
+    // HBM; looked up only for cells that changed (dead cells not at all unless
+    // the "empty" column counts)
+    const int32_t *table = cs.table ? cs.table : B.pool_table + (size_t)st->level_id * 72;
     const bool dead_counts = st->empty_points != 0;
 
     // execute_actions (advance_board.c:217-300): lane 0 acts, lanes 0-3 account
-    // for the (at most four) cells it can touch
+    // for the (at most four) cells it can touch; they are priced after the
+    // stencil.  An in-place (HBM) goal cell is requested now, so that its
+    // latency hides behind the stencil; a resident one is read once the goal
+    // slabs have landed (`goals_bar`, nullptr: they already have).
     int row = st->loc_row, col = st->loc_col;
+    uint32_t before = 0, after = 0, goal_at = 0;
+    int idx = 0;
     if (row >= 0 && action != 0) {
         const ActionCells ac = action_cells(H, W, row, col, action);
-        const int idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
-        const uint32_t before = lane < 4 ? board[idx] : 0u;
+        idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
+        const bool mine = lane < 4 && !(lane == 3 && ac.i3 == ac.i2);
+        if (mine) {
+            before = board[idx];
+            if (!GR) goal_at = goals[idx];
+        }
         __syncwarp();
         if (lane == 0) {
             agent_action_at(board, ac, row, col, action);
@@ -622,14 +679,7 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st
             st->loc_col = col;
         }
         __syncwarp();
-        if (lane < 4 && !(lane == 3 && ac.i3 == ac.i2)) {
-            const uint32_t after = board[idx];
-            if (after != before) {
-                const uint32_t g = goals[idx];
-                delta += cell_points(after, g, table, dead_counts) -
-                         cell_points(before, g, table, dead_counts);
-            }
-        }
+        after = mine ? board[idx] : 0u;
     }
 
     const G t(H, W, lane);
@@ -637,17 +687,42 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st
         const LowPlanesT<P> p = t.load_low(board);
         const RowDeltaT<P> d = stencil_planes(t, p, [&] { return t.load_high(board); });
         const P spawned = warp_spawn_draws(t, state, inc, thr, d.cand);
+        if (GR && goals_bar != nullptr) mbar_wait(goals_bar, 0);
         apply_board(t, d, spawned, board, goals, table, dead_counts, &delta);
     }
+    if (after != before) {
+        if (GR) goal_at = goals[idx];
+        delta += cell_points(after, goal_at, table, dead_counts) -
+                 cell_points(before, goal_at, table, dead_counts);
+    }
     if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
+        uint16_t *gs = goals;
+        if (!GR) {   // through the CTA's scratch slab, one warp at a time
+            if (lane == 0)
+                while (atomicCAS(cs.lock, 0, 1) != 0) __nanosleep(200);
+            __threadfence_block();
+            __syncwarp();
+            for (int i = lane; i < H * W; i += 32) cs.scratch[i] = goals[i];
+            gs = cs.scratch;
+        }
         __syncwarp();
-        const LowPlanesT<P> gp = t.load_low(goals);
-        const RowDeltaT<P> gd = stencil_planes(t, gp, [&] { return t.load_high(goals); });
+        const LowPlanesT<P> gp = t.load_low(gs);
+        const RowDeltaT<P> gd = stencil_planes(t, gp, [&] { return t.load_high(gs); });
         const P gspawned = warp_spawn_draws(t, state, inc, thr, gd.cand);
-        const P gchanged = apply_goals(t, gd, gspawned, goals, board, table, dead_counts, &delta);
+        const P gchanged = apply_goals(t, gd, gspawned, gs, board, table, dead_counts, &delta);
         // static iff nothing changed and no spawner is left (safelife_game.py:756-760)
-        if (sg == 0) sg = __any_sync(FULL, nonzero(gchanged | (gp.S & ~gchanged))) ? 2 : 1;
-        goals_dirty = true;
+        const bool any_changed = __any_sync(FULL, nonzero(gchanged));
+        if (sg == 0) sg = (any_changed || __any_sync(FULL, nonzero(gp.S & ~gchanged))) ? 2 : 1;
+        if (GR) {
+            goals_dirty = true;
+        } else {
+            __syncwarp();
+            if (any_changed)
+                for (int i = lane; i < H * W; i += 32) goals[i] = cs.scratch[i];
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) atomicExch(cs.lock, 0);
+        }
     }
     const int pts = st->count_points + __reduce_add_sync(FULL, delta);
     if (lane == 0) {
@@ -663,24 +738,26 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, SlEnvState *st
 
 // ---- phase B: scalar tail of the step for up to 8 envs, lane w = env w --------
 // update_exit_colors, reward / done, counters (safelife_env.py:153-175), then
-// the auto-reset of finished envs by the whole warp.  Returns true if a reset
-// rewrote a goals slab.
-__device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, int e0, int nenv,
-                                             SlEnvState *sstate, uint16_t *sboard,
-                                             uint16_t *sgoals, int flags, int lane) {
+// the auto-reset of finished envs by the whole warp.  `goals0`: goals slab of the
+// group's first env (shared memory or HBM).  Returns true if a reset rewrote a
+// goals slab.
+__device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, const CtaShared &cs, int e0,
+                                             int nenv, SlEnvState *sstate, uint16_t *sboard,
+                                             uint16_t *goals0, int flags, int lane) {
     const int cells = B.H * B.W;
     bool done = false;
     if (lane < nenv) {
         SlEnvState *s0 = sstate + lane;
         uint16_t *bd = sboard + lane * cells;
-        const uint16_t *gl = sgoals + lane * cells;
+        const uint16_t *gl = goals0 + (size_t)lane * cells;
         const int lvl = s0->level_id;
         bool agent_alive, exited;
         int dmem;
         const int row = s0->loc_row, col = s0->loc_col, pts = s0->count_points;
         const int value = exit_update(bd, gl, B.W, row, col, pts, *s0,
                                       B.pool_exits + (size_t)lvl * B.max_exits,
-                                      B.pool_table + (size_t)lvl * 72, &agent_alive, &exited, &dmem);
+                                      cs.table ? cs.table : B.pool_table + (size_t)lvl * 72,
+                                      &agent_alive, &exited, &dmem);
         done = finish_step(B, e0 + lane, *s0, row, col, value, agent_alive, exited,
                            s0->static_goals, pts + dmem);
     }
@@ -691,7 +768,7 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, int e0, int ne
         while (todo != 0) {
             const int w = __ffs(todo) - 1;
             todo &= todo - 1;
-            warp_reset_env(B, sstate + w, sboard + w * cells, sgoals + w * cells, lane);
+            warp_reset_env(B, sstate + w, sboard + w * cells, goals0 + (size_t)w * cells, lane);
         }
     }
     return any_reset;
@@ -701,9 +778,11 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, int e0, int ne
 // variant, one CTA per group of 8 envs.
 //   phase A  warp w: execute_actions and advance_board of env w on bit planes
 //   phase B  warp 0, lane w: exit colours, reward / done, counters, auto-reset
+// The board slabs (and the goal slabs, when resident) arrive on separate
+// mbarriers, so the stencil starts while the goals are still in flight.
 // Ragged / unaligned batches fall back to scalar copies instead of bulk copies.
-template <class G>
-__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 5 : 2)
+template <class G, bool GR>
+__global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 4 : 2)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
                 int bulk_ok, int flags, int first_group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -712,58 +791,71 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     const int e0 = (first_group + blockIdx.x) * WARP_ENVS_PER_CTA;
     const int nenv = min(WARP_ENVS_PER_CTA, B.n_envs - e0);
     const int group_bytes = nenv * cells * 2, state_bytes = nenv * 96;
-    uint64_t *bar = (uint64_t *)smem_raw;
-    SlEnvState *sstate = (SlEnvState *)(smem_raw + WARP_SMEM_BAR);
-    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_BAR + WARP_SMEM_STATE);
-    uint16_t *sgoals = sboard + warp_slab_stride(cells) / 2;
+    uint64_t *bar = (uint64_t *)smem_raw;             // [0] state + boards, [1] goals
+    int32_t *stable = (int32_t *)(smem_raw + WARP_SMEM_HEAD);
+    SlEnvState *sstate = (SlEnvState *)(smem_raw + WARP_SMEM_HEAD + WARP_SMEM_TABLE);
+    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_HEAD + WARP_SMEM_TABLE + WARP_SMEM_STATE);
+    uint16_t *sgoals = sboard + warp_slab_stride(cells) / 2;   // GR: goal slabs; else: the scratch slab
     uint16_t *gboard = B.board + (size_t)e0 * cells;
     uint16_t *ggoals = B.goals + (size_t)e0 * cells;
     SlEnvState *gstate = B.state + e0;
     const bool bulk = bulk_ok && (group_bytes & 15) == 0;
     SL_TRACE_MARK(threadIdx.x == 0, 0);
 
+    CtaShared cs;
+    cs.scratch = sgoals;
+    cs.lock = (int *)(smem_raw + 16);
     if (bulk) {
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
-            mbar_expect_tx(bar, 2u * group_bytes + state_bytes);
+            mbar_init(bar + 1, 1);
+            *cs.lock = 0;
+            mbar_expect_tx(bar, (uint32_t)(group_bytes + state_bytes));
             bulk_load(sstate, gstate, state_bytes, bar);
             bulk_load(sboard, gboard, group_bytes, bar);
-            bulk_load(sgoals, ggoals, group_bytes, bar);
+            if (GR) {
+                mbar_expect_tx(bar + 1, (uint32_t)group_bytes);
+                bulk_load(sgoals, ggoals, group_bytes, bar + 1);
+            }
         }
     } else {
+        if (threadIdx.x == 0) *cs.lock = 0;
         copy_slabs(sstate, gstate, state_bytes);
         copy_slabs(sboard, gboard, group_bytes);
-        copy_slabs(sgoals, ggoals, group_bytes);
+        if (GR) copy_slabs(sgoals, ggoals, group_bytes);
     }
+    cs.table = stage_table(B, stable);
     const int action = warp < nenv ? actions[e0 + warp] : 0;
-    __syncthreads();                      // mbarrier init / fallback copy visible
+    __syncthreads();                      // mbarrier init / fallback copy / table visible
     if (bulk) mbar_wait(bar, 0);
     SL_TRACE_MARK(threadIdx.x == 0, 1);
 
     bool goals_dirty = false;
     if (warp < nenv)
-        goals_dirty = step_phase_a<G>(B, sstate + warp, sboard + warp * cells,
-                                      sgoals + warp * cells, action, lane);
+        goals_dirty = step_phase_a<G, GR>(B, cs, sstate + warp, sboard + warp * cells,
+                                          GR ? sgoals + warp * cells : ggoals + (size_t)warp * cells,
+                                          GR && bulk ? bar + 1 : nullptr, action, lane);
+    else if (GR && bulk) mbar_wait(bar + 1, 0);
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
     SL_TRACE_MARK(threadIdx.x == 0, 2);
     int any_goals_dirty = __syncthreads_or(goals_dirty);
     if (warp != 0) return;
     SL_TRACE_MARK(threadIdx.x == 0, 3);
 
-    any_goals_dirty |= step_phase_b(B, e0, nenv, sstate, sboard, sgoals, flags, lane);
+    any_goals_dirty |= step_phase_b(B, cs, e0, nenv, sstate, sboard, GR ? sgoals : ggoals, flags, lane);
     fence_async_smem();
     __syncwarp();
     SL_TRACE_MARK(threadIdx.x == 0, 4);
     if (bulk) {
         if (lane == 0) {
             bulk_store(gboard, sboard, group_bytes);
-            if (any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
+            if (GR && any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
             bulk_store(gstate, sstate, state_bytes);
             bulk_commit_and_wait_read();
         }
     } else {
         for (int i = lane; i < (group_bytes >> 1); i += 32) gboard[i] = sboard[i];
-        if (any_goals_dirty)
+        if (GR && any_goals_dirty)
             for (int i = lane; i < (group_bytes >> 1); i += 32) ggoals[i] = sgoals[i];
         for (int i = lane; i < (state_bytes >> 1); i += 32)
             ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
@@ -771,38 +863,44 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     SL_TRACE_MARK(threadIdx.x == 0, 5);
 }
 
-// ---- persistent, warp-specialised, double-buffered variant (narrow boards) ------
+// ---- persistent, warp-specialised, multi-stage variant (narrow boards) ----------
 // One CTA per SM slot loops over groups of 8 envs (group g, g + grid, ...).
 // Warps 0-7 are stencil warps (phase A of env w of the current group); warp 8
-// is the scalar warp: it issues the bulk loads two groups ahead, waits for the
-// 8 stencil warps of a group on an mbarrier, runs phase B for the group's 8
+// is the scalar warp: it issues the bulk loads STAGES groups ahead, waits for
+// the 8 stencil warps of a group on an mbarrier, runs phase B for the group's 8
 // envs on 8 lanes, and issues the bulk stores.  Stencil warps never wait for
 // each other: the TMA head and the scalar tail of one group overlap the
-// stencil work of the next.
-constexpr int PIPE_STAGES = 2;
+// stencil work of the next.  With in-place goals a stage is half the size, so
+// twice as many groups are in flight per SM.
+constexpr int PIPE_MAX_STAGES = 8;
+constexpr uint32_t PIPE_PARK_NS = 20000;
 constexpr int PIPE_THREADS = (WARP_ENVS_PER_CTA + 1) * 32;
-constexpr int PIPE_SMEM_HEAD = 64;    // full[2], fin[2] mbarriers + dirty flags
+// full[8], fin[8] mbarriers, dirty flags [8][8], lock, pad; then the points table
+constexpr int PIPE_SMEM_HEAD = 2 * 8 * PIPE_MAX_STAGES + 8 * PIPE_MAX_STAGES + 16;
 
-__host__ __device__ inline int pipe_stage_bytes(int cells) {
-    return WARP_SMEM_STATE + 2 * warp_slab_stride(cells);
+__host__ __device__ inline int pipe_stage_bytes(int cells, bool goals_resident) {
+    return WARP_SMEM_STATE + (goals_resident ? 2 : 1) * warp_slab_stride(cells);
 }
 
-inline size_t pipe_smem_bytes(int cells) {
-    return PIPE_SMEM_HEAD + PIPE_STAGES * (size_t)pipe_stage_bytes(cells) + 2 * Narrow::PAD_CELLS;
+inline size_t pipe_smem_bytes(int cells, int stages, bool goals_resident) {
+    return PIPE_SMEM_HEAD + WARP_SMEM_TABLE + stages * (size_t)pipe_stage_bytes(cells, goals_resident) +
+           (goals_resident ? 0 : warp_scratch_bytes(cells)) + 2 * Narrow::PAD_CELLS;
 }
 
-__global__ void __launch_bounds__(PIPE_THREADS, 4)
+template <int STAGES, int CTAS_PER_SM, bool GR>
+__global__ void __launch_bounds__(PIPE_THREADS, CTAS_PER_SM)
 k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
                 int flags, int n_groups) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group_bytes = WARP_ENVS_PER_CTA * cells * 2;
-    uint64_t *full = (uint64_t *)smem_raw;            // [2] loads of a stage landed
-    uint64_t *fin = full + PIPE_STAGES;               // [2] the 8 stencil warps are through
-    volatile uint8_t *dirty = (volatile uint8_t *)(fin + PIPE_STAGES);   // [2][8] goals rewritten
-    unsigned char *stages = smem_raw + PIPE_SMEM_HEAD;
-    const int stage_bytes = pipe_stage_bytes(cells);
+    uint64_t *full = (uint64_t *)smem_raw;            // [STAGES] loads of a stage landed
+    uint64_t *fin = full + PIPE_MAX_STAGES;           // [STAGES] the 8 stencil warps are through
+    volatile uint8_t *dirty = (volatile uint8_t *)(fin + PIPE_MAX_STAGES);   // [STAGES][8] goals rewritten
+    int32_t *stable = (int32_t *)(smem_raw + PIPE_SMEM_HEAD);
+    unsigned char *stages = smem_raw + PIPE_SMEM_HEAD + WARP_SMEM_TABLE;
+    const int stage_bytes = pipe_stage_bytes(cells, GR);
     auto stage_state = [&](int s) { return (SlEnvState *)(stages + s * stage_bytes); };
     auto stage_board = [&](int s) { return (uint16_t *)(stages + s * stage_bytes + WARP_SMEM_STATE); };
     auto stage_goals = [&](int s) {
@@ -810,43 +908,48 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     };
     auto issue_load = [&](int s, int g) {
         const size_t e0 = (size_t)g * WARP_ENVS_PER_CTA;
-        mbar_expect_tx(full + s, 2u * group_bytes + WARP_SMEM_STATE);
+        mbar_expect_tx(full + s, (GR ? 2u : 1u) * group_bytes + WARP_SMEM_STATE);
         bulk_load(stage_state(s), B.state + e0, WARP_SMEM_STATE, full + s);
         bulk_load(stage_board(s), B.board + e0 * cells, group_bytes, full + s);
-        bulk_load(stage_goals(s), B.goals + e0 * cells, group_bytes, full + s);
+        if (GR) bulk_load(stage_goals(s), B.goals + e0 * cells, group_bytes, full + s);
     };
+    CtaShared cs;
+    cs.scratch = (uint16_t *)(stages + STAGES * stage_bytes);
+    cs.lock = (int *)(smem_raw + PIPE_SMEM_HEAD - 16);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PIPE_STAGES; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mbar_init(full + s, 1);
             mbar_init(fin + s, WARP_ENVS_PER_CTA);
         }
+        *cs.lock = 0;
     }
+    cs.table = stage_table(B, stable);
     __syncthreads();
     const int first = blockIdx.x, stride = gridDim.x;
 
     if (warp == WARP_ENVS_PER_CTA) {
         // ---- scalar warp: loads, phase B, stores
         if (lane == 0)
-            for (int s = 0; s < PIPE_STAGES; s++)
+            for (int s = 0; s < STAGES; s++)
                 if (first + s * stride < n_groups) issue_load(s, first + s * stride);
         int it = 0;
         for (int g = first; g < n_groups; g += stride, it++) {
-            const int s = it & 1, parity = (it >> 1) & 1;
-            mbar_wait(fin + s, parity);
+            const int s = it % STAGES, parity = (it / STAGES) & 1;
+            mbar_wait_parked(fin + s, parity, PIPE_PARK_NS);
             const int e0 = g * WARP_ENVS_PER_CTA;
-            bool goals_dirty = lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
-            goals_dirty |= step_phase_b(B, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
-                                        stage_goals(s), flags, lane);
+            bool goals_dirty = GR && lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
+            goals_dirty |= step_phase_b(B, cs, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
+                                        GR ? stage_goals(s) : B.goals + (size_t)e0 * cells, flags, lane);
             const bool any_dirty = __any_sync(FULL, goals_dirty);
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
                 bulk_store(B.board + (size_t)e0 * cells, stage_board(s), group_bytes);
-                if (any_dirty) bulk_store(B.goals + (size_t)e0 * cells, stage_goals(s), group_bytes);
+                if (GR && any_dirty) bulk_store(B.goals + (size_t)e0 * cells, stage_goals(s), group_bytes);
                 bulk_store(B.state + e0, stage_state(s), WARP_SMEM_STATE);
                 bulk_commit_and_wait_read();       // the stage may be overwritten after this
-                const int gn = g + PIPE_STAGES * stride;
+                const int gn = g + STAGES * stride;
                 if (gn < n_groups) issue_load(s, gn);
             }
             __syncwarp();
@@ -855,13 +958,14 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
         // ---- stencil warp w: phase A of env w of every group of this CTA
         int it = 0;
         for (int g = first; g < n_groups; g += stride, it++) {
-            const int s = it & 1, parity = (it >> 1) & 1;
-            const int action = actions[g * WARP_ENVS_PER_CTA + warp];
-            mbar_wait(full + s, parity);
-            const bool gd = step_phase_a<Narrow>(B, stage_state(s) + warp,
-                                                 stage_board(s) + warp * cells,
-                                                 stage_goals(s) + warp * cells, action, lane);
-            if (lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
+            const int s = it % STAGES, parity = (it / STAGES) & 1;
+            const size_t e = (size_t)g * WARP_ENVS_PER_CTA + warp;
+            const int action = actions[e];
+            mbar_wait_parked(full + s, parity, PIPE_PARK_NS);
+            const bool gd = step_phase_a<Narrow, GR>(
+                B, cs, stage_state(s) + warp, stage_board(s) + warp * cells,
+                GR ? stage_goals(s) + warp * cells : B.goals + e * cells, nullptr, action, lane);
+            if (GR && lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(fin + s);
@@ -869,35 +973,83 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     }
 }
 
+// Pipeline shapes: (stages, CTAs per SM) by goals mode.  The stage buffers of a
+// 25x25 board fill the shared memory of an SM in every shape.
+struct PipeShape {
+    int stages, ctas;
+};
+
+template <int STAGES, int CTAS, bool GR>
+inline void launch_pipe(const SlEnvBatch &B, const uint8_t *actions, int flags, int full_groups,
+                        int sm_count, cudaStream_t st) {
+    const int cells = B.H * B.W;
+    const int slots = sm_count * CTAS;
+    const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
+    const int grid = (full_groups + per_cta - 1) / per_cta;
+    k_env_step_pipe<STAGES, CTAS, GR><<<grid, PIPE_THREADS, pipe_smem_bytes(cells, STAGES, GR), st>>>(
+        B, actions, flags, full_groups);
+}
+
+inline int env_knob(const char *name, int fallback) {
+    const char *v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
+// The shapes compiled in; `shape` picks one (tuning knob SAFELIFE_B200_PIPE_SHAPE).
+#define SL_PIPE_SHAPES(X) X(2, 4, true) X(3, 3, true) X(3, 4, false) X(4, 4, false) X(5, 3, false) X(6, 3, false)
+
+inline bool pipe_shape_fits(int cells, int stages, int ctas, bool gr, int smem_per_sm) {
+    return ctas * (pipe_smem_bytes(cells, stages, gr) + 1024) <= (size_t)smem_per_sm;
+}
+
 inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
-                                 int sm_count, cudaStream_t st) {
+                                 int sm_count, int smem_per_sm, cudaStream_t st) {
     const int cells = B.H * B.W;
     const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
     const int full_groups = B.n_envs / WARP_ENVS_PER_CTA;
     const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
+    static const bool in_place_ok = env_knob("SAFELIFE_B200_GOALS_IN_PLACE", 1) != 0;
+    const bool gr = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok);
     if (!warp_kernel_is_narrow(B.H, B.W)) {
-        k_env_step_warp<Wide><<<groups, WARP_ENVS_PER_CTA * 32, warp_step_smem_bytes<Wide>(cells), st>>>(
-            B, actions, bulk_ok, flags, 0);
+        if (gr)
+            k_env_step_warp<Wide, true><<<groups, WARP_ENVS_PER_CTA * 32,
+                                          warp_step_smem_bytes<Wide>(cells, true), st>>>(
+                B, actions, bulk_ok, flags, 0);
+        else
+            k_env_step_warp<Wide, false><<<groups, WARP_ENVS_PER_CTA * 32,
+                                           warp_step_smem_bytes<Wide>(cells, false), st>>>(
+                B, actions, bulk_ok, flags, 0);
         return;
     }
     // pipelining pays once a CTA slot sees more than one group
-    static const int slots_per_sm = [] {
-        const char *v = getenv("SAFELIFE_B200_PIPE_SLOTS");   // tuning knob, default 4
-        int k = v ? atoi(v) : 4;
-        return k >= 1 && k <= 4 ? k : 4;
-    }();
-    const int slots = sm_count * slots_per_sm;
+    static const int shape_knob = env_knob("SAFELIFE_B200_PIPE_SHAPE", 0);   // stages * 10 + ctas
+    const int want = shape_knob ? shape_knob : (gr ? 33 : 44);
     int piped = 0;
-    if (bulk_ok && full_groups > slots) {
-        piped = full_groups;
-        const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
-        const int grid = (full_groups + per_cta - 1) / per_cta;
-        k_env_step_pipe<<<grid, PIPE_THREADS, pipe_smem_bytes(cells), st>>>(B, actions, flags, piped);
+    if (bulk_ok && full_groups > sm_count * (want % 10)) {
+#define SL_TRY_SHAPE(S, C, R)                                                          \
+        if (!piped && R == gr && want == S * 10 + C &&                                 \
+            pipe_shape_fits(cells, S, C, R, smem_per_sm)) {                            \
+            launch_pipe<S, C, R>(B, actions, flags, full_groups, sm_count, st);        \
+            piped = full_groups;                                                       \
+        }
+        SL_PIPE_SHAPES(SL_TRY_SHAPE)
+#undef SL_TRY_SHAPE
+        if (!piped) {     // a board too large for the wanted shape: the smallest one
+            if (gr) launch_pipe<2, 4, true>(B, actions, flags, full_groups, sm_count, st);
+            else launch_pipe<3, 4, false>(B, actions, flags, full_groups, sm_count, st);
+            piped = full_groups;
+        }
     }
-    if (groups > piped)
-        k_env_step_warp<Narrow><<<groups - piped, WARP_ENVS_PER_CTA * 32,
-                                  warp_step_smem_bytes<Narrow>(cells), st>>>(
-            B, actions, bulk_ok, flags, piped);
+    if (groups > piped) {
+        if (gr)
+            k_env_step_warp<Narrow, true><<<groups - piped, WARP_ENVS_PER_CTA * 32,
+                                            warp_step_smem_bytes<Narrow>(cells, true), st>>>(
+                B, actions, bulk_ok, flags, piped);
+        else
+            k_env_step_warp<Narrow, false><<<groups - piped, WARP_ENVS_PER_CTA * 32,
+                                             warp_step_smem_bytes<Narrow>(cells, false), st>>>(
+                B, actions, bulk_ok, flags, piped);
+    }
 }
 
 // ------------------------------------------------------------------------

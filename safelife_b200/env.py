@@ -93,6 +93,9 @@ class BatchedSafeLifeEnv(object):
     side_effect_weights = None
     should_calculate_side_effects = False
     side_effect_samples = 1000     # side_effect_score's num_samples default (side_effects.py:60)
+    # keep the goal planes out of the step kernel's shared memory (SL_POOL_STATIC_GOALS):
+    # None = if the pool's goals are static, True / False = force (results never change)
+    goals_in_place = None
 
     def __init__(self, levels, num_envs, device=None, seed=None, auto_reset=True,
                  min_performance_fraction=1.0, kernel=0, **kwargs):
@@ -163,13 +166,32 @@ class BatchedSafeLifeEnv(object):
             self._actions = z((N,), torch.uint8)
         self._batch = _lib.SlEnvBatch(
             n_envs=N, H=H, W=W, max_exits=p.max_exits, time_limit=int(self.time_limit),
-            n_levels=len(p), level_stride=N % len(p),
+            n_levels=len(p), level_stride=N % len(p), pool_flags=self._pool_flags(),
             **{k: t.data_ptr() for k, t in self._t.items()},
             **{k: t.data_ptr() for k, t in self._pool_t.items()})
         self._batch_ref = ctypes.byref(self._batch)
         self._has_reset = False
         # `_t` also answers for the named views of the state record
         self._t = _TensorTable(self._t, self._views)
+
+    def _pool_flags(self):
+        """
+        SL_POOL_* promises (include/safelife_b200.h) that hold for this pool: one
+        shared points table; goals that are a fixed point of advance_board with no
+        spawner (one stencil launch over the pool's goal planes decides).
+        """
+        p, flags = self.pool, 0
+        if (p.table == p.table[0]).all():
+            flags |= _lib.SL_POOL_UNIFORM_TABLE
+        goals = self._pool_t["pool_goals"]
+        nxt = torch.empty_like(goals)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_advance_board(
+                goals.data_ptr(), nxt.data_ptr(), len(p), p.H, p.W, 0.0, 1, None, self._stream()))
+        static = bool((nxt == goals).all()) and not bool((goals & 128).any())
+        if static if self.goals_in_place is None else self.goals_in_place:
+            flags |= _lib.SL_POOL_STATIC_GOALS
+        return flags
 
     # ------------------------------------------------------------ tensors
     @property
@@ -215,6 +237,7 @@ class BatchedSafeLifeEnv(object):
                 self._batch_ref, None, new_level.data_ptr() if new_level is not None else None,
                 0, self._stream()))
             self._has_reset = True
+            self._scored = None
             return self.get_obs()
 
     def get_obs(self):
@@ -318,9 +341,16 @@ class BatchedSafeLifeEnv(object):
         the last step, with the weighted 'total' entry of safelife_env.py:178-184.
         """
         from .side_effects import side_effect_score_batch
-        if not bool(self._t["done"].any()):
+        # once per episode (`self.side_effects is None`, safelife_env.py:176): an env that
+        # stays finished without a reset is not scored again
+        if getattr(self, "_scored", None) is None:
+            self._scored = torch.zeros(self.num_envs, dtype=torch.bool, device=self.device)
+        todo = self._t["done"].bool() & ~self._scored
+        if not bool(todo.any()):
             return {}
-        out = side_effect_score_batch(self, num_samples=int(self.side_effect_samples), strkeys=True)
+        self._scored |= todo
+        out = side_effect_score_batch(self, mask=todo, num_samples=int(self.side_effect_samples),
+                                      strkeys=True)
         if self.side_effect_weights is not None:
             for scores in out.values():
                 total = np.zeros(2)
@@ -336,6 +366,8 @@ class BatchedSafeLifeEnv(object):
         (training/base_algo.py:231-236).  Episode totals stay readable.  Returns obs.
         """
         mask = self._t["done"] if mask is None else mask.to(torch.uint8)
+        if getattr(self, "_scored", None) is not None:
+            self._scored &= ~mask.bool()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.sl_env_reset(
                 self._batch_ref, mask.data_ptr(), None,

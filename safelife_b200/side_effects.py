@@ -188,7 +188,7 @@ def side_effect_score_batch(env, mask=None, num_samples=1000, num_runs=1, includ
         return {}
     lvl = t["level_id"][idx].long()
     init = env._pool_t["pool_board"][lvl].contiguous()
-    final = env.board[idx].contiguous()
+    final = t["board"][idx].contiguous()          # int16 storage of the uint16 boards
     num_steps = t["num_steps"][idx].contiguous()
     thr = env._pool_t["pool_spawn_thr"][lvl].contiguous()
     stochastic = ((init & SPAWNING) != 0).flatten(1).any(1)      # side_effects.py:103-104
@@ -202,6 +202,7 @@ def side_effect_score_batch(env, mask=None, num_samples=1000, num_runs=1, includ
     counts_np = counts.cpu().numpy()
     init_np = init.cpu().numpy().view(np.uint16)
     final_np = final.cpu().numpy().view(np.uint16)
+    assert init_np.dtype == final_np.dtype == np.uint16
     out = {}
     for k, e in enumerate(idx.tolist()):
         # a deterministic board ran `runs` identical simulations: same

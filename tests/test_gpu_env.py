@@ -14,16 +14,26 @@ from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [1, 2]   # generic CTA-per-env, warp bit-plane
+# generic CTA-per-env; warp bit-plane with the goal planes resident in shared
+# memory; warp bit-plane with the goal planes left in HBM (forced, so that pools
+# with dynamic goals exercise its scratch-slab path)
+KERNELS = [1, 2, "2-in-place"]
+
+
+def _mode(kernel):
+    """(kernel id, goals_in_place) of a KERNELS entry."""
+    return (2, True) if kernel == "2-in-place" else (kernel, False)
 
 
 def _make_env(levels, n, time_limit, kernel, rng=None, **kw):
     from safelife_b200.env import BatchedSafeLifeEnv
     H, W = levels[0]["board"].shape
     from safelife_b200 import _lib
+    kernel, in_place = _mode(kernel)
     if kernel == 2 and not _lib.lib().sl_warp_kernel_supported(H, W):
         pytest.skip("warp kernel does not handle %dx%d boards" % (H, W))
-    env = BatchedSafeLifeEnv(levels, n, time_limit=time_limit, kernel=kernel, auto_reset=False, **kw)
+    env = BatchedSafeLifeEnv(levels, n, time_limit=time_limit, kernel=kernel, auto_reset=False,
+                             goals_in_place=in_place, **kw)
     if rng is not None:
         env.set_rng_state(np.asarray(rng, dtype=np.uint64))
     return env
@@ -129,9 +139,9 @@ def test_auto_reset_cycles_levels(kernel):
     L, n = len(levels), 5
     from safelife_b200.env import BatchedSafeLifeEnv
     from safelife_b200 import _lib
-    if kernel == 2 and not _lib.lib().sl_warp_kernel_supported(10, 10):
-        pytest.skip("warp kernel not available")
-    env = BatchedSafeLifeEnv(levels, n, time_limit=7, kernel=kernel, view_shape=(5, 5))
+    kernel, in_place = _mode(kernel)
+    env = BatchedSafeLifeEnv(levels, n, time_limit=7, kernel=kernel, view_shape=(5, 5),
+                             goals_in_place=in_place)
     env.reset()
     assert env._t["level_id"].tolist() == [0, 1, 2, 3, 4]
     pool_after_reset = None
@@ -177,15 +187,14 @@ def test_full_size_properties(kernel):
     from safelife_b200 import _lib
     from safelife_b200.env import BatchedSafeLifeEnv
     from safelife_b200.levels import load_levels
-    if kernel == 2 and not _lib.lib().sl_warp_kernel_supported(25, 25):
-        pytest.skip("warp kernel not available")
+    kernel, in_place = _mode(kernel)
     levels = load_levels(pool_path)
     N, T = 4096, 30
     acts = np.random.default_rng(2).integers(0, 9, (T, N)).astype(np.uint8)
 
     def run(lo, hi):
         env = BatchedSafeLifeEnv([levels[i % len(levels)] for i in range(lo, hi)], hi - lo,
-                                 kernel=kernel, auto_reset=False, seed=1)
+                                 kernel=kernel, auto_reset=False, seed=1, goals_in_place=in_place)
         from safelife_b200.env import seed_rng_states
         env.set_rng_state(seed_rng_states(1, N)[lo:hi])
         env.reset()
@@ -234,15 +243,16 @@ def test_step_host_zero_copy_matches_device_path():
     assert d.dtype == np.uint8 and r.dtype == np.float32
 
 
+@pytest.mark.parametrize("in_place", [False, True])
 @pytest.mark.parametrize("n", [592 * 8 + 8, 592 * 8 * 2 + 13, 20011])
-def test_pipelined_kernel_large_batches_vs_oracle(n):
+def test_pipelined_kernel_large_batches_vs_oracle(n, in_place):
     """Batches large enough for the persistent pipelined kernel (plus a ragged tail)."""
     rs = np.random.default_rng(n)
     base = _random_levels(rs, 64, 25, 25)
     levels = [base[i % 64] for i in range(n)]
     rng = np.stack([orc.rng_from_seed(i % 997) for i in range(n)])
     from safelife_b200.env import BatchedSafeLifeEnv
-    env = BatchedSafeLifeEnv(base, n, time_limit=9, auto_reset=True, kernel=2)
+    env = BatchedSafeLifeEnv(base, n, time_limit=9, auto_reset=True, kernel=2, goals_in_place=in_place)
     env.set_rng_state(rng)
     env.reset()
     idx = np.unique(np.concatenate([np.arange(0, n, 211), [n - 1, n - 2, n - 9, 4735, 4736, 4744]]))

@@ -208,20 +208,23 @@ def test_env_reports_side_effects_at_episode_end():
     levels = gu.levels_of(d)
     n = len(levels)
     weights = {"life-green": 1.0, "spawner-yellow": 2.0}
-    env = BatchedSafeLifeEnv(levels, n, device="cuda:0", time_limit=12, auto_reset=True,
+    env = BatchedSafeLifeEnv(levels, n, device="cuda:0", time_limit=12, auto_reset=False,
                              should_calculate_side_effects=True, side_effect_weights=weights,
                              side_effect_samples=60)
     env.set_rng_state(d["rng_init"])
     ora = orc.OracleEnv(levels, list(d["rng_init"]), time_limit=12)
     env.reset()
     seen = 0
+    finished = np.zeros(n, dtype=bool)
     for t in range(12):
         a = d["action"][:, t]
         obs, reward, done, info = env.step(a)
         r0, d0 = ora.step(a.astype(np.int64))
         assert np.array_equal(done.cpu().numpy(), d0)
         se_info = info["episode"].get("side_effects", {})
-        assert set(se_info) == set(np.flatnonzero(d0).tolist())
+        newly = d0 & ~finished          # scored once, when the episode ends
+        finished |= d0
+        assert set(se_info) == set(np.flatnonzero(newly).tolist())
         for e, scores in se_info.items():
             rng = ora.rng[e].copy()
             want, _ = orc.side_effect_score(levels[e]["board"], ora.board[e], int(ora.num_steps[e]),
