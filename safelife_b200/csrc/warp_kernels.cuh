@@ -80,6 +80,33 @@ template <class P> struct RowDeltaT {
 };
 
 // ------------------------------------------------------ 32-cell transposes
+// The integer ALU pipe (LOP3 / SHF / PRMT, one warp instruction per two cycles
+// per scheduler) is what bounds the step kernel, so the transposes are written
+// to spend as little of it as possible: a butterfly half is ONE three-input
+// LOP3 (bit select under an immediate mask) on top of one shift, left shifts
+// and the 16-bit packing go to the FMA pipe as multiply-adds.
+
+// (a & mask) | (b & ~mask) in one LOP3.
+__device__ __forceinline__ uint32_t bitsel(uint32_t a, uint32_t b, uint32_t mask) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE2;" : "=r"(d) : "r"(a), "r"(mask), "r"(b));
+    return d;
+}
+// lo | hi << 16 for two 16-bit values, as a multiply-add.
+__device__ __forceinline__ uint32_t pack16(uint32_t lo, uint32_t hi) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, 65536, %2;" : "=r"(d) : "r"(hi), "r"(lo));
+    return d;
+}
+// One butterfly stage on the pair (a, b): a keeps its bits under ~MASK << 0 ...
+// i.e. a' = (a & ~MASK) | ((b << S) & MASK),  b' = ((a >> S) & ~MASK) | (b & MASK).
+template <int S, uint32_t MASK>
+__device__ __forceinline__ void butterfly(uint32_t &a, uint32_t &b) {
+    const uint32_t a2 = bitsel(b << S, a, MASK);
+    b = bitsel(b, a >> S, MASK);
+    a = a2;
+}
+
 // 16 cell-pair words -> 16 plane words.  x[k] = cell(k) | cell(k+16) << 16.
 __device__ __forceinline__ void transpose16(uint32_t (&x)[16]) {
 #pragma unroll
@@ -91,46 +118,29 @@ __device__ __forceinline__ void transpose16(uint32_t (&x)[16]) {
 #pragma unroll
     for (int k = 0; k < 16; k++) {           // nibbles
         if (k & 4) continue;
-        uint32_t a = x[k], b = x[k + 4];
-        x[k] = (a & 0x0f0f0f0fu) | ((b << 4) & 0xf0f0f0f0u);
-        x[k + 4] = ((a >> 4) & 0x0f0f0f0fu) | (b & 0xf0f0f0f0u);
+        butterfly<4, 0xf0f0f0f0u>(x[k], x[k + 4]);
     }
 #pragma unroll
     for (int k = 0; k < 16; k++) {           // bit pairs
         if (k & 2) continue;
-        uint32_t a = x[k], b = x[k + 2];
-        x[k] = (a & 0x33333333u) | ((b << 2) & 0xccccccccu);
-        x[k + 2] = ((a >> 2) & 0x33333333u) | (b & 0xccccccccu);
+        butterfly<2, 0xccccccccu>(x[k], x[k + 2]);
     }
 #pragma unroll
-    for (int k = 0; k < 16; k += 2) {        // bits
-        uint32_t a = x[k], b = x[k + 1];
-        x[k] = (a & 0x55555555u) | ((b << 1) & 0xaaaaaaaau);
-        x[k + 1] = ((a >> 1) & 0x55555555u) | (b & 0xaaaaaaaau);
-    }
+    for (int k = 0; k < 16; k += 2)          // bits
+        butterfly<1, 0xaaaaaaaau>(x[k], x[k + 1]);
 }
 
 // 8 words of 4 bytes (cells i, i+8, i+16, i+24) -> 8 plane words (index = bit).
 __device__ __forceinline__ void transpose8(uint32_t (&x)[8]) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        uint32_t a = x[k], b = x[k + 4];
-        x[k] = (a & 0x0f0f0f0fu) | ((b << 4) & 0xf0f0f0f0u);
-        x[k + 4] = ((a >> 4) & 0x0f0f0f0fu) | (b & 0xf0f0f0f0u);
-    }
+    for (int k = 0; k < 4; k++) butterfly<4, 0xf0f0f0f0u>(x[k], x[k + 4]);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
         if (k & 2) continue;
-        uint32_t a = x[k], b = x[k + 2];
-        x[k] = (a & 0x33333333u) | ((b << 2) & 0xccccccccu);
-        x[k + 2] = ((a >> 2) & 0x33333333u) | (b & 0xccccccccu);
+        butterfly<2, 0xccccccccu>(x[k], x[k + 2]);
     }
 #pragma unroll
-    for (int k = 0; k < 8; k += 2) {
-        uint32_t a = x[k], b = x[k + 1];
-        x[k] = (a & 0x55555555u) | ((b << 1) & 0xaaaaaaaau);
-        x[k + 1] = ((a >> 1) & 0x55555555u) | (b & 0xaaaaaaaau);
-    }
+    for (int k = 0; k < 8; k += 2) butterfly<1, 0xaaaaaaaau>(x[k], x[k + 1]);
 }
 
 // Planes of the low (SEL 0x6240) or high (SEL 0x7351) byte of 32 consecutive
@@ -140,8 +150,8 @@ template <unsigned SEL>
 __device__ __forceinline__ void planes32(const uint16_t *cells, uint32_t (&x)[8]) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        uint32_t a = __byte_perm(cells[k], cells[k + 16], 0x5410);
-        uint32_t b = __byte_perm(cells[k + 8], cells[k + 24], 0x5410);
+        uint32_t a = pack16(cells[k], cells[k + 16]);
+        uint32_t b = pack16(cells[k + 8], cells[k + 24]);
         x[k] = __byte_perm(a, b, SEL);
     }
     transpose8(x);
@@ -638,11 +648,11 @@ struct CtaShared {
 // its goals slab in shared memory (GR) or in HBM (in place).  Returns true if a
 // shared-memory goals slab was modified.
 template <class G, bool GR>
-__device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShared &cs,
+__device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShared &cs, const G &t,
                                              SlEnvState *st, uint16_t *board, uint16_t *goals,
-                                             uint64_t *goals_bar, int action, int lane) {
+                                             uint64_t *goals_bar, int action) {
     typedef typename G::P P;
-    const int H = B.H, W = B.W;
+    const int H = B.H, W = B.W, lane = t.lane;
     bool goals_dirty = false;
     const uint64_t thr = st->spawn_thr;
     u128 state = {st->rng[0], st->rng[1]};
@@ -682,7 +692,6 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShare
         after = mine ? board[idx] : 0u;
     }
 
-    const G t(H, W, lane);
     {
         const LowPlanesT<P> p = t.load_low(board);
         const RowDeltaT<P> d = stencil_planes(t, p, [&] { return t.load_high(board); });
@@ -832,9 +841,9 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
 
     bool goals_dirty = false;
     if (warp < nenv)
-        goals_dirty = step_phase_a<G, GR>(B, cs, sstate + warp, sboard + warp * cells,
+        goals_dirty = step_phase_a<G, GR>(B, cs, G(B.H, B.W, lane), sstate + warp, sboard + warp * cells,
                                           GR ? sgoals + warp * cells : ggoals + (size_t)warp * cells,
-                                          GR && bulk ? bar + 1 : nullptr, action, lane);
+                                          GR && bulk ? bar + 1 : nullptr, action);
     else if (GR && bulk) mbar_wait(bar + 1, 0);
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
     SL_TRACE_MARK(threadIdx.x == 0, 2);
@@ -933,9 +942,8 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
         if (lane == 0)
             for (int s = 0; s < STAGES; s++)
                 if (first + s * stride < n_groups) issue_load(s, first + s * stride);
-        int it = 0;
-        for (int g = first; g < n_groups; g += stride, it++) {
-            const int s = it % STAGES, parity = (it / STAGES) & 1;
+        int s = 0, parity = 0;
+        for (int g = first; g < n_groups; g += stride) {
             mbar_wait_parked(fin + s, parity, PIPE_PARK_NS);
             const int e0 = g * WARP_ENVS_PER_CTA;
             bool goals_dirty = GR && lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
@@ -953,22 +961,38 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
                 if (gn < n_groups) issue_load(s, gn);
             }
             __syncwarp();
+            if (++s == STAGES) {
+                s = 0;
+                parity ^= 1;
+            }
         }
     } else {
         // ---- stencil warp w: phase A of env w of every group of this CTA
-        int it = 0;
-        for (int g = first; g < n_groups; g += stride, it++) {
-            const int s = it % STAGES, parity = (it / STAGES) & 1;
+        const Narrow t(B.H, B.W, lane);                 // row masks, neighbour lanes: once per warp
+        const int env_bytes = cells * 2;
+        unsigned char *my = stages + warp * env_bytes;  // this warp's slot inside a stage
+        int s = 0, parity = 0;
+        int next_action = first < n_groups ? actions[(size_t)first * WARP_ENVS_PER_CTA + warp] : 0;
+        for (int g = first; g < n_groups; g += stride) {
             const size_t e = (size_t)g * WARP_ENVS_PER_CTA + warp;
-            const int action = actions[e];
+            const int action = next_action;             // fetched one group ahead
+            if (g + stride < n_groups)
+                next_action = actions[(size_t)(g + stride) * WARP_ENVS_PER_CTA + warp];
+            unsigned char *stage = my + s * stage_bytes;
             mbar_wait_parked(full + s, parity, PIPE_PARK_NS);
             const bool gd = step_phase_a<Narrow, GR>(
-                B, cs, stage_state(s) + warp, stage_board(s) + warp * cells,
-                GR ? stage_goals(s) + warp * cells : B.goals + e * cells, nullptr, action, lane);
+                B, cs, t, (SlEnvState *)(stages + s * stage_bytes) + warp,
+                (uint16_t *)(stage + WARP_SMEM_STATE),
+                GR ? (uint16_t *)(stage + WARP_SMEM_STATE + warp_slab_stride(cells)) : B.goals + e * cells,
+                nullptr, action);
             if (GR && lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(fin + s);
+            if (++s == STAGES) {
+                s = 0;
+                parity ^= 1;
+            }
         }
     }
 }
@@ -1023,7 +1047,7 @@ inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, in
     }
     // pipelining pays once a CTA slot sees more than one group
     static const int shape_knob = env_knob("SAFELIFE_B200_PIPE_SHAPE", 0);   // stages * 10 + ctas
-    const int want = shape_knob ? shape_knob : (gr ? 33 : 44);
+    const int want = shape_knob ? shape_knob : (gr ? 33 : 53);
     int piped = 0;
     if (bulk_ok && full_groups > sm_count * (want % 10)) {
 #define SL_TRY_SHAPE(S, C, R)                                                          \
