@@ -51,12 +51,13 @@ def parse_args():
     return ap.parse_args()
 
 
-def measured_traffic(n, H, W):
+def measured_traffic(plan, n, H, W):
     """DRAM bytes per launch of the step kernel from the committed ncu capture, or None."""
     path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    kernel = plan.split("<")[0] + ("/in-place" if "in place" in plan else "/resident")
     try:
         with open(path) as f:
-            entry = json.load(f)["k_env_step_warp"].get("%dx%dx%d" % (n, H, W))
+            entry = json.load(f)[kernel].get("%dx%dx%d" % (n, H, W))
         return entry["dram_bytes_read"] + entry["dram_bytes_write"] if entry else None
     except (OSError, KeyError, ValueError):
         return None
@@ -284,8 +285,10 @@ def sweep(args, levels, dev, peak):
         torch.cuda.synchronize()
         ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
         gbs = n * (6 * H * W + 64) / (ms * 1e-3) / 1e9
+        plan = env.step_plan()[0]
+        traffic = measured_traffic(plan, n, H, W)
         out.append({"envs": n, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3),
-                    "achieved_gbs": gbs, "frac": gbs / peak})
+                    "achieved_gbs": gbs, "frac": gbs / peak, "kernel": plan, "traffic": traffic})
         del env
     return out
 
@@ -316,7 +319,11 @@ def run_ours(args, levels):
     lo = rank * n                      # contiguous env range of this rank
     my_levels = [levels[(lo + i) % len(levels)] for i in range(n)]
     H, W = levels[0]["board"].shape
-    env = BatchedSafeLifeEnv(my_levels, n, device=dev, kernel=args.kernel, time_limit=1000)
+    # observations as the reference's training envs take them (env_factory.py:301-327):
+    # 25x25 view, 15 channels; timed separately below, not part of `value`
+    train_channels = (0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 25, 26, 27, 12, 13)
+    env = BatchedSafeLifeEnv(my_levels, n, device=dev, kernel=args.kernel, time_limit=1000,
+                             view_shape=(25, 25), output_channels=train_channels)
     env.set_rng_state(seed_rng_states(4, n * world)[lo:lo + n])   # global-index-derived streams
     env.reset()
     K, Wm = args.steps, args.warmup
@@ -327,9 +334,11 @@ def run_ours(args, levels):
     lib, bref = env._lib, env._batch_ref
     from safelife_b200 import _lib
     stream = env._stream()
-    # generic kernel: the auto-reset is a second (masked) launch; warp kernel: fused
+    # generic kernel: the auto-reset is a second (masked) launch; warp kernels: fused
     fused = bool(lib.sl_warp_kernel_supported(H, W)) and args.kernel != 1
-    launches_per_step = 1 if fused else 2
+    plan, launches_per_step = env.step_plan()
+    if not fused:
+        launches_per_step += 1
 
     def step_kernels(t):
         _lib.check(lib.sl_env_step(bref, actions[t].data_ptr(), args.kernel,
@@ -393,6 +402,32 @@ def run_ours(args, levels):
         cp_ev[t][1].synchronize()
     barrier()
     e2e_copy_ms = sum(e[0].elapsed_time(e[1]) for e in cp_ev)
+
+    # ---- supplementary: the rollout regime, K steps back to back with the state
+    # L2-resident (no flush, one event pair); not the headline (timing rules) ----
+    l2_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    l2_ev[0].record()
+    for t in range(K):
+        step_kernels(Wm + t)
+    l2_ev[1].record()
+    barrier()
+    l2_ms = l2_ev[0].elapsed_time(l2_ev[1])
+
+    # ---- supplementary: SafeLifeEnv.get_obs for the whole batch (next row 8f-1) ----
+    Ko = min(K, 100)
+    obs_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(Ko)]
+    env.get_obs()
+    barrier()
+    for t in range(Ko):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        obs_ev[t][0].record()
+        env.get_obs()
+        obs_ev[t][1].record()
+    barrier()
+    obs_ms = sum(e[0].elapsed_time(e[1]) for e in obs_ev) / Ko
+    obs_bytes = n * (4 * H * W + 25 * 25 * len(train_channels))
     if sampler:
         sampler.mark()
     clocks = sampler.stop() if sampler else None
@@ -432,13 +467,23 @@ def run_ours(args, levels):
             "gpu_launches": launches_per_step * K,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": measured_traffic(n, H, W),
-                "kernel": "k_env_step_warp" if fused else "k_env_step_generic",
+                "frac": achieved / peak, "traffic": measured_traffic(plan, n, H, W),
+                "kernel": plan,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms": step_ms / K, "dynamic_goal_envs": dyn,
             },
             "wall_s_timed_region": wall,
+            "obs": {
+                "ms": obs_ms, "bytes_per_launch": obs_bytes,
+                "achieved_gbs": obs_bytes / (obs_ms * 1e-3) / 1e9,
+                "note": "supplementary: k_get_obs, uint8[N,25,25,15] training observations "
+                        "(read board + goals, write obs), L2 flushed; rank 0"},
+            "back_to_back": {
+                "ms_per_step": l2_ms / K, "env_steps_per_s": n * K / (l2_ms * 1e-3),
+                "note": "supplementary: %d steps queued back to back, no L2 flush (state %s the "
+                        "126 MB L2), one event pair; rank 0" % (
+                            K, "fits" if n * 4 * H * W < 100e6 else "exceeds")},
         }
         if not args.no_sweep and world == 1:
             line["sweep"] = sweep(args, levels, dev, peak)

@@ -228,6 +228,12 @@ typedef struct SlEnvBatch {
 int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                 void *stream);
 
+/* Which kernel(s) sl_env_step(batch, ..., kernel, ...) launches on the current
+ * device, as text (for benchmarks and profiles), and how many launches that is
+ * per step without SL_STEP_AUTO_RESET on the generic path.  Launches nothing. */
+int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_len,
+                     int *n_launches);
+
 /* sl_env_step followed by a wait for the stream: for host-driven loops.  The
  * batch's actions / reward / done / success / times_up pointers may be pinned
  * host memory (device-addressable under UVA); the kernel then reads and writes
@@ -252,8 +258,8 @@ int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *ne
 /* SafeLifeEnv.get_obs (safelife_env.py:105-146) with recenter_view
  * (helper_utils.py:42-75): agent-centred toroidal view of board | goal
  * colours << 16, exit cells outside the view clamped to its perimeter.
- * n_channels > 0: obs is uint8[n_envs][vh][vw][n_channels] with
- * obs[...,k] = (view >> channels[k]) & 1 (channels: device int32);
+ * 0 < n_channels <= 32: obs is uint8[n_envs][vh][vw][n_channels] with
+ * obs[...,k] = (view >> channels[k]) & 1 (channels: device int32, each 0..31);
  * n_channels == 0: obs is uint32[n_envs][vh][vw] (output_channels=None). */
 int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw,
                const int32_t *channels, int n_channels, int remove_white_goals,

@@ -447,6 +447,44 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
     return sl_env_reset(batch, batch->done, nullptr, SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS, stream);
 }
 
+int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_len,
+                     int *n_launches) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
+    char buf[256];
+    int launches = 0;
+    const bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
+    if (batch->n_envs == 0) {
+        snprintf(buf, sizeof buf, "nothing to launch");
+    } else if (kernel == 2 || (kernel == 0 && warp_ok)) {
+        if (!warp_ok) return fail(SL_ERR_ARG, "warp kernel needs 3 <= H, W <= %d", sl::WARP_MAX_DIM);
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        const sl::StepPlan p = sl::plan_env_step_warp(*batch, props.sm_count, props.smem_per_sm);
+        const char *goals = p.goals_resident ? "goals resident" : "goals in place";
+        int n = 0;
+        if (p.piped_groups > 0) {
+            n += snprintf(buf + n, sizeof buf - n, "k_env_step_pipe<%d stages, %d CTAs/SM, %s> grid %d",
+                          p.pipe_stages, p.pipe_ctas, goals, p.pipe_grid);
+            launches++;
+        }
+        if (p.single_groups > 0) {
+            n += snprintf(buf + n, sizeof buf - n, "%sk_env_step_warp<%s, %s> grid %d", n ? " + " : "",
+                          p.narrow ? "Narrow" : "Wide", goals, p.single_groups);
+            launches++;
+        }
+    } else {
+        snprintf(buf, sizeof buf, "k_env_step_generic grid %d (+ k_env_reset with SL_STEP_AUTO_RESET)",
+                 grid_for(batch->n_envs));
+        launches = 1;
+    }
+    if (text && text_len > 0) snprintf(text, (size_t)text_len, "%s", buf);
+    if (n_launches) *n_launches = launches;
+    return SL_OK;
+}
+
 int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                      void *stream) {
     int rc = sl_env_step(batch, actions, kernel, flags, stream);
@@ -475,6 +513,7 @@ int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw, const int32_t
     int rc = check_batch(batch);
     if (rc) return rc;
     if (vh < 1 || vw < 1 || n_channels < 0) return fail(SL_ERR_ARG, "bad view shape");
+    if (n_channels > 32) return fail(SL_ERR_ARG, "at most 32 output channels (bits of the uint32 view)");
     if (batch->n_envs == 0) return SL_OK;
     if (!obs || (n_channels > 0 && !channels)) return fail(SL_ERR_ARG, "null pointer");
     size_t smem = (size_t)vh * vw * 4;

@@ -529,8 +529,11 @@ __global__ void __launch_bounds__(GENERIC_THREADS)
 k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
           const int32_t *__restrict__ channels, int n_channels, int remove_white) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int ch[32];
     uint32_t *view = (uint32_t *)smem_raw;
     const int H = B.H, W = B.W, cells = H * W, vcells = vh * vw;
+    if (threadIdx.x < n_channels) ch[threadIdx.x] = channels[threadIdx.x] & 31;
+    __syncthreads();
     for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
         const uint16_t *board = B.board + (size_t)e * cells;
         const uint16_t *goals = B.goals + (size_t)e * cells;
@@ -566,11 +569,44 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
             uint32_t *o = (uint32_t *)obs + (size_t)e * vcells;
             for (int i = threadIdx.x; i < vcells; i += blockDim.x) o[i] = view[i];
         } else {
-            uint8_t *o = (uint8_t *)obs + (size_t)e * vcells * n_channels;
-            const int total = vcells * n_channels;
-            for (int i = threadIdx.x; i < total; i += blockDim.x) {
-                int cell = i / n_channels, k = i - cell * n_channels;
-                o[i] = (uint8_t)((view[cell] >> __ldg(channels + k)) & 1u);
+            // Each view word becomes its channel mask (bit k = channel k of the cell), so
+            // the output is the bit stream of those masks, one byte per bit.  It is
+            // written 16 bytes at a time: 16 stream bits gathered from the (at most a
+            // few) cells they straddle, four bits -> four 0/1 bytes by one multiply.
+            const int C = n_channels;
+            for (int i = threadIdx.x; i < vcells; i += blockDim.x) {
+                const uint32_t v = view[i];
+                uint32_t m = 0;
+                for (int k = 0; k < C; k++) m |= ((v >> ch[k]) & 1u) << k;
+                view[i] = m;
+            }
+            __syncthreads();
+            uint8_t *o = (uint8_t *)obs + (size_t)e * vcells * C;
+            const int total = vcells * C;
+            const int head = min(total, (int)((16u - (unsigned)((uintptr_t)o & 15u)) & 15u));
+            const int nchunks = (total - head) >> 4;
+            auto bit_at = [&](int i) -> uint8_t {
+                const int cell = i / C;
+                return (uint8_t)((view[cell] >> (i - cell * C)) & 1u);
+            };
+            for (int i = threadIdx.x; i < head; i += blockDim.x) o[i] = bit_at(i);
+            for (int i = head + (nchunks << 4) + threadIdx.x; i < total; i += blockDim.x) o[i] = bit_at(i);
+            uint4 *o16 = (uint4 *)(o + head);
+            for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
+                const int i0 = head + (c << 4);
+                int cell = i0 / C;
+                const int k = i0 - cell * C;
+                uint32_t bits = view[cell] >> k;
+                for (int have = C - k; have < 16; have += C) {
+                    cell++;
+                    bits |= (cell < vcells ? view[cell] : 0u) << have;
+                }
+                uint4 w;
+                w.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+                w.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+                w.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+                w.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+                o16[c] = w;
             }
         }
         __syncthreads();

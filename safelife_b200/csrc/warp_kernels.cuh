@@ -1003,17 +1003,6 @@ struct PipeShape {
     int stages, ctas;
 };
 
-template <int STAGES, int CTAS, bool GR>
-inline void launch_pipe(const SlEnvBatch &B, const uint8_t *actions, int flags, int full_groups,
-                        int sm_count, cudaStream_t st) {
-    const int cells = B.H * B.W;
-    const int slots = sm_count * CTAS;
-    const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
-    const int grid = (full_groups + per_cta - 1) / per_cta;
-    k_env_step_pipe<STAGES, CTAS, GR><<<grid, PIPE_THREADS, pipe_smem_bytes(cells, STAGES, GR), st>>>(
-        B, actions, flags, full_groups);
-}
-
 inline int env_knob(const char *name, int fallback) {
     const char *v = getenv(name);
     return v ? atoi(v) : fallback;
@@ -1026,53 +1015,82 @@ inline bool pipe_shape_fits(int cells, int stages, int ctas, bool gr, int smem_p
     return ctas * (pipe_smem_bytes(cells, stages, gr) + 1024) <= (size_t)smem_per_sm;
 }
 
-inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
-                                 int sm_count, int smem_per_sm, cudaStream_t st) {
+// What sl_env_step launches for a batch on the warp path.
+struct StepPlan {
+    bool narrow, goals_resident;
+    int bulk_ok;
+    int pipe_stages, pipe_ctas;     // 0, 0: no pipelined launch
+    int pipe_grid, piped_groups;    // persistent CTAs and the groups they cover
+    int single_groups;              // groups left to the single-pass kernel (one CTA each)
+};
+
+inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_per_sm) {
+    StepPlan p = {};
     const int cells = B.H * B.W;
     const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
     const int full_groups = B.n_envs / WARP_ENVS_PER_CTA;
-    const int bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
+    p.bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
     static const bool in_place_ok = env_knob("SAFELIFE_B200_GOALS_IN_PLACE", 1) != 0;
-    const bool gr = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok);
-    if (!warp_kernel_is_narrow(B.H, B.W)) {
-        if (gr)
-            k_env_step_warp<Wide, true><<<groups, WARP_ENVS_PER_CTA * 32,
-                                          warp_step_smem_bytes<Wide>(cells, true), st>>>(
-                B, actions, bulk_ok, flags, 0);
-        else
-            k_env_step_warp<Wide, false><<<groups, WARP_ENVS_PER_CTA * 32,
-                                           warp_step_smem_bytes<Wide>(cells, false), st>>>(
-                B, actions, bulk_ok, flags, 0);
-        return;
-    }
+    p.goals_resident = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok);
+    p.narrow = warp_kernel_is_narrow(B.H, B.W);
+    p.single_groups = groups;
+    if (!p.narrow) return p;
     // pipelining pays once a CTA slot sees more than one group
     static const int shape_knob = env_knob("SAFELIFE_B200_PIPE_SHAPE", 0);   // stages * 10 + ctas
-    const int want = shape_knob ? shape_knob : (gr ? 33 : 53);
-    int piped = 0;
-    if (bulk_ok && full_groups > sm_count * (want % 10)) {
-#define SL_TRY_SHAPE(S, C, R)                                                          \
-        if (!piped && R == gr && want == S * 10 + C &&                                 \
-            pipe_shape_fits(cells, S, C, R, smem_per_sm)) {                            \
-            launch_pipe<S, C, R>(B, actions, flags, full_groups, sm_count, st);        \
-            piped = full_groups;                                                       \
-        }
-        SL_PIPE_SHAPES(SL_TRY_SHAPE)
-#undef SL_TRY_SHAPE
-        if (!piped) {     // a board too large for the wanted shape: the smallest one
-            if (gr) launch_pipe<2, 4, true>(B, actions, flags, full_groups, sm_count, st);
-            else launch_pipe<3, 4, false>(B, actions, flags, full_groups, sm_count, st);
-            piped = full_groups;
-        }
+    int want = shape_knob ? shape_knob : (p.goals_resident ? 33 : 53);
+    bool known = false;
+#define SL_KNOWN_SHAPE(S, C, R)                                                        \
+    known |= R == p.goals_resident && want == S * 10 + C &&                            \
+             pipe_shape_fits(cells, S, C, R, smem_per_sm);
+    SL_PIPE_SHAPES(SL_KNOWN_SHAPE)
+#undef SL_KNOWN_SHAPE
+    if (!known) want = p.goals_resident ? 24 : 34;    // a large board: the smallest shape
+    const int stages = want / 10, ctas = want % 10;
+    if (p.bulk_ok && full_groups > sm_count * ctas) {
+        const int slots = sm_count * ctas;
+        const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
+        p.pipe_stages = stages;
+        p.pipe_ctas = ctas;
+        p.pipe_grid = (full_groups + per_cta - 1) / per_cta;
+        p.piped_groups = full_groups;
+        p.single_groups = groups - full_groups;
     }
-    if (groups > piped) {
-        if (gr)
-            k_env_step_warp<Narrow, true><<<groups - piped, WARP_ENVS_PER_CTA * 32,
-                                            warp_step_smem_bytes<Narrow>(cells, true), st>>>(
-                B, actions, bulk_ok, flags, piped);
+    return p;
+}
+
+inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
+                                 int sm_count, int smem_per_sm, cudaStream_t st) {
+    const StepPlan p = plan_env_step_warp(B, sm_count, smem_per_sm);
+    const int cells = B.H * B.W;
+    const int threads = WARP_ENVS_PER_CTA * 32;
+    if (!p.narrow) {
+        if (p.goals_resident)
+            k_env_step_warp<Wide, true><<<p.single_groups, threads,
+                                          warp_step_smem_bytes<Wide>(cells, true), st>>>(
+                B, actions, p.bulk_ok, flags, 0);
         else
-            k_env_step_warp<Narrow, false><<<groups - piped, WARP_ENVS_PER_CTA * 32,
+            k_env_step_warp<Wide, false><<<p.single_groups, threads,
+                                           warp_step_smem_bytes<Wide>(cells, false), st>>>(
+                B, actions, p.bulk_ok, flags, 0);
+        return;
+    }
+    if (p.piped_groups > 0) {
+#define SL_LAUNCH_SHAPE(S, C, R)                                                               \
+        if (R == p.goals_resident && S == p.pipe_stages && C == p.pipe_ctas)                   \
+            k_env_step_pipe<S, C, R><<<p.pipe_grid, PIPE_THREADS, pipe_smem_bytes(cells, S, R), st>>>( \
+                B, actions, flags, p.piped_groups);
+        SL_PIPE_SHAPES(SL_LAUNCH_SHAPE)
+#undef SL_LAUNCH_SHAPE
+    }
+    if (p.single_groups > 0) {
+        if (p.goals_resident)
+            k_env_step_warp<Narrow, true><<<p.single_groups, threads,
+                                            warp_step_smem_bytes<Narrow>(cells, true), st>>>(
+                B, actions, p.bulk_ok, flags, p.piped_groups);
+        else
+            k_env_step_warp<Narrow, false><<<p.single_groups, threads,
                                              warp_step_smem_bytes<Narrow>(cells, false), st>>>(
-                B, actions, bulk_ok, flags, piped);
+                B, actions, p.bulk_ok, flags, p.piped_groups);
     }
 }
 

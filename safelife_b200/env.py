@@ -123,6 +123,8 @@ class BatchedSafeLifeEnv(object):
             self.observation_space = Box(0, 2 ** 15, self.view_shape, np.uint32)
         else:
             self.output_channels = tuple(int(c) for c in self.output_channels)
+            if len(self.output_channels) > 32 or any(c < 0 or c > 31 for c in self.output_channels):
+                raise ValueError("output_channels must be at most 32 bit positions of the uint32 view")
             self.observation_space = Box(0, 1, self.view_shape + (len(self.output_channels),),
                                          np.uint8)
         N, H, W, dev = self.num_envs, self.pool.H, self.pool.W, self.device
@@ -269,6 +271,15 @@ class BatchedSafeLifeEnv(object):
             _lib.check(self._lib.sl_env_step(
                 self._batch_ref, self._actions.data_ptr(), self.kernel,
                 _lib.SL_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
+
+    def step_plan(self):
+        """(description, launches per step) of what sl_env_step runs for this batch."""
+        buf = ctypes.create_string_buffer(256)
+        n = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_env_step_plan(self._batch_ref, self.kernel, buf, 256,
+                                                  ctypes.byref(n)))
+        return buf.value.decode(), int(n.value)
 
     def enable_host_io(self):
         """
