@@ -524,15 +524,36 @@ k_env_reset(SlEnvBatch B, const uint8_t *__restrict__ mask, const int32_t *__res
 }
 
 // SafeLifeEnv.get_obs (safelife_env.py:105-146, helper_utils.py:42-75).
-// One CTA per env: build the uint32 view in shared memory, then expand.
+// One CTA per env: build the uint32 view in shared memory, then expand.  The
+// kernel is instruction-bound unless the index arithmetic stays out of the
+// per-cell loops, so: wrapped source rows / columns come from two small tables
+// built once per env, the channel list is applied as runs of consecutive bits
+// (the training list (0-4, 7-11, 25-27, 12-13) is four runs, not fifteen bits),
+// and the byte stream is written 16 bytes per store with stepping indices.
 __global__ void __launch_bounds__(GENERIC_THREADS)
 k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
           const int32_t *__restrict__ channels, int n_channels, int remove_white) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int ch[32];
-    uint32_t *view = (uint32_t *)smem_raw;
+    __shared__ int run_src[32], run_dst[32], n_runs;
+    __shared__ uint32_t run_mask[32];
     const int H = B.H, W = B.W, cells = H * W, vcells = vh * vw;
-    if (threadIdx.x < n_channels) ch[threadIdx.x] = channels[threadIdx.x] & 31;
+    uint32_t *view = (uint32_t *)smem_raw;                  // [vcells]
+    int *ymap = (int *)(view + vcells), *xmap = ymap + vh;   // [vh] source row * W, [vw] source column
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (threadIdx.x == 0) {
+        int nr = 0;
+        for (int k = 0; k < n_channels;) {
+            int len = 1;
+            const int c0 = channels[k];
+            while (k + len < n_channels && channels[k + len] == c0 + len) len++;
+            run_src[nr] = c0;
+            run_dst[nr] = k;
+            run_mask[nr] = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+            nr++;
+            k += len;
+        }
+        n_runs = nr;
+    }
     __syncthreads();
     for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
         const uint16_t *board = B.board + (size_t)e * cells;
@@ -544,11 +565,14 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
             if (remove_white && g == COLORS) g = 0;
             return (uint32_t)board[idx] | (g << 16);
         };
-        for (int i = threadIdx.x; i < vcells; i += blockDim.x) {
-            int r = i / vw, c = i - r * vw;
-            int y = ((y0 - vh / 2 + r) % H + H) % H;
-            int x = ((x0 - vw / 2 + c) % W + W) % W;
-            view[i] = packed(y * W + x);
+        for (int i = threadIdx.x; i < vh + vw; i += blockDim.x) {
+            if (i < vh) ymap[i] = (((y0 - vh / 2 + i) % H + H) % H) * W;
+            else xmap[i - vh] = ((x0 - vw / 2 + (i - vh)) % W + W) % W;
+        }
+        __syncthreads();
+        for (int r = warp; r < vh; r += nwarps) {
+            const int src_row = ymap[r];
+            for (int c = lane; c < vw; c += 32) view[r * vw + c] = packed(src_row + xmap[c]);
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -570,14 +594,14 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
             for (int i = threadIdx.x; i < vcells; i += blockDim.x) o[i] = view[i];
         } else {
             // Each view word becomes its channel mask (bit k = channel k of the cell), so
-            // the output is the bit stream of those masks, one byte per bit.  It is
-            // written 16 bytes at a time: 16 stream bits gathered from the (at most a
-            // few) cells they straddle, four bits -> four 0/1 bytes by one multiply.
-            const int C = n_channels;
+            // the output is the bit stream of those masks, one byte per bit: 16 stream
+            // bits gathered from the cells they straddle, four bits -> four 0/1 bytes by
+            // one multiply, one 16-byte store.
+            const int C = n_channels, nr = n_runs;
             for (int i = threadIdx.x; i < vcells; i += blockDim.x) {
                 const uint32_t v = view[i];
                 uint32_t m = 0;
-                for (int k = 0; k < C; k++) m |= ((v >> ch[k]) & 1u) << k;
+                for (int r = 0; r < nr; r++) m |= ((v >> run_src[r]) & run_mask[r]) << run_dst[r];
                 view[i] = m;
             }
             __syncthreads();
@@ -592,14 +616,17 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
             for (int i = threadIdx.x; i < head; i += blockDim.x) o[i] = bit_at(i);
             for (int i = head + (nchunks << 4) + threadIdx.x; i < total; i += blockDim.x) o[i] = bit_at(i);
             uint4 *o16 = (uint4 *)(o + head);
+            // chunk c starts at stream bit head + 16 c = cell * C + k; stepping by blockDim
+            // chunks advances (cell, k) by a fixed (dq, dk)
+            const int step_bits = (int)blockDim.x << 4, dq = step_bits / C, dk = step_bits - dq * C;
+            int i0 = head + ((int)threadIdx.x << 4);
+            int cell = i0 / C, k = i0 - cell * C;
             for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
-                const int i0 = head + (c << 4);
-                int cell = i0 / C;
-                const int k = i0 - cell * C;
                 uint32_t bits = view[cell] >> k;
+                int cc = cell;
                 for (int have = C - k; have < 16; have += C) {
-                    cell++;
-                    bits |= (cell < vcells ? view[cell] : 0u) << have;
+                    cc++;
+                    bits |= (cc < vcells ? view[cc] : 0u) << have;
                 }
                 uint4 w;
                 w.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
@@ -607,6 +634,12 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
                 w.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
                 w.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
                 o16[c] = w;
+                cell += dq;
+                k += dk;
+                if (k >= C) {
+                    k -= C;
+                    cell++;
+                }
             }
         }
         __syncthreads();

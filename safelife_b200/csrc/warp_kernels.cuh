@@ -1046,7 +1046,8 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_p
 #undef SL_KNOWN_SHAPE
     if (!known) want = p.goals_resident ? 24 : 34;    // a large board: the smallest shape
     const int stages = want / 10, ctas = want % 10;
-    if (p.bulk_ok && full_groups > sm_count * ctas) {
+    // (a batch that fits the single-pass kernel's one wave of 4 CTAs per SM stays there)
+    if (p.bulk_ok && full_groups > sm_count * 4) {
         const int slots = sm_count * ctas;
         const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
         p.pipe_stages = stages;
