@@ -414,6 +414,19 @@ def run_ours(args, levels):
     barrier()
     l2_ms = l2_ev[0].elapsed_time(l2_ev[1])
 
+    # ---- supplementary: the same event pair around an EMPTY kernel of the step's
+    # launch shape, after the same flush: the part of ms_per_step that is not kernel ----
+    fl_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(min(K, 200))]
+    barrier()
+    for ev_pair in fl_ev:
+        if flush is not None:
+            flush.fill_(1)
+        ev_pair[0].record()
+        _lib.check(lib.sl_launch_floor(bref, stream))
+        ev_pair[1].record()
+    barrier()
+    floor_ms = sum(e[0].elapsed_time(e[1]) for e in fl_ev) / len(fl_ev)
+
     # ---- supplementary: SafeLifeEnv.get_obs for the whole batch (next row 8f-1) ----
     Ko = min(K, 100)
     obs_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(Ko)]
@@ -474,6 +487,7 @@ def run_ours(args, levels):
                 "kernel_ms": step_ms / K, "dynamic_goal_envs": dyn,
             },
             "wall_s_timed_region": wall,
+            "launch_floor_ms": floor_ms,
             "obs": {
                 "ms": obs_ms, "bytes_per_launch": obs_bytes,
                 "achieved_gbs": obs_bytes / (obs_ms * 1e-3) / 1e9,

@@ -234,6 +234,11 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
 int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_len,
                      int *n_launches);
 
+/* An empty kernel with the step kernel's launch shape (one 256-thread CTA per 8
+ * envs, the same parameter block): what a benchmark's event pair measures
+ * around a step that does no work. */
+int sl_launch_floor(const SlEnvBatch *batch, void *stream);
+
 /* sl_env_step followed by a wait for the stream: for host-driven loops.  The
  * batch's actions / reward / done / success / times_up pointers may be pinned
  * host memory (device-addressable under UVA); the kernel then reads and writes

@@ -102,6 +102,7 @@ PROTOTYPES = {
     "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_sync": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_plan": [ctypes.POINTER(SlEnvBatch), _i, _vp, _i, _vp],
+    "sl_launch_floor": [ctypes.POINTER(SlEnvBatch), _vp],
     "sl_env_reset": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _i, _vp],
     "sl_get_obs": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _i, _i, _vp],
     "sl_side_effect_cells": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _vp],

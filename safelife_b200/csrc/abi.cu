@@ -117,6 +117,19 @@ int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int 
                                 rng, props.sm_count, st);
         return launch_status("k_advance_warp");
     }
+    if (sl::warp_kernel_supports(H, W)) {      // up to 64x64: planes in registers, two rows per lane
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        const bool counting = counts != nullptr;
+        size_t smem = sl::multistep_wide_smem(H, W, counting);
+        rc = prepare_smem(sl::k_multistep_wide, smem);
+        if (rc) return rc;
+        sl::k_multistep_wide<<<sl::multistep_wide_grid(n, props.sm_count), sl::WIDE_ADV_WARPS * 32, smem, st>>>(
+            counting ? 1 : 0, in, nullptr, out, counts, n, H, W, spawn_threshold(spawn_prob), nullptr,
+            n_steps, nullptr, rng);
+        return launch_status("k_multistep_wide");
+    }
     size_t smem = sl::generic_smem_bytes(H * W);
     rc = prepare_smem(sl::k_advance_generic, smem);
     if (rc) return rc;
@@ -205,6 +218,17 @@ int sl_side_effect_occupancy(const uint16_t *init_board, const uint16_t *final_b
         sl::launch_side_effect_warp(init_board, final_board, counts, n, H, W, spawn_thr, num_steps,
                                     num_samples, rng, props.sm_count, st);
         return launch_status("k_side_effect_warp");
+    }
+    if (sl::warp_kernel_supports(H, W)) {
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        size_t wsmem = sl::multistep_wide_smem(H, W, true);
+        rc = prepare_smem(sl::k_multistep_wide, wsmem);
+        if (rc) return rc;
+        sl::k_multistep_wide<<<sl::multistep_wide_grid(n, props.sm_count), sl::WIDE_ADV_WARPS * 32, wsmem, st>>>(
+            2, init_board, final_board, nullptr, counts, n, H, W, 0, spawn_thr, num_samples, num_steps, rng);
+        return launch_status("k_multistep_wide");
     }
     size_t smem = sl::generic_smem_bytes(H * W);
     rc = prepare_smem(sl::k_side_effect_generic, smem);
@@ -483,6 +507,20 @@ int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_l
     if (text && text_len > 0) snprintf(text, (size_t)text_len, "%s", buf);
     if (n_launches) *n_launches = launches;
     return SL_OK;
+}
+
+namespace {
+__global__ void k_launch_floor(const __grid_constant__ SlEnvBatch B, int *sink) {
+    if (sink != nullptr && B.n_envs < 0) *sink = B.H;     // never true: keeps the parameter alive
+}
+}  // namespace
+
+int sl_launch_floor(const SlEnvBatch *batch, void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    const int groups = batch->n_envs > 0 ? (batch->n_envs + 7) / 8 : 1;
+    k_launch_floor<<<groups, 256, 0, (cudaStream_t)stream>>>(*batch, nullptr);
+    return launch_status("k_launch_floor");
 }
 
 int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,

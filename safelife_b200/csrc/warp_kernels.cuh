@@ -334,13 +334,23 @@ __device__ __forceinline__ RowDeltaT<typename G::P> stencil_planes(
 // its rows; returns the subset whose draw was below thr; the (uniform) state
 // advances by the total number of candidates.  Raster order = row order (all
 // rows of slot 0 come before those of slot 1), then bit order within the row.
+// Per-lane leapfrog constants of one stream: lane l jumps l + 1 steps at once,
+// state' = la * state + ginc with la = A^(l+1), ginc = G_(l+1) * inc.
+struct SpawnCtx {
+    u128 la, ginc;
+};
+__device__ __forceinline__ SpawnCtx make_spawn_ctx(int lane, const u128 &inc) {
+    const u128 la = {__ldg(&d_lane_a[lane][0]), __ldg(&d_lane_a[lane][1])};
+    const u128 lg = {__ldg(&d_lane_g[lane][0]), __ldg(&d_lane_g[lane][1])};
+    return {la, mul128(lg, inc)};
+}
+
 template <class G>
-__device__ __forceinline__ typename G::P warp_spawn_draws(const G &t, u128 &state, const u128 &inc,
-                                                          uint64_t thr, typename G::P cand) {
+__device__ __forceinline__ typename G::P warp_spawn_draws_ctx(const G &t, u128 &state,
+                                                              const SpawnCtx &ctx, uint64_t thr,
+                                                              typename G::P cand) {
     typedef typename G::P P;
     typedef typename G::RowMask M;
-    P spawned = cand & ~cand;
-    if (!__any_sync(FULL, nonzero(cand))) return spawned;
     const int lane = t.lane;
     M todo[G::ROWS];
     int next[G::ROWS];      // index of the next draw of each row
@@ -357,14 +367,11 @@ __device__ __forceinline__ typename G::P warp_spawn_draws(const G &t, u128 &stat
         next[s] = total + incl - cnt;
         total += __shfl_sync(FULL, incl, 31);
     }
-    const u128 la = {__ldg(&d_lane_a[lane][0]), __ldg(&d_lane_a[lane][1])};
-    const u128 lg = {__ldg(&d_lane_g[lane][0]), __ldg(&d_lane_g[lane][1])};
-    const u128 ginc = mul128(lg, inc);
     M got[G::ROWS];
 #pragma unroll
     for (int s = 0; s < G::ROWS; s++) got[s] = 0;
     for (int base = 0; base < total; base += 32) {
-        u128 sn = add128(mul128(la, state), ginc);          // state after lane+1 more steps
+        u128 sn = add128(mul128(ctx.la, state), ctx.ginc);  // state after lane+1 more steps
         uint32_t ok = __ballot_sync(FULL, (pcg_output(sn) >> 11) < thr);
 #pragma unroll
         for (int s = 0; s < G::ROWS; s++) {
@@ -379,9 +386,21 @@ __device__ __forceinline__ typename G::P warp_spawn_draws(const G &t, u128 &stat
         state.hi = __shfl_sync(FULL, sn.hi, last);
         state.lo = __shfl_sync(FULL, sn.lo, last);
     }
+    P spawned = cand & ~cand;
 #pragma unroll
     for (int s = 0; s < G::ROWS; s++) t.set_row(spawned, s, got[s]);
     return spawned;
+}
+
+// Resolve the spawn draws of one board: each lane holds the candidate masks of
+// its rows; returns the subset whose draw was below thr; the (uniform) state
+// advances by the total number of candidates.  Raster order = row order (all
+// rows of slot 0 come before those of slot 1), then bit order within the row.
+template <class G>
+__device__ __forceinline__ typename G::P warp_spawn_draws(const G &t, u128 &state, const u128 &inc,
+                                                          uint64_t thr, typename G::P cand) {
+    if (!__any_sync(FULL, nonzero(cand))) return cand & ~cand;
+    return warp_spawn_draws_ctx(t, state, make_spawn_ctx(t.lane, inc), thr, cand);
 }
 
 // New value of a changed cell: 0 if it died, else ALIVE | inherited colours |
@@ -1138,12 +1157,13 @@ __device__ __forceinline__ AdvBoard adv_load(const Narrow &t, const uint16_t *sl
 }
 
 // One advance_board step (advance_board.c:34-125) on the register image.
-__device__ __forceinline__ void adv_step(const Narrow &t, AdvBoard &b, u128 &state, const u128 &inc,
-                                         uint64_t thr, bool draws) {
+__device__ __forceinline__ void adv_step(const Narrow &t, AdvBoard &b, u128 &state,
+                                         const SpawnCtx &ctx, uint64_t thr, bool draws) {
     LowPlanesT<uint32_t> &lp = b.lp;
     HighPlanesT<uint32_t> &hp = b.hp;
     const RowDeltaT<uint32_t> d = stencil_planes(t, lp, [&] { return hp; });
-    const uint32_t spawned = draws ? warp_spawn_draws(t, state, inc, thr, d.cand) : 0u;
+    uint32_t spawned = 0u;
+    if (draws && __any_sync(FULL, d.cand != 0)) spawned = warp_spawn_draws_ctx(t, state, ctx, thr, d.cand);
     const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
     lp.A = (lp.A & keep) | fresh;
     lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
@@ -1244,17 +1264,18 @@ k_advance_warp(const uint16_t *in, uint16_t *out, int32_t *__restrict__ counts, 
             state = {rng[4 * (size_t)b], rng[4 * (size_t)b + 1]};
             inc = {rng[4 * (size_t)b + 2], rng[4 * (size_t)b + 3]};
         }
+        const SpawnCtx ctx = make_spawn_ctx(lane, inc);
         if (counts != nullptr) {
             int32_t *dst = counts + (size_t)b * cells * 8;
             OccCounters occ;
             occ.clear();
             for (int s = 0; s < n_steps; s++) {
-                adv_step(t, bd, state, inc, thr, rng != nullptr);
+                adv_step(t, bd, state, ctx, thr, rng != nullptr);
                 occ.add(t, bd, dst);
             }
             if (occ.pending) occ.flush(t, dst);
         } else {
-            for (int s = 0; s < n_steps; s++) adv_step(t, bd, state, inc, thr, rng != nullptr);
+            for (int s = 0; s < n_steps; s++) adv_step(t, bd, state, ctx, thr, rng != nullptr);
             adv_store(t, bd, slab);
             __syncwarp();
             uint16_t *dst = out + (size_t)b * cells;
@@ -1291,6 +1312,7 @@ k_side_effect_warp(const uint16_t *__restrict__ init_board, const uint16_t *__re
         }
         const uint64_t th = thr[b];
         const bool draws = rng != nullptr;
+        const SpawnCtx ctx = make_spawn_ctx(lane, inc);
         OccCounters occ;
         for (int run = 0; run < 2; run++) {
             const uint16_t *src = (run == 0 ? init_board : final_board) + (size_t)b * cells;
@@ -1300,12 +1322,12 @@ k_side_effect_warp(const uint16_t *__restrict__ init_board, const uint16_t *__re
             AdvBoard bd = adv_load(t, slab);
             if (run == 0) {
                 const int ns = num_steps[b];
-                for (int s = 0; s < ns; s++) adv_step(t, bd, state, inc, th, draws);
+                for (int s = 0; s < ns; s++) adv_step(t, bd, state, ctx, th, draws);
             }
             int32_t *dst = counts + ((size_t)b * 2 + run) * cells * 8;
             occ.clear();
             for (int s = 0; s < num_samples; s++) {
-                adv_step(t, bd, state, inc, th, draws);
+                adv_step(t, bd, state, ctx, th, draws);
                 occ.add(t, bd, dst);
             }
             if (occ.pending) occ.flush(t, dst);
@@ -1315,6 +1337,182 @@ k_side_effect_warp(const uint16_t *__restrict__ init_board, const uint16_t *__re
             rng[4 * (size_t)b + 1] = state.lo;
         }
     }
+}
+
+// ---- the same for boards up to 64x64 (Wide: two 64-bit rows per lane) ----------
+// The planes stay in registers; the occupancy counts of a board are byte
+// counters in shared memory (one per cell and colour, bumped for every live cell
+// of a step and flushed into the int32 output every 255 steps).
+struct WideBoard {
+    LowPlanesT<P2> lp;
+    HighPlanesT<P2> hp;
+    P2 agent, kept;
+};
+
+__device__ __forceinline__ WideBoard wide_load(const Wide &t, const uint16_t *slab) {
+    uint64_t a[8], b[8];
+    WideBoard w;
+    t.load_bytes<0x6240>(slab, a, b);
+    w.lp = {{a[0], b[0]}, {a[3], b[3]}, {a[4], b[4]}, {a[5], b[5]}, {a[6], b[6]}, {a[7], b[7]}};
+    w.agent = {a[1], b[1]};
+    t.load_bytes<0x7351>(slab, a, b);
+    w.hp = {{a[0], b[0]}, {a[1], b[1]}, {a[2], b[2]}, {a[3], b[3]}};
+    w.kept = t.mask();
+    return w;
+}
+
+__device__ __forceinline__ void wide_step(const Wide &t, WideBoard &b, u128 &state,
+                                          const SpawnCtx &ctx, uint64_t thr, bool draws) {
+    LowPlanesT<P2> &lp = b.lp;
+    HighPlanesT<P2> &hp = b.hp;
+    const RowDeltaT<P2> d = stencil_planes(t, lp, [&] { return hp; });
+    P2 spawned = {0ull, 0ull};
+    if (draws && __any_sync(FULL, nonzero(d.cand))) spawned = warp_spawn_draws_ctx(t, state, ctx, thr, d.cand);
+    const P2 fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
+    lp.A = (lp.A & keep) | fresh;
+    lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
+    hp.R = (hp.R & keep) | (d.tR & fresh);
+    hp.G = (hp.G & keep) | (d.tG & fresh);
+    hp.B = (hp.B & keep) | (d.tB & fresh);
+    lp.P_ = lp.P_ & keep; lp.I = lp.I & keep; lp.S = lp.S & keep;
+    hp.E = hp.E & keep; b.agent = b.agent & keep;
+    b.kept = b.kept & keep;
+}
+
+__device__ __forceinline__ void wide_store(const Wide &t, const WideBoard &b, uint16_t *slab) {
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        uint16_t *row = slab + t.row_of(s) * t.W;
+        uint64_t m = t.row(t.mask(), s) & ~t.row(b.kept, s);
+        const uint64_t A = t.row(b.lp.A, s), D = t.row(b.lp.D, s), R = t.row(b.hp.R, s),
+                       G = t.row(b.hp.G, s), B = t.row(b.hp.B, s);
+        while (m != 0) {
+            const int j = lowest(m);
+            m &= m - 1;
+            row[j] = (uint16_t)(((A >> j) & 1u) | (((D >> j) & 1u) << 3) | (((R >> j) & 1u) << 9) |
+                                (((G >> j) & 1u) << 10) | (((B >> j) & 1u) << 11));
+        }
+    }
+}
+
+// +1 for cells ALIVE and none of AGENT | EXIT | FROZEN, by colour (advance_board.c:153-162)
+__device__ __forceinline__ void wide_count(const Wide &t, const WideBoard &b, uint8_t *cnt8) {
+    const P2 occ = b.lp.A & ~(b.agent | b.hp.E | b.lp.F);
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        uint64_t m = t.row(occ, s);
+        const uint64_t R = t.row(b.hp.R, s), G = t.row(b.hp.G, s), B = t.row(b.hp.B, s);
+        uint8_t *row = cnt8 + (size_t)t.row_of(s) * t.W * 8;
+        while (m != 0) {
+            const int j = lowest(m);
+            m &= m - 1;
+            const int c = (int)((R >> j) & 1u) | ((int)((G >> j) & 1u) << 1) | ((int)((B >> j) & 1u) << 2);
+            row[j * 8 + c]++;
+        }
+    }
+}
+
+__device__ __forceinline__ void wide_flush(uint8_t *cnt8, int32_t *dst, int cells, int lane) {
+    __syncwarp();
+    uint32_t *w = (uint32_t *)cnt8;
+    for (int i = lane; i < cells * 2; i += 32) {        // 4 counters per word
+        const uint32_t v = w[i];
+        if (v != 0) {
+            int32_t *d = dst + 4 * i;
+            if (v & 0xffu) d[0] += v & 0xffu;
+            if (v & 0xff00u) d[1] += (v >> 8) & 0xffu;
+            if (v & 0xff0000u) d[2] += (v >> 16) & 0xffu;
+            if (v >> 24) d[3] += v >> 24;
+            w[i] = 0;
+        }
+    }
+    __syncwarp();
+}
+
+constexpr int WIDE_ADV_WARPS = 4;
+// the plane loads of lanes past the last row read up to cell 63 * W + 32 + 56 of the slab
+__host__ __device__ inline int wide_slab_cells(int H, int W) {
+    return H * W > 64 * W + 96 ? H * W : 64 * W + 96;
+}
+__host__ __device__ inline size_t wide_slab_bytes(int H, int W) {
+    return ((size_t)wide_slab_cells(H, W) * 2 + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t wide_warp_bytes(int H, int W, bool counting) {
+    return wide_slab_bytes(H, W) + (counting ? (size_t)H * W * 8 : 0);
+}
+
+// mode 0: out[b] = board after n_steps (advance_board_nstep); mode 1: counts[b] +=
+// life_occupancy over n_steps; mode 2: the three runs of side_effect_score
+// (counts[b][0..1], first run preceded by num_steps[b] uncounted steps).
+__global__ void __launch_bounds__(WIDE_ADV_WARPS * 32)
+k_multistep_wide(int mode, const uint16_t *in, const uint16_t *in2, uint16_t *out,
+                 int32_t *__restrict__ counts, int n, int H, int W, uint64_t thr_all,
+                 const uint64_t *__restrict__ thr_each, int n_steps,
+                 const int32_t *__restrict__ lead_steps, uint64_t *__restrict__ rng) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = H * W;
+    const bool counting = mode != 0;
+    unsigned char *mine = smem_raw + warp * wide_warp_bytes(H, W, counting);
+    uint16_t *slab = (uint16_t *)mine;
+    uint8_t *cnt8 = mine + wide_slab_bytes(H, W);
+    const Wide t(H, W, lane);
+    if (counting)
+        for (int i = lane; i < cells * 2; i += 32) ((uint32_t *)cnt8)[i] = 0;
+    for (int b = blockIdx.x * WIDE_ADV_WARPS + warp; b < n; b += gridDim.x * WIDE_ADV_WARPS) {
+        u128 state = {0, 0}, inc = {0, 0};
+        if (rng != nullptr) {
+            state = {rng[4 * (size_t)b], rng[4 * (size_t)b + 1]};
+            inc = {rng[4 * (size_t)b + 2], rng[4 * (size_t)b + 3]};
+        }
+        const uint64_t th = thr_each != nullptr ? thr_each[b] : thr_all;
+        const bool draws = rng != nullptr;
+        const SpawnCtx ctx = make_spawn_ctx(lane, inc);
+        const int runs = mode == 2 ? 2 : 1;
+        for (int run = 0; run < runs; run++) {
+            const uint16_t *src = (run == 0 ? in : in2) + (size_t)b * cells;
+            __syncwarp();
+            for (int i = lane; i < cells; i += 32) slab[i] = src[i];
+            __syncwarp();
+            WideBoard bd = wide_load(t, slab);
+            if (mode == 2 && run == 0) {
+                const int lead = lead_steps[b];
+                for (int s = 0; s < lead; s++) wide_step(t, bd, state, ctx, th, draws);
+            }
+            if (!counting) {
+                for (int s = 0; s < n_steps; s++) wide_step(t, bd, state, ctx, th, draws);
+                wide_store(t, bd, slab);
+                __syncwarp();
+                uint16_t *dst = out + (size_t)b * cells;
+                for (int i = lane; i < cells; i += 32) dst[i] = slab[i];
+            } else {
+                int32_t *dst = counts + ((size_t)b * runs + run) * cells * 8;
+                int pending = 0;
+                for (int s = 0; s < n_steps; s++) {
+                    wide_step(t, bd, state, ctx, th, draws);
+                    wide_count(t, bd, cnt8);
+                    if (++pending == 255) {
+                        wide_flush(cnt8, dst, cells, lane);
+                        pending = 0;
+                    }
+                }
+                if (pending) wide_flush(cnt8, dst, cells, lane);
+            }
+        }
+        if (rng != nullptr && lane == 0) {
+            rng[4 * (size_t)b] = state.hi;
+            rng[4 * (size_t)b + 1] = state.lo;
+        }
+        __syncwarp();
+    }
+}
+
+inline size_t multistep_wide_smem(int H, int W, bool counting) {
+    return WIDE_ADV_WARPS * wide_warp_bytes(H, W, counting);
+}
+inline int multistep_wide_grid(int n, int sm_count) {
+    const int grid = (n + WIDE_ADV_WARPS - 1) / WIDE_ADV_WARPS, cap = sm_count * 2;
+    return grid > cap ? cap : grid;
 }
 
 inline int advance_warp_grid(int n, int sm_count) {

@@ -197,9 +197,13 @@ def test_error_conventions(sp):
 
 
 @pytest.mark.parametrize("shape,steps", [((25, 25), 1100), ((7, 9), 2050), ((32, 32), 300),
-                                         ((40, 33), 60)])
+                                         ((40, 33), 60), ((50, 50), 300), ((64, 64), 270),
+                                         ((20, 50), 40), ((70, 41), 30)])
 def test_life_occupancy_long_runs_vs_oracle(sp, shape, steps):
-    """More steps than a 10-bit occupancy counter holds (flush path) and a generic-size board."""
+    """
+    More steps than an occupancy counter holds (10-bit sliced counters of the narrow
+    kernel, byte counters of the wide one: flush paths) and a generic-size board.
+    """
     H, W = shape
     rs = np.random.default_rng(steps)
     n = 6

@@ -117,7 +117,7 @@ def test_side_effect_occupancy_golden_fused():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("shape", [(25, 25), (32, 32), (9, 14), (40, 35), (50, 50)])
+@pytest.mark.parametrize("shape", [(25, 25), (32, 32), (9, 14), (40, 35), (50, 50), (64, 64), (66, 30)])
 def test_side_effect_occupancy_random_vs_oracle(shape):
     """Warp (H, W <= 32) and generic kernels against the oracle's three separate calls."""
     from safelife_b200 import side_effects as se
