@@ -9,6 +9,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+#include <vector>
+
 #include "../../include/safelife_b200.h"
 #include "cells.cuh"
 #include "emd_host.h"
@@ -79,6 +82,18 @@ int device_props(DeviceProps *out) {
     return SL_OK;
 }
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute is sticky
+// per device, so it is set once per (kernel, device) and raised only when a
+// later call needs more: a step in a host-driven loop must not pay a dozen
+// driver calls.  (The only process-global state of the library; no simulation
+// state.)
+struct SmemGrant {
+    const void *kernel;
+    int dev, bytes;
+};
+std::mutex g_grant_mutex;
+std::vector<SmemGrant> g_grants;
+
 template <typename K>
 int prepare_smem(K kernel, size_t bytes) {
     DeviceProps p;
@@ -87,8 +102,21 @@ int prepare_smem(K kernel, size_t bytes) {
     if (bytes > (size_t)p.max_smem_optin)
         return fail(SL_ERR_ARG, "board too large: needs %zu bytes of shared memory (max %d)",
                     bytes, p.max_smem_optin);
-    if (bytes > 48 * 1024)
-        SL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (bytes <= 48 * 1024) return SL_OK;
+    int dev = 0;
+    SL_CUDA(cudaGetDevice(&dev));
+    const void *key = (const void *)kernel;
+    std::lock_guard<std::mutex> lock(g_grant_mutex);
+    for (SmemGrant &g : g_grants) {
+        if (g.kernel == key && g.dev == dev) {
+            if ((int)bytes <= g.bytes) return SL_OK;
+            SL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+            g.bytes = (int)bytes;
+            return SL_OK;
+        }
+    }
+    SL_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    g_grants.push_back({key, dev, (int)bytes});
     return SL_OK;
 }
 

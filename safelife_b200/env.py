@@ -318,10 +318,18 @@ class BatchedSafeLifeEnv(object):
         if actions is not h["actions"]:
             np.copyto(h["actions"], actions, casting="unsafe")
         auto = self.auto_reset if auto_reset is None else auto_reset
-        with torch.cuda.device(self.device):
-            _lib.check(self._lib.sl_env_step_sync(
-                self._batch_host_ref, self._host_actions_ptr, self.kernel,
-                _lib.SL_STEP_AUTO_RESET if auto else 0, self._stream()))
+        flags = _lib.SL_STEP_AUTO_RESET if auto else 0
+        # host-driven loop: keep the per-step Python overhead out of the way (the
+        # device context manager costs more than the kernel launch)
+        if torch.cuda.current_device() == self.device.index:
+            status = self._lib.sl_env_step_sync(self._batch_host_ref, self._host_actions_ptr,
+                                                self.kernel, flags, self._stream())
+        else:
+            with torch.cuda.device(self.device):
+                status = self._lib.sl_env_step_sync(self._batch_host_ref, self._host_actions_ptr,
+                                                    self.kernel, flags, self._stream())
+        if status:
+            _lib.check(status)
         return h["reward"], h["done"]
 
     def step(self, actions):
