@@ -582,7 +582,8 @@ int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw, const int32_t
     if (n_channels > 32) return fail(SL_ERR_ARG, "at most 32 output channels (bits of the uint32 view)");
     if (batch->n_envs == 0) return SL_OK;
     if (!obs || (n_channels > 0 && !channels)) return fail(SL_ERR_ARG, "null pointer");
-    size_t smem = ((size_t)vh * vw + vh + vw) * 4;     // view, source-row and -column tables
+    // view, source-row and -column tables, packed channel bit stream
+    size_t smem = ((size_t)vh * vw + vh + vw + ((size_t)vh * vw * n_channels + 31) / 32 + 2) * 4;
     rc = prepare_smem(sl::k_get_obs, smem);
     if (rc) return rc;
     sl::k_get_obs<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, (cudaStream_t)stream>>>(

@@ -539,6 +539,7 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
     const int H = B.H, W = B.W, cells = H * W, vcells = vh * vw;
     uint32_t *view = (uint32_t *)smem_raw;                  // [vcells]
     int *ymap = (int *)(view + vcells), *xmap = ymap + vh;   // [vh] source row * W, [vw] source column
+    uint32_t *stream = (uint32_t *)(xmap + vw);              // [vcells * C / 32 + 2] packed channel bits
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     if (threadIdx.x == 0) {
         int nr = 0;
@@ -593,53 +594,42 @@ k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
             uint32_t *o = (uint32_t *)obs + (size_t)e * vcells;
             for (int i = threadIdx.x; i < vcells; i += blockDim.x) o[i] = view[i];
         } else {
-            // Each view word becomes its channel mask (bit k = channel k of the cell), so
-            // the output is the bit stream of those masks, one byte per bit: 16 stream
-            // bits gathered from the cells they straddle, four bits -> four 0/1 bytes by
-            // one multiply, one 16-byte store.
+            // The output is a stream of bits, C per cell (bit k = channel k of the cell),
+            // one byte per bit.  The cells' channel masks are first packed into that bit
+            // stream in shared memory; then every thread expands 16 consecutive stream
+            // bits into one 16-byte store: a funnel shift fetches them, one multiply per
+            // four bits spreads them into 0/1 bytes.
             const int C = n_channels, nr = n_runs;
+            const int total = vcells * C, nwords = (total + 31) / 32 + 1;
+            for (int i = threadIdx.x; i < nwords; i += blockDim.x) stream[i] = 0;
+            __syncthreads();
             for (int i = threadIdx.x; i < vcells; i += blockDim.x) {
                 const uint32_t v = view[i];
                 uint32_t m = 0;
                 for (int r = 0; r < nr; r++) m |= ((v >> run_src[r]) & run_mask[r]) << run_dst[r];
-                view[i] = m;
+                if (m != 0) {
+                    const int bit = i * C, w = bit >> 5, sh = bit & 31;
+                    atomicOr(stream + w, m << sh);
+                    if (sh + C > 32) atomicOr(stream + w + 1, m >> (32 - sh));
+                }
             }
             __syncthreads();
-            uint8_t *o = (uint8_t *)obs + (size_t)e * vcells * C;
-            const int total = vcells * C;
+            uint8_t *o = (uint8_t *)obs + (size_t)e * total;
             const int head = min(total, (int)((16u - (unsigned)((uintptr_t)o & 15u)) & 15u));
             const int nchunks = (total - head) >> 4;
-            auto bit_at = [&](int i) -> uint8_t {
-                const int cell = i / C;
-                return (uint8_t)((view[cell] >> (i - cell * C)) & 1u);
-            };
+            auto bit_at = [&](int i) -> uint8_t { return (uint8_t)((stream[i >> 5] >> (i & 31)) & 1u); };
             for (int i = threadIdx.x; i < head; i += blockDim.x) o[i] = bit_at(i);
             for (int i = head + (nchunks << 4) + threadIdx.x; i < total; i += blockDim.x) o[i] = bit_at(i);
             uint4 *o16 = (uint4 *)(o + head);
-            // chunk c starts at stream bit head + 16 c = cell * C + k; stepping by blockDim
-            // chunks advances (cell, k) by a fixed (dq, dk)
-            const int step_bits = (int)blockDim.x << 4, dq = step_bits / C, dk = step_bits - dq * C;
-            int i0 = head + ((int)threadIdx.x << 4);
-            int cell = i0 / C, k = i0 - cell * C;
             for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
-                uint32_t bits = view[cell] >> k;
-                int cc = cell;
-                for (int have = C - k; have < 16; have += C) {
-                    cc++;
-                    bits |= (cc < vcells ? view[cc] : 0u) << have;
-                }
+                const int i0 = head + (c << 4);
+                const uint32_t bits = __funnelshift_r(stream[i0 >> 5], stream[(i0 >> 5) + 1], i0 & 31);
                 uint4 w;
                 w.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
                 w.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
                 w.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
                 w.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
                 o16[c] = w;
-                cell += dq;
-                k += dk;
-                if (k >= C) {
-                    k -= C;
-                    cell++;
-                }
             }
         }
         __syncthreads();
