@@ -1065,8 +1065,10 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_p
 #undef SL_KNOWN_SHAPE
     if (!known) want = p.goals_resident ? 24 : 34;    // a large board: the smallest shape
     const int stages = want / 10, ctas = want % 10;
-    // (a batch that fits the single-pass kernel's one wave of 4 CTAs per SM stays there)
-    if (p.bulk_ok && full_groups > sm_count * 4) {
+    // (measured crossover: the single-pass kernel wins up to about two waves of its 4 CTAs
+    // per SM -- 8192 envs: 18.4 vs 19.2 us, 16384 envs: 27.2 vs 25.6 us)
+    static const int min_waves = env_knob("SAFELIFE_B200_PIPE_MIN_WAVES", 2);   // tuning knob
+    if (p.bulk_ok && full_groups > sm_count * 4 * min_waves) {
         const int slots = sm_count * ctas;
         const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
         p.pipe_stages = stages;
