@@ -330,3 +330,23 @@ def test_baseline_configs_vs_oracle(pool, n, steps):
         assert draws > 0                      # the stochastic path was exercised
     if "navigation" in pool:
         assert (sg == 2).any()                # dynamic goals: two stencils per step
+
+
+def test_step_plan_and_launch_floor():
+    """sl_env_step_plan names what sl_env_step launches; sl_launch_floor launches an empty kernel."""
+    import torch
+    from safelife_b200 import _lib
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(3)
+    base = _random_levels(rs, 16, 25, 25)
+    small = BatchedSafeLifeEnv(base, 64, kernel=2, goals_in_place=False)
+    text, launches = small.step_plan()
+    assert "k_env_step_warp<Narrow, goals resident>" in text and launches == 1
+    big = BatchedSafeLifeEnv(base, 592 * 8 * 2 + 8 * 40 + 3, kernel=2, goals_in_place=True)
+    text, launches = big.step_plan()
+    assert "k_env_step_pipe<" in text and "goals in place" in text and "k_env_step_warp" in text
+    assert launches == 2                      # pipelined kernel + the ragged tail group
+    generic = BatchedSafeLifeEnv(_random_levels(rs, 4, 70, 41), 8)
+    assert "k_env_step_generic" in generic.step_plan()[0]
+    assert _lib.lib().sl_launch_floor(small._batch_ref, small._stream()) == _lib.SL_OK
+    torch.cuda.synchronize()
