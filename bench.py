@@ -35,6 +35,30 @@ POOL_DIR = os.path.join(ROOT, "tests", "golden", "pools")
 METRIC = "env-steps/sec (batched boards) at 1/2/4/8 B200 vs C-ext on host cores"
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """
+    Everything but the JSON line goes to stderr: libraries (NCCL prints its version
+    banner on stdout) must not add lines to the one-line contract.
+    """
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,7 +212,7 @@ def run_reference(args, levels):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------
@@ -503,7 +527,7 @@ def run_ours(args, levels):
             line["sweep"] = sweep(args, levels, dev, peak)
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"], _ = cpu_arm(levels, n, min(K, 100), 2, args.cpu_seconds)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -517,6 +541,7 @@ def main():
                "--nproc-per-node", str(args.gpus), "--master-addr", "127.0.0.1",
                "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
         raise SystemExit(subprocess.call(cmd))
+    quiet_stdout()
     from safelife_b200.levels import load_levels
     levels = load_levels(os.path.join(POOL_DIR, args.pool + ".npz"))
     if args.impl == "reference":
