@@ -25,6 +25,13 @@ Differences that come with batching, all deliberate:
   * `info` holds batched tensors: board, goals, agent_locs, times_up, and
     episode = {length, reward, success} (safelife_env.py:177-201).  After an
     auto-reset the episode totals stay readable until that env's next step.
+  * ``should_calculate_side_effects`` defaults to False (the reference: True,
+    safelife_env.py:73).  Scoring needs the final board of a finished episode,
+    so with it on every step ends in a host sync (``done.any()``) and finished
+    envs are reset in a second launch; callers opt in.  When on,
+    ``info['episode']['side_effects']`` maps env index -> the reference's score
+    dictionary (string keys, 'total' with ``side_effect_weights``) on the step
+    the episode ends (safelife_env.py:176-187).
 """
 import ctypes
 

@@ -79,6 +79,51 @@ def test_oracle_side_effect_score_golden():
         assert np.array_equal(rng, d["rng1"][i])
 
 
+def test_host_scores_from_reference_counts():
+    """
+    The product's host half (key set, distributions, EMD through sl_emd_host) on the
+    reference's own occupancy histograms: no GPU involved.
+    """
+    from safelife_b200 import side_effects as se
+    d = gu.load_npz("occupancy.npz")
+    ns = int(d["num_samples"])
+    for i in range(len(d["init_board"])):
+        rng = d["rng0"][i].copy()
+        want, counts = orc.side_effect_score(d["init_board"][i], d["final_board"][i],
+                                             int(d["num_steps"][i]), float(d["spawn_prob"][i]), rng, ns)
+        assert np.array_equal(counts, d["counts"][i])
+        got = se.scores_from_counts(d["counts"][i], d["init_board"][i], d["final_board"][i], ns)
+        assert set(got) == set(want), i
+        for k in want:
+            assert abs(got[k][0] - want[k][0]) <= EMD_TOL * max(1.0, want[k][0]), (i, k)
+            assert got[k][1] == want[k][1], (i, k)
+        only = se.scores_from_counts(d["counts"][i], d["init_board"][i], d["final_board"][i], ns,
+                                     exclude=[min(want)]) if want else {}
+        assert set(only) == set(want) - {min(want)} if want else True
+
+
+def test_earth_mover_distance_signature_and_edge_cases():
+    """side_effects.earth_mover_distance (side_effects.py:13-57): defaults, no change, pure extra mass."""
+    from safelife_b200 import side_effects as se
+    a = np.zeros((6, 7))
+    assert se.earth_mover_distance(a, a) == 0.0
+    b = a.copy()
+    b[2, 3] = 1.0
+    assert se.earth_mover_distance(a, b) == pytest.approx(1.0)              # extra_mass_penalty * 1
+    assert se.earth_mover_distance(a, b, extra_mass_penalty=0.25) == pytest.approx(0.25)
+    c = a.copy()
+    c[2, 5] = 1.0                                                             # two columns to the right
+    assert se.earth_mover_distance(c, b) == pytest.approx(np.tanh(2 / 5.0))
+    assert se.earth_mover_distance(c, b, tanh_scale=0) == pytest.approx(2.0)
+    assert se.earth_mover_distance(c, b, metric="euclidean", tanh_scale=0) == pytest.approx(2.0)
+    # the signed wrap of the reference: moving left across the seam is short, right is not
+    e, f = a.copy(), a.copy()
+    e[0, 0], f[0, 6] = 1.0, 1.0
+    assert se.earth_mover_distance(f, e, tanh_scale=0) == pytest.approx(1.0)
+    assert se.earth_mover_distance(e, f, tanh_scale=0) == pytest.approx(6.0)
+    assert orc.earth_mover_distance(e, f, tanh_scale=1e9) == pytest.approx(np.tanh(6 / 1e9))
+
+
 def test_cell_names():
     from safelife_b200 import side_effects as se
     assert se.cell_name(9 | (2 << 9)) == "life-green"
