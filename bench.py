@@ -185,12 +185,38 @@ def cpu_arm(levels, n_envs, steps, warmup, seconds_budget):
         res = pool.map(_cpu_worker, jobs)
     elapsed = max(r[0] for r in res)
     value = sample * steps / elapsed
+    extra = _cpu_pure_c(levels) if kind == "reference" else {}
     return {
         "value": value, "unit": "env-steps/s", "cores": cores, "kind": kind,
         "sample": "%d envs x %d steps (of %d envs/step), %s speedups execute_actions+advance_board"
                   "+alive_counts+dot from a Python loop, one process per core" % (
                       sample, steps, n_envs, "reference C" if kind == "reference" else "oracle"),
+        **extra,
     }, elapsed
+
+
+def _cpu_pure_c(levels):
+    """
+    BASELINE.md section 3, items 3 and 4, on ONE host core: the reference's C loops
+    with no Python per step -- advance_board(board, p, n_step=1000) and
+    life_occupancy(board, p, 1000), in board-steps/s.
+    """
+    from oracle import refload
+    sp = refload.load_ref_speedups()
+    gen = np.random.default_rng(11)
+    sp.set_bit_generator(gen.bit_generator)
+    boards = [np.array(lv["board"], dtype=np.uint16) for lv in levels[:6]]
+    probs = [float(lv["spawn_prob"]) for lv in levels[:6]]
+    t0 = time.perf_counter()
+    for b, p in zip(boards, probs):
+        sp.advance_board(b, p, 1000)
+    t_adv = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for b, p in zip(boards[:3], probs[:3]):
+        sp.life_occupancy(b, p, 1000)
+    t_occ = time.perf_counter() - t0
+    return {"pure_c_advance_board_steps_per_s_one_core": len(boards) * 1000 / t_adv,
+            "pure_c_life_occupancy_steps_per_s_one_core": 3 * 1000 / t_occ}
 
 
 def run_reference(args, levels):
