@@ -12,6 +12,9 @@ Fixture groups written (np.savez_compressed):
                      initial level data, PCG64 state, per-step reward / done /
                      success / agent loc / crc32(board) / crc32(goals) /
                      crc32(obs) / PCG64 state, and the final board + goals.
+                     Groups: benchmark / puzzle / maze level files and procgen levels
+                     of every BASELINE pool (25x25 append-still / append-spawn /
+                     prune-still, 50x50 navigation, 26x26 append-still).
   ops.npz            direct calls of the reference C functions on random
                      bit-pattern boards (advance_board, alive_counts,
                      execute_actions, life_occupancy, wrapped_label).
@@ -445,6 +448,18 @@ def main():
     if want("procgen25spawn"):
         group_procgen("procgen25spawn", "random/append-spawn", (25, 25), 6, 200, (25, 25),
                       TRAIN_CHANNELS, seed0=4)
+    # the other BASELINE pools, straight through the reference env: config 3 (prune-still
+    # 25x25), config 5 (navigation 50x50: dynamic goals, spawners, the wide kernels) and
+    # the reference-native 26x26 append-still
+    if want("procgen25prune"):
+        group_procgen("procgen25prune", "random/prune-still", (25, 25), 6, 250, (25, 25),
+                      TRAIN_CHANNELS, seed0=3)
+    if want("procgen50nav"):
+        group_procgen("procgen50nav", "random/navigation", (50, 50), 3, 150, (25, 25),
+                      TRAIN_CHANNELS, seed0=5)
+    if want("procgen26"):
+        group_procgen("procgen26", "random/append-still", (26, 26), 4, 300, (15, 15),
+                      SafeLifeEnv.output_channels, seed0=1)
 
 
 if __name__ == "__main__":
