@@ -371,6 +371,34 @@ def make_occupancy():
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def make_occupancy_nav50():
+    """The same on procgen 50x50 navigation levels (BASELINE config 5: the wide kernels)."""
+    recs = []
+    (fname, kind, data), = _load_files(["random/navigation"])
+    data = dict(data, board_shape=[50, 50])
+    for k, seed in enumerate(np.random.SeedSequence(55).spawn(2)):
+        game = _game_from_data(fname, kind, data, seed=seed)
+        rec, log, game = run_episode(game, seed, 40, (15, 15), None, action_seed=500 + k)
+        g = np.random.default_rng(5050 + k)
+        r0 = orc.rng_from_generator(g)
+        b0 = game._init_data["board"]
+        with set_rng(g):
+            b1 = speedups.advance_board(b0, game.spawn_prob, game.num_steps)
+            c0 = speedups.life_occupancy(b1, game.spawn_prob, 300)
+            c1 = speedups.life_occupancy(game.board, game.spawn_prob, 300)
+        recs.append({
+            "init_board": np.asarray(b0, dtype=np.uint16), "final_board": game.board.copy(),
+            "num_steps": np.int32(game.num_steps), "spawn_prob": np.float32(game.spawn_prob),
+            "rng0": r0, "rng1": orc.rng_from_generator(g),
+            "inaction_board": b1, "counts": np.stack([c0, c1]),
+        })
+    out = {k: np.stack([r[k] for r in recs]) for k in recs[0]}
+    out["num_samples"] = np.int32(300)
+    path = os.path.join(HERE, "occupancy_nav50.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+
+
 def make_side_effects():
     """side_effects.side_effect_score end to end on the reference."""
     from safelife.side_effects import side_effect_score
@@ -420,6 +448,8 @@ def main():
         make_occupancy()
     if want("side_effects"):
         make_side_effects()
+    if want("occupancy_nav50"):
+        make_occupancy_nav50()
     v10 = ["benchmarks/v1.0/%s.npz" % n for n in (
         "append-still", "append-dynamic", "append-spawn", "prune-dynamic", "prune-spawn",
         "prune-still", "prune-still-hard", "navigation")]

@@ -109,8 +109,9 @@ def test_wrapped_label_golden(sp, ops):
         assert num == n and np.array_equal(lab.ravel(), outs[i]), i
 
 
-def test_side_effect_occupancy_golden(sp):
-    d = gu.load_npz("occupancy.npz")
+@pytest.mark.parametrize("fixture", ["occupancy.npz", "occupancy_nav50.npz"])
+def test_side_effect_occupancy_golden(sp, fixture):
+    d = gu.load_npz(fixture)
     ns = int(d["num_samples"])
     for i in range(len(d["init_board"])):
         bg = _bitgen(d["rng0"][i])

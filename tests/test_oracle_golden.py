@@ -86,8 +86,9 @@ def test_wrapped_label_golden(ops):
         assert np.array_equal(lab.ravel(), outs[i]), i
 
 
-def test_side_effect_occupancy_golden():
-    d = gu.load_npz("occupancy.npz")
+@pytest.mark.parametrize("fixture", ["occupancy.npz", "occupancy_nav50.npz"])
+def test_side_effect_occupancy_golden(fixture):
+    d = gu.load_npz(fixture)
     ns = int(d["num_samples"])
     for i in range(len(d["init_board"])):
         rng = d["rng0"][i].copy()

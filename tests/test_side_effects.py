@@ -148,11 +148,13 @@ def _dev(a, dtype=None):
 
 
 @pytest.mark.gpu
-def test_side_effect_occupancy_golden_fused():
-    """sl_side_effect_occupancy on the reference's occupancy fixture, all episodes in one launch."""
+@pytest.mark.parametrize("fixture", ["occupancy.npz", "occupancy_nav50.npz"])
+def test_side_effect_occupancy_golden_fused(fixture):
+    """sl_side_effect_occupancy on the reference's occupancy fixtures (26x26 benchmark levels:
+    the narrow kernel; 50x50 navigation: the wide one), all episodes in one launch."""
     from safelife_b200 import side_effects as se
     from safelife_b200.levels import spawn_threshold
-    d = gu.load_npz("occupancy.npz")
+    d = gu.load_npz(fixture)
     thr = np.array([spawn_threshold(float(p)) for p in d["spawn_prob"]], dtype=np.int64)
     rng = _dev(d["rng0"].copy())
     counts = se.occupancy_counts(_dev(d["init_board"]), _dev(d["final_board"]), _dev(d["num_steps"]),
