@@ -127,11 +127,19 @@ int sl_wrapped_label_host(int32_t *data, int32_t *num_labels, int n, int H, int 
 /* Earth mover's distance between two histograms over the same k points, host
  * memory, no GPU involved: *out = min-cost flow of min(sum a, sum b) mass under
  * dist[k][k] + extra_mass_penalty * |sum a - sum b| (extra_mass_penalty < 0:
- * max(dist)).  Stands in for pyemd.emd as called by
+ * max(dist)).  dist must be a (quasi-)metric -- dist[i][i] = 0 and the directed
+ * triangle inequality -- as for pyemd's emd_hat_gd_metric: mass common to a[i]
+ * and b[i] stays in place.  Stands in for pyemd.emd as called by
  * side_effects.earth_mover_distance (side_effects.py:57); exact in double
  * precision, where pyemd/FastEMD quantises to 1e-6 of the maxima. */
 int sl_emd_host(const double *a, const double *b, const double *dist, int k,
                 double extra_mass_penalty, double *out);
+/* n independent problems (k[i] points each) on up to n_threads host threads
+ * (n_threads <= 0: one per hardware thread): the per-cell-type distances of all
+ * the episodes that finished in one step. */
+int sl_emd_host_batch(const double *const *a, const double *const *b,
+                      const double *const *dist, const int *k, int n,
+                      double extra_mass_penalty, double *out, int n_threads);
 
 /* ---- batched environment (SafeLifeEnv.step / reset) ------------------- */
 

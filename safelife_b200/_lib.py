@@ -91,6 +91,7 @@ PROTOTYPES = {
     "sl_life_occupancy": [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp],
     "sl_side_effect_occupancy": [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp],
     "sl_emd_host": [_vp, _vp, _vp, _i, ctypes.c_double, _vp],
+    "sl_emd_host_batch": [_vp, _vp, _vp, _vp, _i, ctypes.c_double, _vp, _i],
     "sl_alive_counts": [_vp, _vp, _vp, _i, _i, _vp],
     "sl_execute_actions": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "sl_wrapped_label": [_vp, _vp, _i, _i, _i, _vp],

@@ -431,6 +431,21 @@ int sl_emd_host(const double *a, const double *b, const double *dist, int k,
     return SL_OK;
 }
 
+int sl_emd_host_batch(const double *const *a, const double *const *b, const double *const *dist,
+                      const int *k, int n, double extra_mass_penalty, double *out, int n_threads) {
+    if (n < 0) return fail(SL_ERR_ARG, "n must be >= 0");
+    if (n == 0) return SL_OK;
+    if (!a || !b || !dist || !k || !out) return fail(SL_ERR_ARG, "null pointer");
+    for (int i = 0; i < n; i++) {
+        if (k[i] < 0) return fail(SL_ERR_ARG, "k must be >= 0");
+        if (k[i] > 0 && (!a[i] || !b[i] || !dist[i])) return fail(SL_ERR_ARG, "null pointer");
+        for (int j = 0; j < k[i]; j++)
+            if (!(a[i][j] >= 0.0) || !(b[i][j] >= 0.0)) return fail(SL_ERR_ARG, "histograms must be >= 0");
+    }
+    sl::emd_hat_batch(a, b, dist, k, n, extra_mass_penalty, out, n_threads);
+    return SL_OK;
+}
+
 // ---- batched environment ---------------------------------------------------
 
 static int check_batch(const SlEnvBatch *b) {

@@ -49,6 +49,33 @@ def test_emd_host_vs_lp(k):
             assert abs(got - want) <= EMD_TOL * max(1.0, abs(want)), (k, trial, penalty, got, want)
 
 
+def test_emd_host_batch_threads_and_larger_problems():
+    """sl_emd_host_batch: same values as one-by-one calls and as the LP, any thread count,
+    including problems where most mass is common to both histograms (pre-flowed)."""
+    from safelife_b200 import side_effects as se
+    rs = np.random.default_rng(99)
+    problems = [None]
+    for k in (5, 60, 150):
+        a = np.zeros((26, 26))
+        cells = rs.choice(26 * 26, k, replace=False)
+        a.flat[cells] = rs.random(k)
+        b = a.copy()
+        moved = rs.choice(cells, k // 2, replace=False)
+        b.flat[moved] *= rs.random(k // 2)                       # common mass + a deficit
+        b.flat[rs.choice(26 * 26, k // 3, replace=False)] += 0.2 * rs.random(k // 3)
+        problems.append(se._emd_problem(a, b))
+    problems.append(None)
+    want = [0.0 if p is None else orc.emd_lp(p[0], p[1], p[2], 1.0) for p in problems]
+    for threads in (1, 3, 0):
+        got = se.solve_emd_problems(problems, 1.0, threads)
+        assert got.shape == (len(problems),)
+        for g, w in zip(got, want):
+            assert abs(g - w) <= EMD_TOL * max(1.0, abs(w)), (threads, g, w)
+    for p, w in zip(problems, want):
+        if p is not None:
+            assert abs(_emd_host(p[0], p[1], p[2], 1.0) - w) <= EMD_TOL * max(1.0, abs(w))
+
+
 def test_emd_host_argument_errors():
     from safelife_b200 import _lib
     out = ctypes.c_double()
