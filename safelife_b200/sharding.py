@@ -5,8 +5,12 @@ Each env's step touches only its own board, goals and state record (the torus
 wrap is internal to a board), so the path shards with no exchange: rank g owns
 the contiguous env range [lo, hi), the level pool is replicated, and every
 per-env quantity that must not depend on the GPU count (level assignment, RNG
-stream) is derived from the *global* env index.  The only collective is the
-optional gather of step outputs to every rank (reward f32 + done u8 = 5 B/env).
+stream) is derived from the *global* env index.  The only collectives are
+optional and off the step path: the gather of step outputs to every rank
+(reward f32 + done u8 = 5 B/env) and the all-gather that reassembles the
+observation batch for a learner that wants all of it on one GPU (NCCL over
+NVLink / NVSwitch; 9 375 B/env for the training observation shape -- keeping the
+observations sharded and the policy data-parallel avoids it altogether).
 """
 import numpy as np
 import torch
@@ -69,3 +73,29 @@ def gather_step_outputs(reward, done, n_total, group=None):
     rewards = torch.cat([out[r, : h - l, 0] for r, (l, h) in enumerate(sizes)])
     dones = torch.cat([out[r, : h - l, 1] for r, (l, h) in enumerate(sizes)]).to(torch.uint8)
     return rewards, dones
+
+
+def gather_observations(obs, n_total, group=None):
+    """
+    All-gather of the per-rank observation tensors [n_local, ...] into the whole
+    batch [n_total, ...] in global env order, on every rank (one
+    all_gather_into_tensor; shards padded to the largest one).
+    """
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return obs.clone()
+    rank = dist.get_rank(group)
+    sizes = [shard_range(n_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    lo, hi = sizes[rank]
+    if obs.shape[0] != hi - lo:
+        raise ValueError("obs has %d envs, this rank owns %d" % (obs.shape[0], hi - lo))
+    padded = obs
+    if hi - lo < width:
+        padded = torch.zeros((width,) + tuple(obs.shape[1:]), dtype=obs.dtype, device=obs.device)
+        padded[: hi - lo] = obs
+    flat = torch.empty((world * width,) + tuple(obs.shape[1:]), dtype=obs.dtype, device=obs.device)
+    dist.all_gather_into_tensor(flat, padded.contiguous(), group=group)
+    if all(h - l == width for l, h in sizes):
+        return flat
+    return torch.cat([flat[r * width: r * width + (h - l)] for r, (l, h) in enumerate(sizes)])

@@ -44,7 +44,13 @@ def _worker(rank, world, port, n_total, ret):
         r, d = sharding.gather_step_outputs(reward, done, n_total)
         want_r = torch.arange(n_total, dtype=torch.float32) * 0.5
         want_d = (torch.arange(n_total) % 3 == 0).to(torch.uint8)
-        ret[rank] = bool(torch.equal(r, want_r) and torch.equal(d, want_d))
+        obs = (torch.arange(lo, hi, dtype=torch.int64)[:, None, None, None] +
+               torch.arange(3 * 2 * 5).reshape(3, 2, 5)).to(torch.uint8)
+        whole = sharding.gather_observations(obs, n_total)
+        want_o = (torch.arange(n_total, dtype=torch.int64)[:, None, None, None] +
+                  torch.arange(3 * 2 * 5).reshape(3, 2, 5)).to(torch.uint8)
+        ret[rank] = bool(torch.equal(r, want_r) and torch.equal(d, want_d) and
+                         torch.equal(whole, want_o) and whole.dtype == torch.uint8)
     finally:
         dist.destroy_process_group()
 
