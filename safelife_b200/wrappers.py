@@ -175,7 +175,37 @@ class SimpleSideEffectPenalty(BaseWrapper):
     penalty_coef = 0.0
     baseline = "starting-state"     # or "inaction"
     ignore_reward_cells = False
-    spawn_prob = 0.3                # used to advance an "inaction" baseline
+
+    def _advance_baseline(self, base):
+        """
+        The counterfactual board advances with its level's spawn_prob
+        (``advance_board(self.baseline_board, self.game.spawn_prob)``,
+        env_wrappers.py:179-180).  Its draws come from per-env PCG64 streams of
+        their own: the reference takes them from the process-global generator,
+        which has no batched counterpart.
+        """
+        from . import _lib
+        pool = getattr(self, "_pool_spawn", None)
+        if pool is None:
+            probs = np.array([lv["spawn_prob"] for lv in base.pool.levels], dtype=np.float64)
+            self._uniform_spawn = float(probs[0]) if (probs == probs[0]).all() else None
+            pool = self._pool_spawn = torch.from_numpy(probs).to(base.device)
+        bb, rng = self.baseline_board, self._baseline_rng
+        H, W = base.pool.H, base.pool.W
+        if self._uniform_spawn is not None:
+            _lib.check(base._lib.sl_advance_board(
+                bb.data_ptr(), bb.data_ptr(), base.num_envs, H, W, self._uniform_spawn, 1,
+                rng.data_ptr(), base._stream()))
+            return
+        per_env = pool[base._t["level_id"].long()]
+        for p in torch.unique(per_env).tolist():          # mixed pools: one launch per value
+            idx = torch.nonzero(per_env == p).flatten()
+            sub, sub_rng = bb[idx].contiguous(), rng[idx].contiguous()
+            _lib.check(base._lib.sl_advance_board(
+                sub.data_ptr(), sub.data_ptr(), idx.numel(), H, W, float(p), 1,
+                sub_rng.data_ptr(), base._stream()))
+            bb[idx] = sub
+            rng[idx] = sub_rng
 
     def _after_reset(self, mask):
         base = self.unwrapped
@@ -192,13 +222,7 @@ class SimpleSideEffectPenalty(BaseWrapper):
         obs, reward, done, info = self.env.step(action)
         base = self.unwrapped
         if self.baseline == "inaction":
-            # the counterfactual board advances too (own PCG64 streams: the reference
-            # draws these from the process-global generator, env_wrappers.py:179-180)
-            from . import _lib
-            bb = self.baseline_board
-            _lib.check(base._lib.sl_advance_board(
-                bb.data_ptr(), bb.data_ptr(), base.num_envs, base.pool.H, base.pool.W,
-                float(self.spawn_prob), 1, self._baseline_rng.data_ptr(), base._stream()))
+            self._advance_baseline(base)
         if not self.ignore_reward_cells:
             side_effect = base.side_effect_cells(self.baseline_board).to(torch.int64)
         else:
@@ -229,10 +253,12 @@ class SimpleSideEffectPenalty(BaseWrapper):
         return (~non_effects).sum(dim=1)
 
 
-def training_stack(env, exit_difficulty=1.0, se_baseline="starting-state", se_penalty=0.0):
+def training_stack(env, exit_difficulty=1.0, se_baseline="starting-state", se_penalty=0.0,
+                   ignore_reward_cells=False):
     """The wrapper chain of training/env_factory.py:274-283 (without the logger)."""
     env = MovementBonusWrapper(env, as_penalty=True)
     env = ExtraExitBonus(env)
-    env = SimpleSideEffectPenalty(env, baseline=se_baseline, penalty_coef=se_penalty)
+    env = SimpleSideEffectPenalty(env, baseline=se_baseline, penalty_coef=se_penalty,
+                                  ignore_reward_cells=ignore_reward_cells)
     env = MinPerformanceScheduler(env, min_performance_fraction=exit_difficulty)
     return env

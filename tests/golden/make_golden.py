@@ -113,7 +113,8 @@ def run_episode(game, seed, time_limit, view_shape, channels, action_seed):
     return rec, log, env.game
 
 
-def run_wrapped_episode(game, seed, time_limit, action_seed, se_penalty, exit_difficulty):
+def run_wrapped_episode(game, seed, time_limit, action_seed, se_penalty, exit_difficulty,
+                        baseline="starting-state", ignore_reward_cells=False):
     """One episode through the training wrapper stack of training/env_factory.py:274-283."""
     from safelife import env_wrappers
     game.seed = seed
@@ -121,8 +122,8 @@ def run_wrapped_episode(game, seed, time_limit, action_seed, se_penalty, exit_di
                       output_channels=None, should_calculate_side_effects=False)
     env = env_wrappers.MovementBonusWrapper(env, as_penalty=True)
     env = env_wrappers.ExtraExitBonus(env)
-    env = env_wrappers.SimpleSideEffectPenalty(env, baseline="starting-state",
-                                               penalty_coef=se_penalty)
+    env = env_wrappers.SimpleSideEffectPenalty(env, baseline=baseline, penalty_coef=se_penalty,
+                                               ignore_reward_cells=ignore_reward_cells)
     env = env_wrappers.MinPerformanceScheduler(env, min_performance_fraction=exit_difficulty)
     rec = level_record(game)        # before reset: the scheduler rescales min_performance
     env.reset()
@@ -141,7 +142,7 @@ def run_wrapped_episode(game, seed, time_limit, action_seed, se_penalty, exit_di
 
 
 def group_wrapped(name, paths, limit, time_limit, seed0, se_penalty, exit_difficulty,
-                  min_performance=None):
+                  min_performance=None, baseline="starting-state", ignore_reward_cells=False):
     recs, logs = [], []
     ss = np.random.SeedSequence(seed0)
     for path in paths:
@@ -151,7 +152,8 @@ def group_wrapped(name, paths, limit, time_limit, seed0, se_penalty, exit_diffic
                 game.min_performance = min_performance
                 game._init_data = game.serialize()
             rec, log = run_wrapped_episode(game, ss.spawn(1)[0], time_limit,
-                                           len(recs) + 1000 * seed0, se_penalty, exit_difficulty)
+                                           len(recs) + 1000 * seed0, se_penalty, exit_difficulty,
+                                           baseline, ignore_reward_cells)
             recs.append(rec)
             logs.append(log)
     L, T = len(recs), max(len(lg["action"]) for lg in logs)
@@ -165,6 +167,8 @@ def group_wrapped(name, paths, limit, time_limit, seed0, se_penalty, exit_diffic
     out["time_limit"] = np.int32(time_limit)
     out["se_penalty"] = np.float64(se_penalty)
     out["exit_difficulty"] = np.float64(exit_difficulty)
+    out["baseline"] = np.array(baseline)
+    out["ignore_reward_cells"] = np.uint8(ignore_reward_cells)
     path = os.path.join(HERE, "wrapped_%s.npz" % name)
     np.savez_compressed(path, **out)
     print("wrote", path, "levels", L, "max steps", T, os.path.getsize(path) // 1024, "KiB")
@@ -469,6 +473,17 @@ def main():
                      TRAIN_CHANNELS, seed0=14)
     if want("wrapped"):
         group_wrapped("v1.0", v10[:6], 3, 120, seed0=21, se_penalty=0.7, exit_difficulty=0.5)
+        # the "inaction" baseline (a second stencil on a shadow board per step,
+        # env_wrappers.py:179-180) on levels without spawners: the reference draws the
+        # shadow board's spawns from the process-global generator, which has no batched
+        # counterpart, so only deterministic levels can be pinned -- the -dynamic tasks
+        # (oscillators: the shadow board really moves) and one still task
+        quiet = ["benchmarks/v1.0/%s.npz" % n for n in ("append-dynamic", "prune-dynamic", "prune-still")]
+        group_wrapped("inaction", quiet, 3, 120, seed0=23, se_penalty=0.5, exit_difficulty=0.7,
+                      baseline="inaction")
+        # ignore_reward_cells=True (env_wrappers.py:197-205), with spawners on the real board
+        group_wrapped("ignore", [v10[0], v10[2], v10[4]], 3, 120, seed0=24, se_penalty=0.3,
+                      exit_difficulty=1.0, ignore_reward_cells=True)
         group_wrapped("mazes", ["mazes/*.npz"], None, 600, seed0=22, se_penalty=0.25,
                       exit_difficulty=1.0, min_performance=0.0)
     if want("procgen25"):

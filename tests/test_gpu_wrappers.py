@@ -12,7 +12,12 @@ import golden_util as gu
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["v1.0", "mazes"])
+def _as_i16(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint16).view(np.int16))
+
+
+@pytest.mark.parametrize("name", ["v1.0", "mazes", "inaction", "ignore"])
 def test_training_stack_matches_reference(name):
     from safelife_b200.env import BatchedSafeLifeEnv
     from safelife_b200 import wrappers
@@ -23,7 +28,8 @@ def test_training_stack_matches_reference(name):
                               view_shape=(5, 5), output_channels=None)
     base.set_rng_state(d["rng_init"])
     env = wrappers.training_stack(base, exit_difficulty=float(d["exit_difficulty"]),
-                                  se_penalty=float(d["se_penalty"]))
+                                  se_penalty=float(d["se_penalty"]), se_baseline=str(d["baseline"]),
+                                  ignore_reward_cells=bool(d["ignore_reward_cells"]))
     env.reset()
     exits = 0
     for t in range(d["action"].shape[1]):
@@ -37,6 +43,9 @@ def test_training_stack_matches_reference(name):
             exits += int(done[i] and not info["times_up"][i].item())
     if name == "mazes":
         assert exits > 0          # ExtraExitBonus was exercised
+    if name == "inaction":        # oscillators: the shadow board is not the starting state any more
+        start = _as_i16(np.stack([lv["board"] for lv in levels])).cuda()
+        assert not (env.env.baseline_board == start).all()
 
 
 def test_reset_done_restarts_wrapper_state():
