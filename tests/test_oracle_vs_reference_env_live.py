@@ -75,3 +75,38 @@ def test_oracle_env_follows_reference_env(yaml_name, shape, seed0, steps, view):
                 break
         assert ora.ep_reward[0] == np.float32(env.episode_reward)
         assert ora.ep_length[0] == env.episode_length
+
+
+@pytest.mark.parametrize("yaml_name,seed0", [("random/append-still-easy", 911), ("random/append-spawn", 912),
+                                             ("random/prune-dynamic", 913)])
+def test_oracle_side_effect_score_follows_reference(yaml_name, seed0):
+    """side_effects.side_effect_score (with the LP stand-in for pyemd) at the end of a short
+    random episode: same keys, same inaction totals, same EMD, same RNG consumption."""
+    refload.load_reference()
+    from safelife.level_iterator import _game_from_data, _load_files
+    from safelife.random import set_rng
+    from safelife.safelife_env import SafeLifeEnv
+    from safelife.side_effects import side_effect_score
+    (fname, kind, data), = _load_files([yaml_name])
+    data = dict(data, board_shape=[25, 25])
+    seed = np.random.SeedSequence(seed0).spawn(1)[0]
+    game = _game_from_data(fname, kind, data, seed=seed)
+    game.seed = seed
+    env = SafeLifeEnv(iter([game]), time_limit=60, should_calculate_side_effects=False)
+    env.reset()
+    arng = np.random.default_rng(seed0)
+    for t in range(60):
+        _, _, done, _ = env.step(int(arng.integers(0, 9)))
+        if done:
+            break
+    g = np.random.default_rng(seed0 + 1)
+    rng = orc.rng_from_generator(g)
+    with set_rng(g):
+        want = side_effect_score(env.game, num_samples=150)
+    got, _ = orc.side_effect_score(env.game._init_data["board"], env.game.board, env.game.num_steps,
+                                   env.game.spawn_prob, rng, 150)
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k][0] - want[k][0]) <= 1e-9 * max(1.0, want[k][0]), k
+        assert got[k][1] == want[k][1], k
+    assert np.array_equal(rng, orc.rng_from_generator(g))
