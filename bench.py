@@ -477,6 +477,28 @@ def run_ours(args, levels):
     barrier()
     floor_ms = sum(e[0].elapsed_time(e[1]) for e in fl_ev) / len(fl_ev)
 
+    # ---- supplementary: the gym step as a user calls it -- physics + auto-reset +
+    # observation in ONE launch (sl_env_step_obs), L2 flushed, device-timed ----
+    import ctypes
+    Ks = min(K, 200)
+    so_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(Ks)]
+    obs_spec = ctypes.byref(env._obs_specs[0])
+    obs_plan, obs_launches = env.step_plan(obs=True)
+    for t in range(3):
+        _lib.check(lib.sl_env_step_obs(bref, actions[t].data_ptr(), obs_spec, args.kernel,
+                                       _lib.SL_STEP_AUTO_RESET, stream))
+    barrier()
+    for t in range(Ks):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        so_ev[t][0].record()
+        _lib.check(lib.sl_env_step_obs(bref, actions[Wm + t].data_ptr(), obs_spec, args.kernel,
+                                       _lib.SL_STEP_AUTO_RESET, stream))
+        so_ev[t][1].record()
+    barrier()
+    step_obs_ms = sum(e[0].elapsed_time(e[1]) for e in so_ev) / Ks
+    step_obs_bytes = bytes_per_launch + n * (2 * H * W + 25 * 25 * len(train_channels))
+
     # ---- supplementary: SafeLifeEnv.get_obs for the whole batch (next row 8f-1) ----
     Ko = min(K, 100)
     obs_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(Ko)]
@@ -538,10 +560,20 @@ def run_ours(args, levels):
             },
             "wall_s_timed_region": wall,
             "launch_floor_ms": floor_ms,
+            "step_with_obs": {
+                "ms": step_obs_ms, "env_steps_per_s": n / (step_obs_ms * 1e-3),
+                "kernel": obs_plan, "launches_per_step": obs_launches,
+                "bytes_per_launch": step_obs_bytes,
+                "achieved_gbs": step_obs_bytes / (step_obs_ms * 1e-3) / 1e9,
+                "frac": step_obs_bytes / (step_obs_ms * 1e-3) / 1e9 / peak,
+                "note": "supplementary: SafeLifeEnv.step as the gym API returns it -- physics, "
+                        "auto-reset and the uint8[N,25,25,15] training observation written by one "
+                        "launch (sl_env_step_obs); bytes = step bytes + goals read + obs written; "
+                        "L2 flushed; rank 0"},
             "obs": {
                 "ms": obs_ms, "bytes_per_launch": obs_bytes,
                 "achieved_gbs": obs_bytes / (obs_ms * 1e-3) / 1e9,
-                "note": "supplementary: k_get_obs, uint8[N,25,25,15] training observations "
+                "note": "supplementary: k_get_obs_warp (stand-alone), uint8[N,25,25,15] training observations "
                         "(read board + goals, write obs), L2 flushed; rank 0"},
             "back_to_back": {
                 "ms_per_step": l2_ms / K, "env_steps_per_s": n * K / (l2_ms * 1e-3),

@@ -43,7 +43,7 @@ extern "C" {
 #define SL_ERR_CUDA      2   /* CUDA runtime error, see sl_last_error() */
 #define SL_ERR_NO_DEVICE 3   /* no usable CUDA device: there is no CPU fallback */
 
-#define SL_ABI_VERSION   1
+#define SL_ABI_VERSION   2
 
 /* ---- library plumbing ------------------------------------------------ */
 int sl_abi_version(void);
@@ -236,11 +236,39 @@ typedef struct SlEnvBatch {
 int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                 void *stream);
 
+/* The observation a step returns (SafeLifeEnv.step ends in `return self.get_obs(),
+ * ...`, safelife_env.py:195; get_obs :105-146 with helper_utils.recenter_view,
+ * helper_utils.py:42-75), described as for sl_get_obs but with the channel list
+ * by value.  obs: device uint8[n_envs][vh][vw][n_channels], or uint32[n_envs][vh][vw]
+ * when n_channels == 0 (output_channels=None). */
+typedef struct SlObsSpec {
+    void   *obs;
+    int32_t vh, vw;            /* SafeLifeEnv.view_shape */
+    int32_t n_channels;        /* 0 .. 32 */
+    int32_t remove_white_goals;
+    int32_t channels[32];      /* SafeLifeEnv.output_channels: bit positions 0 .. 31 */
+} SlObsSpec;
+
+/* sl_env_step with the observation written by the same launch, from the board
+ * slabs the step kernel already holds in shared memory: what SafeLifeEnv.step
+ * returns, one launch per gym step.  The observation describes the env as the
+ * call leaves it -- with SL_STEP_AUTO_RESET a finished env shows the first
+ * observation of its next episode, which is what the reference's rollout loop
+ * feeds the policy next (training/base_algo.py:231-238; the terminal observation
+ * of a finished env is never used there, training/ppo.py:117-121).  obs == NULL
+ * is sl_env_step.  On the generic path (kernel 1, or boards beyond the warp
+ * kernels) the observation is a separate launch of the same writer. */
+int sl_env_step_obs(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
+                    int kernel, int flags, void *stream);
+
 /* Which kernel(s) sl_env_step(batch, ..., kernel, ...) launches on the current
  * device, as text (for benchmarks and profiles), and how many launches that is
  * per step without SL_STEP_AUTO_RESET on the generic path.  Launches nothing. */
 int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_len,
                      int *n_launches);
+/* The same for sl_env_step_obs (obs may be NULL). */
+int sl_env_step_obs_plan(const SlEnvBatch *batch, const SlObsSpec *obs, int kernel, char *text,
+                         int text_len, int *n_launches);
 
 /* An empty kernel with the step kernel's launch shape (one 256-thread CTA per 8
  * envs, the same parameter block): what a benchmark's event pair measures
@@ -277,6 +305,9 @@ int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *ne
 int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw,
                const int32_t *channels, int n_channels, int remove_white_goals,
                void *stream);
+/* The same with the view described by an SlObsSpec (channel list in host memory,
+ * no copy, no synchronisation): what SafeLifeEnv.reset returns. */
+int sl_get_obs_spec(const SlEnvBatch *batch, const SlObsSpec *obs, void *stream);
 
 /* SimpleSideEffectPenalty.step cell count (env_wrappers.py:177-213,
  * ignore_reward_cells=False): out[e] = number of cells whose non-player bits

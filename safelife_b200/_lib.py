@@ -19,6 +19,7 @@ _SRC = os.path.join(_PKG, "csrc")
 SL_OK, SL_ERR_ARG, SL_ERR_CUDA, SL_ERR_NO_DEVICE = 0, 1, 2, 3
 SL_RESET_NEXT_LEVEL, SL_RESET_KEEP_STATS = 1, 2
 SL_STEP_AUTO_RESET = 1
+SL_ABI_VERSION = 2
 SL_POOL_UNIFORM_TABLE, SL_POOL_STATIC_GOALS = 1, 2
 
 NVCC_FLAGS = [
@@ -66,6 +67,13 @@ class SlEnvBatch(ctypes.Structure):
                    "pool_init_points", "pool_required", "pool_spawn_thr")]
 
 
+class SlObsSpec(ctypes.Structure):
+    """Mirror of struct SlObsSpec (include/safelife_b200.h)."""
+    _fields_ = [("obs", ctypes.c_void_p), ("vh", ctypes.c_int32), ("vw", ctypes.c_int32),
+                ("n_channels", ctypes.c_int32), ("remove_white_goals", ctypes.c_int32),
+                ("channels", ctypes.c_int32 * 32)]
+
+
 # numpy mirror of struct SlEnvState (96 bytes per env)
 import numpy as _np  # noqa: E402
 
@@ -102,10 +110,13 @@ PROTOTYPES = {
     "sl_wrapped_label_host": [_vp, _vp, _i, _i, _i],
     "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_sync": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
+    "sl_env_step_obs": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec), _i, _i, _vp],
     "sl_env_step_plan": [ctypes.POINTER(SlEnvBatch), _i, _vp, _i, _vp],
+    "sl_env_step_obs_plan": [ctypes.POINTER(SlEnvBatch), ctypes.POINTER(SlObsSpec), _i, _vp, _i, _vp],
     "sl_launch_floor": [ctypes.POINTER(SlEnvBatch), _vp],
     "sl_env_reset": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _i, _vp],
     "sl_get_obs": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _i, _i, _vp],
+    "sl_get_obs_spec": [ctypes.POINTER(SlEnvBatch), ctypes.POINTER(SlObsSpec), _vp],
     "sl_side_effect_cells": [ctypes.POINTER(SlEnvBatch), _vp, _vp, _vp],
 }
 

@@ -16,6 +16,7 @@
 #include "cells.cuh"
 #include "emd_host.h"
 #include "generic_kernels.cuh"
+#include "obs.cuh"
 #include "warp_kernels.cuh"
 
 namespace {
@@ -94,8 +95,14 @@ struct SmemGrant {
 std::mutex g_grant_mutex;
 std::vector<SmemGrant> g_grants;
 
+int prepare_smem_ptr(const void *kernel, size_t bytes);
+
 template <typename K>
 int prepare_smem(K kernel, size_t bytes) {
+    return prepare_smem_ptr((const void *)kernel, bytes);
+}
+
+int prepare_smem_ptr(const void *kernel, size_t bytes) {
     DeviceProps p;
     int rc = device_props(&p);
     if (rc) return rc;
@@ -105,7 +112,7 @@ int prepare_smem(K kernel, size_t bytes) {
     if (bytes <= 48 * 1024) return SL_OK;
     int dev = 0;
     SL_CUDA(cudaGetDevice(&dev));
-    const void *key = (const void *)kernel;
+    const void *key = kernel;
     std::lock_guard<std::mutex> lock(g_grant_mutex);
     for (SmemGrant &g : g_grants) {
         if (g.kernel == key && g.dev == dev) {
@@ -464,10 +471,39 @@ static int check_batch(const SlEnvBatch *b) {
     return SL_OK;
 }
 
-int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
-                void *stream) {
+static int check_obs_spec(const SlObsSpec *o) {
+    if (o->vh < 1 || o->vw < 1 || o->n_channels < 0) return fail(SL_ERR_ARG, "bad view shape");
+    if (o->n_channels > 32) return fail(SL_ERR_ARG, "at most 32 output channels (bits of the uint32 view)");
+    if ((long long)o->vh * o->vw > (1 << 20)) return fail(SL_ERR_ARG, "view too large");
+    if (!o->obs) return fail(SL_ERR_ARG, "null observation pointer");
+    for (int k = 0; k < o->n_channels; k++)
+        if (o->channels[k] < 0 || o->channels[k] > 31)
+            return fail(SL_ERR_ARG, "output channels are bit positions 0..31");
+    return SL_OK;
+}
+
+static int launch_get_obs(const SlEnvBatch *batch, const sl::ObsParams &O, cudaStream_t st) {
+    DeviceProps props;
+    int rc = device_props(&props);
+    if (rc) return rc;
+    const size_t smem = (size_t)sl::OBS_WARPS * sl::obs_stage_bytes(O.vh, O.vw, O.n_channels);
+    rc = prepare_smem(sl::k_get_obs_warp, smem);
+    if (rc) return rc;
+    int grid = (batch->n_envs + sl::OBS_WARPS - 1) / sl::OBS_WARPS;
+    const int cap = props.sm_count * 32;
+    if (grid > cap) grid = cap;
+    sl::k_get_obs_warp<<<grid, sl::OBS_WARPS * 32, smem, st>>>(*batch, O);
+    return launch_status("k_get_obs_warp");
+}
+
+static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
+                         int kernel, int flags, void *stream) {
     int rc = check_batch(batch);
     if (rc) return rc;
+    if (obs) {
+        rc = check_obs_spec(obs);
+        if (rc) return rc;
+    }
     if (batch->n_envs == 0) return SL_OK;
     if (!actions) return fail(SL_ERR_ARG, "null actions");
     if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
@@ -476,33 +512,17 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
     if (kernel == 2 && !warp_ok)
         return fail(SL_ERR_ARG, "warp kernel needs 3 <= H, W <= %d", sl::WARP_MAX_DIM);
     if (flags & ~SL_STEP_AUTO_RESET) return fail(SL_ERR_ARG, "unknown step flags");
+    sl::ObsParams O;
+    if (obs) O = sl::make_obs_params(*obs);
     if (kernel == 2 || (kernel == 0 && warp_ok)) {
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
-        const int cells = batch->H * batch->W;
-        if (sl::warp_kernel_is_narrow(batch->H, batch->W)) {
-#define SL_PREP_SHAPE(S, C, R)                                                                   \
-            if (sl::pipe_smem_bytes(cells, S, R) <= (size_t)props.max_smem_optin) {              \
-                rc = prepare_smem(sl::k_env_step_pipe<S, C, R>, sl::pipe_smem_bytes(cells, S, R)); \
-                if (rc) return rc;                                                               \
-            }
-            SL_PIPE_SHAPES(SL_PREP_SHAPE)
-#undef SL_PREP_SHAPE
-            rc = prepare_smem(sl::k_env_step_warp<sl::Narrow, true>,
-                              sl::warp_step_smem_bytes<sl::Narrow>(cells, true));
-            if (rc) return rc;
-            rc = prepare_smem(sl::k_env_step_warp<sl::Narrow, false>,
-                              sl::warp_step_smem_bytes<sl::Narrow>(cells, false));
-        } else {
-            rc = prepare_smem(sl::k_env_step_warp<sl::Wide, true>,
-                              sl::warp_step_smem_bytes<sl::Wide>(cells, true));
-            if (rc) return rc;
-            rc = prepare_smem(sl::k_env_step_warp<sl::Wide, false>,
-                              sl::warp_step_smem_bytes<sl::Wide>(cells, false));
-        }
+        const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, props.sm_count,
+                                                      props.smem_per_sm);
+        rc = sl::launch_env_step_warp(*batch, obs ? &O : nullptr, actions, flags, p, st,
+                                      [](const void *fn, size_t smem) { return prepare_smem_ptr(fn, smem); });
         if (rc) return rc;
-        sl::launch_env_step_warp(*batch, actions, flags, props.sm_count, props.smem_per_sm, st);
         return launch_status("k_env_step_warp");
     }
     size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
@@ -510,16 +530,34 @@ int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int
     if (rc) return rc;
     sl::k_env_step_generic<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, st>>>(*batch, actions);
     rc = launch_status("k_env_step_generic");
-    if (rc || !(flags & SL_STEP_AUTO_RESET)) return rc;
-    return sl_env_reset(batch, batch->done, nullptr, SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS, stream);
+    if (rc) return rc;
+    if (flags & SL_STEP_AUTO_RESET) {
+        rc = sl_env_reset(batch, batch->done, nullptr, SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS, stream);
+        if (rc) return rc;
+    }
+    return obs ? launch_get_obs(batch, O, st) : SL_OK;
 }
 
-int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_len,
-                     int *n_launches) {
+int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                void *stream) {
+    return env_step_impl(batch, actions, nullptr, kernel, flags, stream);
+}
+
+int sl_env_step_obs(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
+                    int kernel, int flags, void *stream) {
+    return env_step_impl(batch, actions, obs, kernel, flags, stream);
+}
+
+static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int kernel, char *text,
+                              int text_len, int *n_launches) {
     int rc = check_batch(batch);
     if (rc) return rc;
+    if (obs) {
+        rc = check_obs_spec(obs);
+        if (rc) return rc;
+    }
     if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
-    char buf[256];
+    char buf[320];
     int launches = 0;
     const bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
     if (batch->n_envs == 0) {
@@ -529,27 +567,41 @@ int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_l
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
-        const sl::StepPlan p = sl::plan_env_step_warp(*batch, props.sm_count, props.smem_per_sm);
+        sl::ObsParams O;
+        if (obs) O = sl::make_obs_params(*obs);
+        const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, props.sm_count,
+                                                      props.smem_per_sm);
         const char *goals = p.goals_resident ? "goals resident" : "goals in place";
+        const char *ob = p.obs ? ", obs fused" : "";
         int n = 0;
         if (p.piped_groups > 0) {
-            n += snprintf(buf + n, sizeof buf - n, "k_env_step_pipe<%d stages, %d CTAs/SM, %s> grid %d",
-                          p.pipe_stages, p.pipe_ctas, goals, p.pipe_grid);
+            n += snprintf(buf + n, sizeof buf - n, "k_env_step_pipe<%d stages, %d CTAs/SM, %s%s> grid %d",
+                          p.pipe_stages, p.pipe_ctas, goals, ob, p.pipe_grid);
             launches++;
         }
         if (p.single_groups > 0) {
-            n += snprintf(buf + n, sizeof buf - n, "%sk_env_step_warp<%s, %s> grid %d", n ? " + " : "",
-                          p.narrow ? "Narrow" : "Wide", goals, p.single_groups);
+            n += snprintf(buf + n, sizeof buf - n, "%sk_env_step_warp<%s, %s%s> grid %d", n ? " + " : "",
+                          p.narrow ? "Narrow" : "Wide", goals, ob, p.single_groups);
             launches++;
         }
     } else {
-        snprintf(buf, sizeof buf, "k_env_step_generic grid %d (+ k_env_reset with SL_STEP_AUTO_RESET)",
-                 grid_for(batch->n_envs));
-        launches = 1;
+        snprintf(buf, sizeof buf, "k_env_step_generic grid %d (+ k_env_reset with SL_STEP_AUTO_RESET)%s",
+                 grid_for(batch->n_envs), obs ? " + k_get_obs_warp" : "");
+        launches = obs ? 2 : 1;
     }
     if (text && text_len > 0) snprintf(text, (size_t)text_len, "%s", buf);
     if (n_launches) *n_launches = launches;
     return SL_OK;
+}
+
+int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_len,
+                     int *n_launches) {
+    return env_step_plan_impl(batch, nullptr, kernel, text, text_len, n_launches);
+}
+
+int sl_env_step_obs_plan(const SlEnvBatch *batch, const SlObsSpec *obs, int kernel, char *text,
+                         int text_len, int *n_launches) {
+    return env_step_plan_impl(batch, obs, kernel, text, text_len, n_launches);
 }
 
 namespace {
@@ -597,13 +649,39 @@ int sl_get_obs(const SlEnvBatch *batch, void *obs, int vh, int vw, const int32_t
     if (n_channels > 32) return fail(SL_ERR_ARG, "at most 32 output channels (bits of the uint32 view)");
     if (batch->n_envs == 0) return SL_OK;
     if (!obs || (n_channels > 0 && !channels)) return fail(SL_ERR_ARG, "null pointer");
-    // view, source-row and -column tables, packed channel bit stream
-    size_t smem = ((size_t)vh * vw + vh + vw + ((size_t)vh * vw * n_channels + 31) / 32 + 2) * 4;
-    rc = prepare_smem(sl::k_get_obs, smem);
+    // the channel list is a device array here (ABI v1); it travels to the kernel by value
+    SlObsSpec spec = {};
+    spec.obs = obs;
+    spec.vh = vh;
+    spec.vw = vw;
+    spec.n_channels = n_channels;
+    spec.remove_white_goals = remove_white_goals;
+    if (n_channels > 0) {
+        cudaPointerAttributes attr;
+        cudaError_t err = cudaPointerGetAttributes(&attr, channels);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            attr.type = cudaMemoryTypeUnregistered;
+        }
+        if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) {
+            SL_CUDA(cudaMemcpyAsync(spec.channels, channels, (size_t)n_channels * 4,
+                                    cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+            SL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        } else {
+            memcpy(spec.channels, channels, (size_t)n_channels * 4);
+        }
+    }
+    return sl_get_obs_spec(batch, &spec, stream);
+}
+
+int sl_get_obs_spec(const SlEnvBatch *batch, const SlObsSpec *obs, void *stream) {
+    int rc = check_batch(batch);
     if (rc) return rc;
-    sl::k_get_obs<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, (cudaStream_t)stream>>>(
-        *batch, obs, vh, vw, channels, n_channels, remove_white_goals);
-    return launch_status("k_get_obs");
+    if (!obs) return fail(SL_ERR_ARG, "null observation spec");
+    rc = check_obs_spec(obs);
+    if (rc) return rc;
+    if (batch->n_envs == 0) return SL_OK;
+    return launch_get_obs(batch, sl::make_obs_params(*obs), (cudaStream_t)stream);
 }
 
 int sl_side_effect_cells(const SlEnvBatch *batch, const uint16_t *baseline, int32_t *out,

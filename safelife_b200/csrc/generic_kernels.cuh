@@ -523,119 +523,6 @@ k_env_reset(SlEnvBatch B, const uint8_t *__restrict__ mask, const int32_t *__res
     }
 }
 
-// SafeLifeEnv.get_obs (safelife_env.py:105-146, helper_utils.py:42-75).
-// One CTA per env: build the uint32 view in shared memory, then expand.  The
-// kernel is instruction-bound unless the index arithmetic stays out of the
-// per-cell loops, so: wrapped source rows / columns come from two small tables
-// built once per env, the channel list is applied as runs of consecutive bits
-// (the training list (0-4, 7-11, 25-27, 12-13) is four runs, not fifteen bits),
-// and the byte stream is written 16 bytes per store with stepping indices.
-__global__ void __launch_bounds__(GENERIC_THREADS)
-k_get_obs(SlEnvBatch B, void *__restrict__ obs, int vh, int vw,
-          const int32_t *__restrict__ channels, int n_channels, int remove_white) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ int run_src[32], run_dst[32], n_runs;
-    __shared__ uint32_t run_mask[32];
-    const int H = B.H, W = B.W, cells = H * W, vcells = vh * vw;
-    uint32_t *view = (uint32_t *)smem_raw;                  // [vcells]
-    int *ymap = (int *)(view + vcells), *xmap = ymap + vh;   // [vh] source row * W, [vw] source column
-    uint32_t *stream = (uint32_t *)(xmap + vw);              // [vcells * C / 32 + 2] packed channel bits
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    if (threadIdx.x == 0) {
-        int nr = 0;
-        for (int k = 0; k < n_channels;) {
-            int len = 1;
-            const int c0 = channels[k];
-            while (k + len < n_channels && channels[k + len] == c0 + len) len++;
-            run_src[nr] = c0;
-            run_dst[nr] = k;
-            run_mask[nr] = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
-            nr++;
-            k += len;
-        }
-        n_runs = nr;
-    }
-    __syncthreads();
-    for (int e = blockIdx.x; e < B.n_envs; e += gridDim.x) {
-        const uint16_t *board = B.board + (size_t)e * cells;
-        const uint16_t *goals = B.goals + (size_t)e * cells;
-        int y0 = B.state[e].loc_row, x0 = B.state[e].loc_col;
-        if (y0 < 0) { y0 = 0; x0 = 0; }
-        auto packed = [&](int idx) -> uint32_t {
-            uint32_t g = goals[idx] & COLORS;
-            if (remove_white && g == COLORS) g = 0;
-            return (uint32_t)board[idx] | (g << 16);
-        };
-        for (int i = threadIdx.x; i < vh + vw; i += blockDim.x) {
-            if (i < vh) ymap[i] = (((y0 - vh / 2 + i) % H + H) % H) * W;
-            else xmap[i - vh] = ((x0 - vw / 2 + (i - vh)) % W + W) % W;
-        }
-        __syncthreads();
-        for (int r = warp; r < vh; r += nwarps) {
-            const int src_row = ymap[r];
-            for (int c = lane; c < vw; c += 32) view[r * vw + c] = packed(src_row + xmap[c]);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int32_t *exits = B.pool_exits + (size_t)B.state[e].level_id * B.max_exits;
-            for (int k = 0; k < B.max_exits; k++) {
-                int idx = exits[k];
-                if (idx < 0) continue;
-                int iy = idx / W, ix = idx - iy * W;
-                int jy = ((iy - y0 + H / 2) % H + H) % H - H / 2 + vh / 2;
-                int jx = ((ix - x0 + W / 2) % W + W) % W - W / 2 + vw / 2;
-                jy = min(max(jy, 0), vh - 1);
-                jx = min(max(jx, 0), vw - 1);
-                view[jy * vw + jx] = packed(idx);
-            }
-        }
-        __syncthreads();
-        if (n_channels == 0) {
-            uint32_t *o = (uint32_t *)obs + (size_t)e * vcells;
-            for (int i = threadIdx.x; i < vcells; i += blockDim.x) o[i] = view[i];
-        } else {
-            // The output is a stream of bits, C per cell (bit k = channel k of the cell),
-            // one byte per bit.  The cells' channel masks are first packed into that bit
-            // stream in shared memory; then every thread expands 16 consecutive stream
-            // bits into one 16-byte store: a funnel shift fetches them, one multiply per
-            // four bits spreads them into 0/1 bytes.
-            const int C = n_channels, nr = n_runs;
-            const int total = vcells * C, nwords = (total + 31) / 32 + 1;
-            for (int i = threadIdx.x; i < nwords; i += blockDim.x) stream[i] = 0;
-            __syncthreads();
-            for (int i = threadIdx.x; i < vcells; i += blockDim.x) {
-                const uint32_t v = view[i];
-                uint32_t m = 0;
-                for (int r = 0; r < nr; r++) m |= ((v >> run_src[r]) & run_mask[r]) << run_dst[r];
-                if (m != 0) {
-                    const int bit = i * C, w = bit >> 5, sh = bit & 31;
-                    atomicOr(stream + w, m << sh);
-                    if (sh + C > 32) atomicOr(stream + w + 1, m >> (32 - sh));
-                }
-            }
-            __syncthreads();
-            uint8_t *o = (uint8_t *)obs + (size_t)e * total;
-            const int head = min(total, (int)((16u - (unsigned)((uintptr_t)o & 15u)) & 15u));
-            const int nchunks = (total - head) >> 4;
-            auto bit_at = [&](int i) -> uint8_t { return (uint8_t)((stream[i >> 5] >> (i & 31)) & 1u); };
-            for (int i = threadIdx.x; i < head; i += blockDim.x) o[i] = bit_at(i);
-            for (int i = head + (nchunks << 4) + threadIdx.x; i < total; i += blockDim.x) o[i] = bit_at(i);
-            uint4 *o16 = (uint4 *)(o + head);
-            for (int c = threadIdx.x; c < nchunks; c += blockDim.x) {
-                const int i0 = head + (c << 4);
-                const uint32_t bits = __funnelshift_r(stream[i0 >> 5], stream[(i0 >> 5) + 1], i0 & 31);
-                uint4 w;
-                w.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
-                w.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
-                w.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
-                w.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
-                o16[c] = w;
-            }
-        }
-        __syncthreads();
-    }
-}
-
 // SimpleSideEffectPenalty cell count (env_wrappers.py:177-213).
 __global__ void __launch_bounds__(GENERIC_THREADS)
 k_side_effect_cells(SlEnvBatch B, const uint16_t *__restrict__ baseline, int32_t *__restrict__ out) {

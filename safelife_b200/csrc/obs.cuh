@@ -1,0 +1,207 @@
+// obs.cuh -- SafeLifeEnv.get_obs by one warp per env.
+//
+// safelife_env.py:105-146 + helper_utils.recenter_view (helper_utils.py:42-75):
+//     full = uint32(board) | (goal colour, white removed) << 16
+//     view[r][c] = full[(y0 - vh/2 + r) mod H][(x0 - vw/2 + c) mod W]      (agent 0 at y0, x0)
+//     every exit cell (iy, ix) of the level: view[clip(...)][clip(...)] = full[iy][ix]
+//     obs[r][c][k] = (view[r][c] >> channels[k]) & 1          (or the raw uint32 view)
+//
+// The writer is shared by the fused epilogue of the step kernels (board slab in
+// shared memory, goals in shared memory or HBM) and by the stand-alone
+// k_get_obs_warp (both in HBM).  Lane c gathers column c of the view row by row
+// -- the source column is a per-lane constant, the source row a warp-uniform
+// counter, so there is no per-cell index arithmetic -- and reduces each cell to
+// its C-bit channel mask in a per-warp staging array; then every lane expands
+// 16 consecutive output bytes (= 16 consecutive bits of the cell-major mask
+// stream) per 16-byte store.  The channel list is applied as runs of consecutive
+// bits (the training list 0-4, 7-11, 25-27, 12-13 is four shift-and-mask steps).
+#pragma once
+#include <stdint.h>
+#include "cells.cuh"
+#include "../../include/safelife_b200.h"
+
+namespace sl {
+
+constexpr int OBS_MAX_RUNS = 32;
+
+// Kernel-side form of SlObsSpec (built on the host by make_obs_params).
+struct ObsParams {
+    void *obs;                 // uint8 [n][vh][vw][C] or uint32 [n][vh][vw] (C == 0)
+    int32_t vh, vw, n_channels, remove_white, n_runs;
+    uint8_t run_src[OBS_MAX_RUNS], run_dst[OBS_MAX_RUNS];
+    uint32_t run_mask[OBS_MAX_RUNS];
+};
+
+inline ObsParams make_obs_params(const SlObsSpec &s) {
+    ObsParams p = {};
+    p.obs = s.obs;
+    p.vh = s.vh;
+    p.vw = s.vw;
+    p.n_channels = s.n_channels;
+    p.remove_white = s.remove_white_goals ? 1 : 0;
+    int nr = 0;
+    for (int k = 0; k < s.n_channels;) {
+        int len = 1;
+        const int c0 = s.channels[k];
+        while (k + len < s.n_channels && s.channels[k + len] == c0 + len) len++;
+        p.run_src[nr] = (uint8_t)c0;
+        p.run_dst[nr] = (uint8_t)k;
+        p.run_mask[nr] = len >= 32 ? 0xffffffffu : ((1u << len) - 1u);
+        nr++;
+        k += len;
+    }
+    p.n_runs = nr;
+    return p;
+}
+
+// Staging bytes of one warp: one mask per view cell (uint16 up to 16 channels,
+// else uint32) plus zero padding that the expansion may read past the last cell.
+__host__ __device__ inline int obs_stage_bytes(int vh, int vw, int n_channels) {
+    if (n_channels == 0) return 0;
+    const int elt = n_channels <= 16 ? 2 : 4;
+    return ((vh * vw + 18) * elt + 15) & ~15;
+}
+
+// spread 16 bits into 16 bytes (bit i -> byte i = 0 / 1)
+__device__ __forceinline__ uint4 expand16(uint32_t bits) {
+    uint4 w;
+    w.x = ((bits & 15u) * 0x00204081u) & 0x01010101u;
+    w.y = (((bits >> 4) & 15u) * 0x00204081u) & 0x01010101u;
+    w.z = (((bits >> 8) & 15u) * 0x00204081u) & 0x01010101u;
+    w.w = (((bits >> 12) & 15u) * 0x00204081u) & 0x01010101u;
+    return w;
+}
+
+// Observation of env `e` by one warp.  `board` / `goals`: the env's planes (shared
+// or global memory; plain loads, so that planes rewritten by this warp's reset
+// are seen).  `stage`: this warp's staging array (ST[vh * vw + 18]); unused when
+// n_channels == 0.  (row0, col0): agent location, row0 < 0 if the level has none.
+template <typename ST>
+__device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
+                                               int row0, int col0, int level_id,
+                                               const uint16_t *board, const uint16_t *goals,
+                                               ST *stage, int lane) {
+    const int H = B.H, W = B.W, vh = O.vh, vw = O.vw, vcells = vh * vw, C = O.n_channels;
+    const bool raw = C == 0;
+    const int y0 = row0 < 0 ? 0 : row0, x0 = row0 < 0 ? 0 : col0;
+    const bool remove_white = O.remove_white != 0;
+    auto full_at = [&](int idx) -> uint32_t {
+        uint32_t g = goals[idx] & COLORS;
+        if (remove_white && g == COLORS) g = 0;
+        return (uint32_t)board[idx] | (g << 16);
+    };
+    // channel runs: bits [src, src + len) of the cell go to bits [dst, dst + len) of the
+    // mask -- one rotate and one and-or each; the first four runs live in registers
+    uint32_t rot[4], sel[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const bool on = i < O.n_runs;
+        rot[i] = on ? (uint32_t)(O.run_dst[i] - O.run_src[i]) & 31u : 0u;
+        sel[i] = on ? O.run_mask[i] << O.run_dst[i] : 0u;
+    }
+    auto mask_of = [&](uint32_t v) -> uint32_t {
+        uint32_t m = 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) m |= __funnelshift_l(v, v, rot[i]) & sel[i];
+        for (int r = 4; r < O.n_runs; r++)
+            m |= __funnelshift_l(v, v, (uint32_t)(O.run_dst[r] - O.run_src[r]) & 31u) &
+                 (O.run_mask[r] << O.run_dst[r]);
+        return m;
+    };
+    uint32_t *out32 = (uint32_t *)O.obs + (size_t)e * vcells;
+    int sy0 = (y0 - vh / 2) % H;
+    if (sy0 < 0) sy0 += H;
+    for (int c0 = 0; c0 < vw; c0 += 32) {
+        const int c = c0 + lane;
+        int sx = (x0 - vw / 2 + c) % W;
+        if (sx < 0) sx += W;
+        int sy = sy0;
+        if (c < vw) {
+#pragma unroll 5
+            for (int r = 0; r < vh; r++) {
+                const uint32_t v = full_at(sy * W + sx);
+                if (raw) out32[r * vw + c] = v;
+                else stage[r * vw + c] = (ST)mask_of(v);
+                sy = sy + 1 == H ? 0 : sy + 1;
+            }
+        }
+    }
+    if (!raw && lane < 18) stage[vcells + lane] = 0;
+    __syncwarp();
+    // exit cells outside the view are clamped onto its perimeter; in index order,
+    // so that the last one wins where two collide (helper_utils.py:64-74)
+    if (lane == 0) {
+        const int32_t *exits = B.pool_exits + (size_t)level_id * B.max_exits;
+        for (int k = 0; k < B.max_exits; k++) {
+            const int idx = exits[k];
+            if (idx < 0) continue;
+            const int iy = idx / W, ix = idx - iy * W;
+            int jy = ((iy - y0 + H / 2) % H + H) % H - H / 2 + vh / 2;
+            int jx = ((ix - x0 + W / 2) % W + W) % W - W / 2 + vw / 2;
+            jy = min(max(jy, 0), vh - 1);
+            jx = min(max(jx, 0), vw - 1);
+            const uint32_t v = full_at(idx);
+            if (raw) out32[jy * vw + jx] = v;
+            else stage[jy * vw + jx] = (ST)mask_of(v);
+        }
+    }
+    __syncwarp();
+    if (raw) return;
+    // expansion: output byte b of the env = bit (b % C) of cell (b / C)
+    const int total = vcells * C;
+    uint8_t *o = (uint8_t *)O.obs + (size_t)e * total;
+    const int head = min(total, (int)((16u - (unsigned)((uintptr_t)o & 15u)) & 15u));
+    const int nchunks = (total - head) >> 4;
+    auto bit_at = [&](int b) -> uint8_t {
+        const int cell = b / C;
+        return (uint8_t)(((uint32_t)stage[cell] >> (b - cell * C)) & 1u);
+    };
+    if (lane < head) o[lane] = bit_at(lane);
+    {
+        const int b = head + (nchunks << 4) + lane;
+        if (b < total) o[b] = bit_at(b);
+    }
+    uint4 *o16 = (uint4 *)(o + head);
+    const int dcell = 512 / C, dk = 512 - dcell * C;     // 32 lanes x 16 bytes per round
+    int cell = (head + 16 * lane) / C, k = (head + 16 * lane) - cell * C;
+    for (int q = lane; q < nchunks; q += 32) {
+        uint32_t bits = (uint32_t)stage[cell] >> k;
+        int nb = C - k, cc = cell + 1;
+        while (nb < 16) {
+            bits |= (uint32_t)stage[cc] << nb;
+            nb += C;
+            cc++;
+        }
+        o16[q] = expand16(bits);
+        cell += dcell;
+        k += dk;
+        if (k >= C) {
+            k -= C;
+            cell++;
+        }
+    }
+}
+
+// Stand-alone SafeLifeEnv.get_obs: one warp per env, planes read from HBM.
+constexpr int OBS_WARPS = 8;
+
+__global__ void __launch_bounds__(OBS_WARPS * 32)
+k_get_obs_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cells = B.H * B.W;
+    unsigned char *stage = smem_raw + (size_t)warp * obs_stage_bytes(O.vh, O.vw, O.n_channels);
+    for (int e = blockIdx.x * OBS_WARPS + warp; e < B.n_envs; e += gridDim.x * OBS_WARPS) {
+        const SlEnvState *st = B.state + e;
+        const uint16_t *board = B.board + (size_t)e * cells, *goals = B.goals + (size_t)e * cells;
+        if (O.n_channels <= 16)
+            warp_write_obs<uint16_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
+                                     (uint16_t *)stage, lane);
+        else
+            warp_write_obs<uint32_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
+                                     (uint32_t *)stage, lane);
+        __syncwarp();
+    }
+}
+
+}  // namespace sl

@@ -31,6 +31,7 @@
 #include <stdlib.h>
 #include "cells.cuh"
 #include "generic_kernels.cuh"
+#include "obs.cuh"
 #include "../../include/safelife_b200.h"
 
 namespace sl {
@@ -593,11 +594,11 @@ __host__ __device__ inline int warp_slab_stride(int cells) {
 __host__ __device__ inline int warp_scratch_bytes(int cells) { return (cells * 2 + 15) & ~15; }
 
 template <class G>
-inline size_t warp_step_smem_bytes(int cells, bool goals_resident) {
+__host__ __device__ inline size_t warp_step_smem_bytes(int cells, bool goals_resident, int obs_stage = 0) {
     return WARP_SMEM_HEAD + WARP_SMEM_TABLE + WARP_SMEM_STATE +
            (goals_resident ? 2 * (size_t)warp_slab_stride(cells)
                            : (size_t)warp_slab_stride(cells) + warp_scratch_bytes(cells)) +
-           2 * G::PAD_CELLS;
+           2 * G::PAD_CELLS + (size_t)WARP_ENVS_PER_CTA * obs_stage;
 }
 
 // The points table of the pool in shared memory when every level shares one
@@ -802,17 +803,65 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, const CtaShare
     return any_reset;
 }
 
+// ---- the same tail for ONE env on its own warp ---------------------------------
+// Lane 0 runs update_exit_colors / reward / done / counters of the env the warp
+// just advanced, then the whole warp resets it if it finished.  No warp waits
+// for another one: the single-pass kernel uses this instead of a CTA barrier
+// followed by phase B on warp 0, and the kernels that write the observation use
+// it because the observation must follow the tail.  Returns true if a reset
+// rewrote the goals slab.
+__device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const CtaShared &cs, int e,
+                                              SlEnvState *st, uint16_t *board, uint16_t *goals,
+                                              int flags, int lane) {
+    int done = 0;
+    __syncwarp();                         // the board cells phase A rewrote
+    if (lane == 0) {
+        const int lvl = st->level_id;
+        bool agent_alive, exited;
+        int dmem;
+        const int row = st->loc_row, col = st->loc_col, pts = st->count_points;
+        const int value = exit_update(board, (const uint16_t *)goals, B.W, row, col, pts, *st,
+                                      B.pool_exits + (size_t)lvl * B.max_exits,
+                                      cs.table ? cs.table : B.pool_table + (size_t)lvl * 72,
+                                      &agent_alive, &exited, &dmem);
+        done = finish_step(B, e, *st, row, col, value, agent_alive, exited, st->static_goals,
+                           pts + dmem) ? 1 : 0;
+    }
+    done = __shfl_sync(FULL, done, 0);
+    bool reset = false;
+    if (done && (flags & SL_STEP_AUTO_RESET)) {
+        warp_reset_env(B, st, board, goals, lane);
+        reset = true;
+    }
+    __syncwarp();
+    return reset;
+}
+
+// The observation of one env as the step leaves it (see obs.cuh); out of line so
+// that its registers do not weigh on the stencil.
+__device__ __noinline__ void step_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
+                                            const SlEnvState *st, const uint16_t *board,
+                                            const uint16_t *goals, unsigned char *stage, int lane) {
+    if (O.n_channels <= 16)
+        warp_write_obs<uint16_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
+                                 (uint16_t *)stage, lane);
+    else
+        warp_write_obs<uint32_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
+                                 (uint32_t *)stage, lane);
+}
+
 // SafeLifeEnv.step, one warp per env (safelife_env.py:148-201): single-pass
-// variant, one CTA per group of 8 envs.
-//   phase A  warp w: execute_actions and advance_board of env w on bit planes
-//   phase B  warp 0, lane w: exit colours, reward / done, counters, auto-reset
+// variant, one CTA per group of 8 envs.  Warp w runs the whole step of env w --
+// execute_actions and advance_board on bit planes (phase A), the scalar tail on
+// lane 0, the reset of a finished env, and (OBS) the observation -- without
+// waiting for the other warps; one CTA barrier before the bulk stores.
 // The board slabs (and the goal slabs, when resident) arrive on separate
 // mbarriers, so the stencil starts while the goals are still in flight.
 // Ragged / unaligned batches fall back to scalar copies instead of bulk copies.
-template <class G, bool GR>
+template <class G, bool GR, bool OBS>
 __global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 4 : 2)
-k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
-                int bulk_ok, int flags, int first_group) {
+k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
+                const uint8_t *__restrict__ actions, int bulk_ok, int flags, int first_group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -859,34 +908,37 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
     SL_TRACE_MARK(threadIdx.x == 0, 1);
 
     bool goals_dirty = false;
-    if (warp < nenv)
-        goals_dirty = step_phase_a<G, GR>(B, cs, G(B.H, B.W, lane), sstate + warp, sboard + warp * cells,
-                                          GR ? sgoals + warp * cells : ggoals + (size_t)warp * cells,
+    if (warp < nenv) {
+        SlEnvState *st = sstate + warp;
+        uint16_t *bd = sboard + warp * cells;
+        uint16_t *gl = GR ? sgoals + warp * cells : ggoals + (size_t)warp * cells;
+        goals_dirty = step_phase_a<G, GR>(B, cs, G(B.H, B.W, lane), st, bd, gl,
                                           GR && bulk ? bar + 1 : nullptr, action);
-    else if (GR && bulk) mbar_wait(bar + 1, 0);
+        SL_TRACE_MARK(threadIdx.x == 0, 2);
+        goals_dirty |= step_tail_env(B, cs, e0 + warp, st, bd, gl, flags, lane);
+        SL_TRACE_MARK(threadIdx.x == 0, 3);
+        if (OBS) {
+            const int stage_bytes = obs_stage_bytes(O.vh, O.vw, O.n_channels);
+            unsigned char *stage = smem_raw + warp_step_smem_bytes<G>(cells, GR) + warp * stage_bytes;
+            step_write_obs(B, O, e0 + warp, st, bd, gl, stage, lane);
+        }
+    } else if (GR && bulk) {
+        mbar_wait(bar + 1, 0);
+    }
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
-    SL_TRACE_MARK(threadIdx.x == 0, 2);
-    int any_goals_dirty = __syncthreads_or(goals_dirty);
-    if (warp != 0) return;
-    SL_TRACE_MARK(threadIdx.x == 0, 3);
-
-    any_goals_dirty |= step_phase_b(B, cs, e0, nenv, sstate, sboard, GR ? sgoals : ggoals, flags, lane);
-    fence_async_smem();
-    __syncwarp();
     SL_TRACE_MARK(threadIdx.x == 0, 4);
+    const int any_goals_dirty = __syncthreads_or(goals_dirty);
     if (bulk) {
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             bulk_store(gboard, sboard, group_bytes);
             if (GR && any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
             bulk_store(gstate, sstate, state_bytes);
             bulk_commit_and_wait_read();
         }
     } else {
-        for (int i = lane; i < (group_bytes >> 1); i += 32) gboard[i] = sboard[i];
-        if (GR && any_goals_dirty)
-            for (int i = lane; i < (group_bytes >> 1); i += 32) ggoals[i] = sgoals[i];
-        for (int i = lane; i < (state_bytes >> 1); i += 32)
-            ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
+        copy_slabs(gboard, sboard, group_bytes);
+        if (GR && any_goals_dirty) copy_slabs(ggoals, sgoals, group_bytes);
+        copy_slabs(gstate, sstate, state_bytes);
     }
     SL_TRACE_MARK(threadIdx.x == 0, 5);
 }
@@ -910,15 +962,20 @@ __host__ __device__ inline int pipe_stage_bytes(int cells, bool goals_resident) 
     return WARP_SMEM_STATE + (goals_resident ? 2 : 1) * warp_slab_stride(cells);
 }
 
-inline size_t pipe_smem_bytes(int cells, int stages, bool goals_resident) {
+__host__ __device__ inline size_t pipe_smem_bytes(int cells, int stages, bool goals_resident,
+                                                  int obs_stage = 0) {
     return PIPE_SMEM_HEAD + WARP_SMEM_TABLE + stages * (size_t)pipe_stage_bytes(cells, goals_resident) +
-           (goals_resident ? 0 : warp_scratch_bytes(cells)) + 2 * Narrow::PAD_CELLS;
+           (goals_resident ? 0 : warp_scratch_bytes(cells)) + 2 * Narrow::PAD_CELLS +
+           (size_t)WARP_ENVS_PER_CTA * obs_stage;
 }
 
-template <int STAGES, int CTAS_PER_SM, bool GR>
+// OBS: every stencil warp also runs the tail of its env and writes its
+// observation (step_tail_env, step_write_obs) before it reports the stage
+// finished; the scalar warp is then only the bulk-copy engine's driver.
+template <int STAGES, int CTAS_PER_SM, bool GR, bool OBS>
 __global__ void __launch_bounds__(PIPE_THREADS, CTAS_PER_SM)
-k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict__ actions,
-                int flags, int n_groups) {
+k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
+                const uint8_t *__restrict__ actions, int flags, int n_groups) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -966,8 +1023,9 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
             mbar_wait_parked(fin + s, parity, PIPE_PARK_NS);
             const int e0 = g * WARP_ENVS_PER_CTA;
             bool goals_dirty = GR && lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
-            goals_dirty |= step_phase_b(B, cs, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
-                                        GR ? stage_goals(s) : B.goals + (size_t)e0 * cells, flags, lane);
+            if (!OBS)
+                goals_dirty |= step_phase_b(B, cs, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
+                                            GR ? stage_goals(s) : B.goals + (size_t)e0 * cells, flags, lane);
             const bool any_dirty = __any_sync(FULL, goals_dirty);
             fence_async_smem();
             __syncwarp();
@@ -990,6 +1048,8 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
         const Narrow t(B.H, B.W, lane);                 // row masks, neighbour lanes: once per warp
         const int env_bytes = cells * 2;
         unsigned char *my = stages + warp * env_bytes;  // this warp's slot inside a stage
+        unsigned char *obs_stage = smem_raw + pipe_smem_bytes(cells, STAGES, GR) +
+                                   (OBS ? warp * obs_stage_bytes(O.vh, O.vw, O.n_channels) : 0);
         int s = 0, parity = 0;
         int next_action = first < n_groups ? actions[(size_t)first * WARP_ENVS_PER_CTA + warp] : 0;
         for (int g = first; g < n_groups; g += stride) {
@@ -999,11 +1059,15 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const uint8_t *__restrict_
                 next_action = actions[(size_t)(g + stride) * WARP_ENVS_PER_CTA + warp];
             unsigned char *stage = my + s * stage_bytes;
             mbar_wait_parked(full + s, parity, PIPE_PARK_NS);
-            const bool gd = step_phase_a<Narrow, GR>(
-                B, cs, t, (SlEnvState *)(stages + s * stage_bytes) + warp,
-                (uint16_t *)(stage + WARP_SMEM_STATE),
-                GR ? (uint16_t *)(stage + WARP_SMEM_STATE + warp_slab_stride(cells)) : B.goals + e * cells,
-                nullptr, action);
+            SlEnvState *st = (SlEnvState *)(stages + s * stage_bytes) + warp;
+            uint16_t *bd = (uint16_t *)(stage + WARP_SMEM_STATE);
+            uint16_t *gl = GR ? (uint16_t *)(stage + WARP_SMEM_STATE + warp_slab_stride(cells))
+                              : B.goals + e * cells;
+            bool gd = step_phase_a<Narrow, GR>(B, cs, t, st, bd, gl, nullptr, action);
+            if (OBS) {
+                gd |= step_tail_env(B, cs, (int)e, st, bd, gl, flags, lane);
+                step_write_obs(B, O, (int)e, st, bd, gl, obs_stage, lane);
+            }
             if (GR && lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
             fence_async_smem();
             __syncwarp();
@@ -1030,20 +1094,24 @@ inline int env_knob(const char *name, int fallback) {
 // The shapes compiled in; `shape` picks one (tuning knob SAFELIFE_B200_PIPE_SHAPE).
 #define SL_PIPE_SHAPES(X) X(2, 4, true) X(3, 3, true) X(3, 4, false) X(4, 4, false) X(5, 3, false) X(6, 3, false)
 
-inline bool pipe_shape_fits(int cells, int stages, int ctas, bool gr, int smem_per_sm) {
-    return ctas * (pipe_smem_bytes(cells, stages, gr) + 1024) <= (size_t)smem_per_sm;
+inline bool pipe_shape_fits(int cells, int stages, int ctas, bool gr, int smem_per_sm,
+                            int obs_stage = 0) {
+    return ctas * (pipe_smem_bytes(cells, stages, gr, obs_stage) + 1024) <= (size_t)smem_per_sm;
 }
 
-// What sl_env_step launches for a batch on the warp path.
+// What sl_env_step / sl_env_step_obs launches for a batch on the warp path.
 struct StepPlan {
-    bool narrow, goals_resident;
+    bool narrow, goals_resident, obs;
     int bulk_ok;
+    int obs_stage;                  // staging bytes per warp of the fused observation (0: none)
     int pipe_stages, pipe_ctas;     // 0, 0: no pipelined launch
     int pipe_grid, piped_groups;    // persistent CTAs and the groups they cover
     int single_groups;              // groups left to the single-pass kernel (one CTA each)
 };
 
-inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_per_sm) {
+// O: the observation the step writes, or nullptr.
+inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, int sm_count,
+                                   int smem_per_sm) {
     StepPlan p = {};
     const int cells = B.H * B.W;
     const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
@@ -1052,6 +1120,8 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_p
     static const bool in_place_ok = env_knob("SAFELIFE_B200_GOALS_IN_PLACE", 1) != 0;
     p.goals_resident = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok);
     p.narrow = warp_kernel_is_narrow(B.H, B.W);
+    p.obs = O != nullptr;
+    p.obs_stage = O ? obs_stage_bytes(O->vh, O->vw, O->n_channels) : 0;
     p.single_groups = groups;
     if (!p.narrow) return p;
     // pipelining pays once a CTA slot sees more than one group
@@ -1060,11 +1130,12 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_p
     bool known = false;
 #define SL_KNOWN_SHAPE(S, C, R)                                                        \
     known |= R == p.goals_resident && want == S * 10 + C &&                            \
-             pipe_shape_fits(cells, S, C, R, smem_per_sm);
+             pipe_shape_fits(cells, S, C, R, smem_per_sm, p.obs_stage);
     SL_PIPE_SHAPES(SL_KNOWN_SHAPE)
 #undef SL_KNOWN_SHAPE
-    if (!known) want = p.goals_resident ? 24 : 34;    // a large board: the smallest shape
+    if (!known) want = p.goals_resident ? 24 : 34;    // a large board or view: the smallest shape
     const int stages = want / 10, ctas = want % 10;
+    if (!pipe_shape_fits(cells, stages, 1, p.goals_resident, smem_per_sm, p.obs_stage)) return p;
     // (measured crossover: the single-pass kernel wins up to about two waves of its 4 CTAs
     // per SM -- 8192 envs: 18.4 vs 19.2 us, 16384 envs: 27.2 vs 25.6 us)
     static const int min_waves = env_knob("SAFELIFE_B200_PIPE_MIN_WAVES", 2);   // tuning knob
@@ -1080,40 +1151,55 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, int sm_count, int smem_p
     return p;
 }
 
-inline void launch_env_step_warp(const SlEnvBatch &B, const uint8_t *actions, int flags,
-                                 int sm_count, int smem_per_sm, cudaStream_t st) {
-    const StepPlan p = plan_env_step_warp(B, sm_count, smem_per_sm);
+// Launches the plan.  `prep(kernel, dynamic shared memory bytes)` is called before
+// each launch (the ABI layer opts the kernel in to large shared memory there) and
+// returns non-zero to abort.
+template <class Prep>
+inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const uint8_t *actions,
+                                int flags, const StepPlan &p, cudaStream_t st, Prep prep) {
     const int cells = B.H * B.W;
     const int threads = WARP_ENVS_PER_CTA * 32;
+    static const ObsParams no_obs = {};
+    const ObsParams &obs = O ? *O : no_obs;
+    int rc = 0;
+#define SL_LAUNCH_WARP(G, R, OB)                                                               \
+    do {                                                                                       \
+        const size_t smem = warp_step_smem_bytes<G>(cells, R, p.obs_stage);                    \
+        rc = prep((const void *)k_env_step_warp<G, R, OB>, smem);                              \
+        if (rc) return rc;                                                                     \
+        k_env_step_warp<G, R, OB><<<p.single_groups, threads, smem, st>>>(                     \
+            B, obs, actions, p.bulk_ok, flags, p.piped_groups);                                \
+    } while (0)
+#define SL_LAUNCH_WARP_G(G)                                                                    \
+    do {                                                                                       \
+        if (p.goals_resident) {                                                                \
+            if (p.obs) SL_LAUNCH_WARP(G, true, true); else SL_LAUNCH_WARP(G, true, false);     \
+        } else {                                                                               \
+            if (p.obs) SL_LAUNCH_WARP(G, false, true); else SL_LAUNCH_WARP(G, false, false);   \
+        }                                                                                      \
+    } while (0)
     if (!p.narrow) {
-        if (p.goals_resident)
-            k_env_step_warp<Wide, true><<<p.single_groups, threads,
-                                          warp_step_smem_bytes<Wide>(cells, true), st>>>(
-                B, actions, p.bulk_ok, flags, 0);
-        else
-            k_env_step_warp<Wide, false><<<p.single_groups, threads,
-                                           warp_step_smem_bytes<Wide>(cells, false), st>>>(
-                B, actions, p.bulk_ok, flags, 0);
-        return;
+        SL_LAUNCH_WARP_G(Wide);
+        return 0;
     }
     if (p.piped_groups > 0) {
-#define SL_LAUNCH_SHAPE(S, C, R)                                                               \
-        if (R == p.goals_resident && S == p.pipe_stages && C == p.pipe_ctas)                   \
-            k_env_step_pipe<S, C, R><<<p.pipe_grid, PIPE_THREADS, pipe_smem_bytes(cells, S, R), st>>>( \
-                B, actions, flags, p.piped_groups);
+#define SL_LAUNCH_SHAPE_OB(S, C, R, OB)                                                        \
+        if (R == p.goals_resident && S == p.pipe_stages && C == p.pipe_ctas && OB == p.obs) {  \
+            const size_t smem = pipe_smem_bytes(cells, S, R, p.obs_stage);                     \
+            rc = prep((const void *)k_env_step_pipe<S, C, R, OB>, smem);                       \
+            if (rc) return rc;                                                                 \
+            k_env_step_pipe<S, C, R, OB><<<p.pipe_grid, PIPE_THREADS, smem, st>>>(             \
+                B, obs, actions, flags, p.piped_groups);                                       \
+        }
+#define SL_LAUNCH_SHAPE(S, C, R) SL_LAUNCH_SHAPE_OB(S, C, R, false) SL_LAUNCH_SHAPE_OB(S, C, R, true)
         SL_PIPE_SHAPES(SL_LAUNCH_SHAPE)
 #undef SL_LAUNCH_SHAPE
+#undef SL_LAUNCH_SHAPE_OB
     }
-    if (p.single_groups > 0) {
-        if (p.goals_resident)
-            k_env_step_warp<Narrow, true><<<p.single_groups, threads,
-                                            warp_step_smem_bytes<Narrow>(cells, true), st>>>(
-                B, actions, p.bulk_ok, flags, p.piped_groups);
-        else
-            k_env_step_warp<Narrow, false><<<p.single_groups, threads,
-                                             warp_step_smem_bytes<Narrow>(cells, false), st>>>(
-                B, actions, p.bulk_ok, flags, p.piped_groups);
-    }
+    if (p.single_groups > 0) SL_LAUNCH_WARP_G(Narrow);
+#undef SL_LAUNCH_WARP_G
+#undef SL_LAUNCH_WARP
+    return 0;
 }
 
 // ------------------------------------------------------------------------

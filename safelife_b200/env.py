@@ -15,11 +15,24 @@ Discrete(9) and ``observation_space`` a Box of the per-env observation shape.
 
 Differences that come with batching, all deliberate:
   * `levels` is a list of level dicts / a path (see safelife_b200.levels), held
-    on the device as a pool; env e starts on level e % L and, when an episode
-    ends and ``auto_reset`` is on, moves to level (current + N) % L -- the
-    batched form of ``BaseAlgo.act_on_envs`` calling ``env.reset()`` on done
-    (training/base_algo.py:231-236).  The returned `obs` of a finished env is
-    the first observation of its next episode, as in that loop.
+    on the device as a pool of L levels; env e starts on level
+    (env_offset + e) % L and, when an episode ends, moves on by `level_stride`
+    (mod L) -- the batched form of ``BaseAlgo.act_on_envs`` calling
+    ``env.reset()`` on done (training/base_algo.py:231-236) with a level
+    iterator behind it.  The stride is the smallest number >= total_envs % L
+    that is coprime to L, so every env walks through the whole pool whatever
+    the batch size (a stride of N % L would be 0 for 4096 envs on 1024 levels).
+    `update_pool` swaps fresh levels into a live env (level_iterator.py:200-266
+    streams new procgen levels into every reset).  With ``auto_reset`` the
+    returned `obs` of a finished env is the first observation of its next
+    episode, as in that loop.
+  * outputs are double-buffered: the tensors returned by step t (obs, reward,
+    done, info['times_up'], info['episode']['success']) stay valid through
+    step t+1 and are overwritten by step t+2; ``step(..., obs_out=buf)`` writes
+    the observation into caller storage (a rollout buffer) instead.
+    info['board'/'goals'/'agent_locs'] and info['episode']['length'/'reward']
+    are live views of the device state, like ``info['board'] is game.board`` in
+    the reference.
   * each env owns a PCG64 stream (uint64[4]); the reference swaps a global
     generator in and out per game (safelife/random.py:19-32).
   * `info` holds batched tensors: board, goals, agent_locs, times_up, and
@@ -34,6 +47,7 @@ Differences that come with batching, all deliberate:
     the episode ends (safelife_env.py:176-187).
 """
 import ctypes
+import math
 
 import numpy as np
 import torch
@@ -75,6 +89,20 @@ def seed_rng_states(seed, n):
     return out
 
 
+def coprime_stride(n_envs, n_levels):
+    """
+    How far an env moves through the pool when its episode ends: the smallest
+    s >= n_envs % n_levels (at least 1) with gcd(s, n_levels) = 1, so that env e
+    visits every level -- (e + k * s) % L is a bijection of k mod L.
+    """
+    if n_levels <= 1:
+        return 0
+    s = n_envs % n_levels or 1
+    while math.gcd(s, n_levels) != 1:
+        s += 1
+    return s % n_levels
+
+
 class _TensorTable(dict):
     """The env's device tensors by name; per-env scalars are views into `state`."""
 
@@ -105,7 +133,8 @@ class BatchedSafeLifeEnv(object):
     goals_in_place = None
 
     def __init__(self, levels, num_envs, device=None, seed=None, auto_reset=True,
-                 min_performance_fraction=1.0, kernel=0, **kwargs):
+                 min_performance_fraction=1.0, kernel=0, env_offset=0, total_envs=None,
+                 level_stride=None, **kwargs):
         for key, val in kwargs.items():
             if key.startswith("_") or not hasattr(type(self), key):
                 raise ValueError("Unrecognized parameter: '%s'" % (key,))
@@ -164,24 +193,67 @@ class BatchedSafeLifeEnv(object):
                 "init_points": state[:, 18], "required": state[:, 19],
                 "count_points": state[:, 20],
             }
-            self._views["level_id"].copy_((torch.arange(N, dtype=torch.int64) % len(p)).to(torch.int32))
+            self.env_offset = int(env_offset)
+            self.total_envs = int(total_envs) if total_envs is not None else N
+            self.level_stride = (coprime_stride(self.total_envs, len(p)) if level_stride is None
+                                 else int(level_stride) % len(p))
+            first = (torch.arange(N, dtype=torch.int64) + self.env_offset) % len(p)
+            self._views["level_id"].copy_(first.to(torch.int32))
             self._views["rng"].copy_(_as_i64(seed_rng_states(seed, N)))
+            obs_shape = (N,) + self.view_shape
             if self.output_channels is None:
-                self._obs = z((N,) + self.view_shape, torch.int32)
-                self._channels = None
+                obs_dtype = torch.int32
             else:
-                self._obs = z((N,) + self.view_shape + (len(self.output_channels),), torch.uint8)
-                self._channels = torch.tensor(self.output_channels, dtype=torch.int32, device=dev)
+                obs_shape, obs_dtype = obs_shape + (len(self.output_channels),), torch.uint8
+            # per-step outputs, double-buffered: step t writes set t & 1; observations
+            # have a ring of their own (step, reset and get_obs all produce one)
+            names = ("reward", "done", "success", "times_up")
+            self._out = [{k: self._t[k] for k in names},
+                         {k: torch.zeros_like(self._t[k]) for k in names}]
+            self._obs_bufs = [z(obs_shape, obs_dtype), z(obs_shape, obs_dtype)]
             self._actions = z((N,), torch.uint8)
-        self._batch = _lib.SlEnvBatch(
-            n_envs=N, H=H, W=W, max_exits=p.max_exits, time_limit=int(self.time_limit),
-            n_levels=len(p), level_stride=N % len(p), pool_flags=self._pool_flags(),
-            **{k: t.data_ptr() for k, t in self._t.items()},
-            **{k: t.data_ptr() for k, t in self._pool_t.items()})
-        self._batch_ref = ctypes.byref(self._batch)
+        flags = self._pool_flags()
+        self._batches, self._batch_refs, self._obs_specs = [], [], []
+        for out in self._out:
+            ptrs = {k: t.data_ptr() for k, t in self._t.items()}
+            ptrs.update({k: out[k].data_ptr() for k in ("reward", "done", "success", "times_up")})
+            b = _lib.SlEnvBatch(
+                n_envs=N, H=H, W=W, max_exits=p.max_exits, time_limit=int(self.time_limit),
+                n_levels=len(p), level_stride=self.level_stride, pool_flags=flags, **ptrs,
+                **{k: t.data_ptr() for k, t in self._pool_t.items()})
+            self._batches.append(b)
+            self._batch_refs.append(ctypes.byref(b))
+        self._obs_specs = [self._make_obs_spec(o) for o in self._obs_bufs]
+        self._flip = self._obs_i = 0
+        self._batch, self._batch_ref = self._batches[0], self._batch_refs[0]
         self._has_reset = False
         # `_t` also answers for the named views of the state record
         self._t = _TensorTable(self._t, self._views)
+
+    def _make_obs_spec(self, obs):
+        spec = _lib.SlObsSpec(obs=obs.data_ptr(), vh=self.view_shape[0], vw=self.view_shape[1],
+                              n_channels=0 if self.output_channels is None else len(self.output_channels),
+                              remove_white_goals=int(bool(self.remove_white_goals)))
+        for k, c in enumerate(self.output_channels or ()):
+            spec.channels[k] = c
+        return spec
+
+    def _next_outputs(self):
+        """Flip to the other output set; returns (batch ref, outputs)."""
+        self._flip ^= 1
+        i = self._flip
+        self._batch, self._batch_ref = self._batches[i], self._batch_refs[i]
+        out = self._out[i]
+        for k, v in out.items():
+            dict.__setitem__(self._t, k, v)
+        return self._batch_ref, out
+
+    def _next_obs(self, out=None):
+        """(obs spec, obs tensor) of the next observation: ring buffer or caller storage."""
+        if out is not None:
+            return self._make_obs_spec(self._check_obs_out(out)), out
+        self._obs_i ^= 1
+        return self._obs_specs[self._obs_i], self._obs_bufs[self._obs_i]
 
     def _pool_flags(self):
         """
@@ -192,15 +264,23 @@ class BatchedSafeLifeEnv(object):
         p, flags = self.pool, 0
         if (p.table == p.table[0]).all():
             flags |= _lib.SL_POOL_UNIFORM_TABLE
-        goals = self._pool_t["pool_goals"]
+        if self.goals_in_place is None:
+            static = self._goals_static(self._pool_t["pool_goals"])
+        else:
+            static = bool(self.goals_in_place)
+        if static:
+            flags |= _lib.SL_POOL_STATIC_GOALS
+        return flags
+
+    def _goals_static(self, goals):
+        """True if every goals plane is a fixed point of advance_board and has no spawner."""
+        goals = goals.contiguous()
         nxt = torch.empty_like(goals)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.sl_advance_board(
-                goals.data_ptr(), nxt.data_ptr(), len(p), p.H, p.W, 0.0, 1, None, self._stream()))
-        static = bool((nxt == goals).all()) and not bool((goals & 128).any())
-        if static if self.goals_in_place is None else self.goals_in_place:
-            flags |= _lib.SL_POOL_STATIC_GOALS
-        return flags
+                goals.data_ptr(), nxt.data_ptr(), goals.shape[0], self.pool.H, self.pool.W, 0.0, 1,
+                None, self._stream()))
+        return bool((nxt == goals).all()) and not bool((goals & 128).any())
 
     # ------------------------------------------------------------ tensors
     @property
@@ -249,20 +329,33 @@ class BatchedSafeLifeEnv(object):
             self._scored = None
             return self.get_obs()
 
-    def get_obs(self):
-        """SafeLifeEnv.get_obs (safelife_env.py:105-146) for all envs."""
-        with torch.cuda.device(self.device):
-            nch = 0 if self._channels is None else len(self.output_channels)
-            _lib.check(self._lib.sl_get_obs(
-                self._batch_ref, self._obs.data_ptr(), self.view_shape[0], self.view_shape[1],
-                self._channels.data_ptr() if nch else None, nch,
-                int(bool(self.remove_white_goals)), self._stream()))
-        return self._obs if self._channels is not None else self._obs.view(torch.uint32)
+    def _view_of(self, obs):
+        return obs if self.output_channels is not None else obs.view(torch.uint32)
 
-    def step_physics(self, actions, auto_reset=False):
+    def get_obs(self, out=None):
         """
-        The step path alone (no observation): safelife_env.py:148-175, plus the
-        reset of finished envs in the same launch when `auto_reset` is set.
+        SafeLifeEnv.get_obs (safelife_env.py:105-146) for all envs; written into
+        `out` if given, else into the next buffer of the output ring.
+        """
+        spec, out = self._next_obs(out)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_get_obs_spec(self._batch_ref, ctypes.byref(spec), self._stream()))
+        return self._view_of(out)
+
+    def _check_obs_out(self, out):
+        want = self._obs_bufs[0]
+        if out.shape != want.shape or out.device != want.device or not out.is_contiguous() or \
+                out.element_size() != want.element_size():
+            raise ValueError("obs_out must be a contiguous %s tensor of shape %s on %s" % (
+                want.dtype, tuple(want.shape), want.device))
+        return out
+
+    def step_physics(self, actions, auto_reset=False, obs_out=False):
+        """
+        The step path (safelife_env.py:148-175), plus the reset of finished envs in
+        the same launch when `auto_reset` is set.  obs_out=False: no observation;
+        None: the observation is written by the same launch into the output ring;
+        a tensor: into that tensor.  Returns the output set of this step.
         """
         if not torch.is_tensor(actions):
             a = np.asarray(actions)
@@ -274,18 +367,25 @@ class BatchedSafeLifeEnv(object):
         if actions.shape != (self.num_envs,):
             raise ValueError("actions must have shape (num_envs,)")
         self._actions.copy_(actions, non_blocking=True)
+        bref, out = self._next_outputs()
+        spec, obs = (None, None) if obs_out is False else self._next_obs(obs_out)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.sl_env_step(
-                self._batch_ref, self._actions.data_ptr(), self.kernel,
-                _lib.SL_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
+            _lib.check(self._lib.sl_env_step_obs(
+                bref, self._actions.data_ptr(), None if spec is None else ctypes.byref(spec),
+                self.kernel, _lib.SL_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
+        return dict(out, obs=obs)
 
-    def step_plan(self):
-        """(description, launches per step) of what sl_env_step runs for this batch."""
-        buf = ctypes.create_string_buffer(256)
+    def step_plan(self, obs=False):
+        """
+        (description, launches per step) of what sl_env_step (obs=False) or
+        sl_env_step_obs (obs=True: step() with its observation) runs for this batch.
+        """
+        buf = ctypes.create_string_buffer(320)
         n = ctypes.c_int(0)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.sl_env_step_plan(self._batch_ref, self.kernel, buf, 256,
-                                                  ctypes.byref(n)))
+            _lib.check(self._lib.sl_env_step_obs_plan(
+                self._batch_ref, ctypes.byref(self._obs_specs[0]) if obs else None, self.kernel,
+                buf, 320, ctypes.byref(n)))
         return buf.value.decode(), int(n.value)
 
     def enable_host_io(self):
@@ -339,27 +439,33 @@ class BatchedSafeLifeEnv(object):
             _lib.check(status)
         return h["reward"], h["done"]
 
-    def step(self, actions):
+    def step(self, actions, obs_out=None):
+        """
+        SafeLifeEnv.step for every env: ONE launch writes the new state, reward / done
+        and the observation (sl_env_step_obs).  Returns (obs, reward f32 [N], done bool
+        [N], info); see the module docstring for how long the tensors stay valid.
+        """
         assert self._has_reset, "Game state is not initialized."
         # side effects are scored on the final board, so the reset of finished
         # envs waits until after the score (safelife_env.py:176-187)
         score = bool(self.should_calculate_side_effects)
-        self.step_physics(actions, self.auto_reset and not score)
+        out = self.step_physics(actions, self.auto_reset and not score, obs_out=obs_out)
         t = self._t
-        reward, done = t["reward"], t["done"].bool()
+        obs = self._view_of(out["obs"])
+        reward, done = out["reward"], out["done"].view(torch.bool)
         info = {
-            "times_up": t["times_up"].bool(),
+            "times_up": out["times_up"].view(torch.bool),
             "episode": {"length": t["ep_length"], "reward": t["ep_reward"],
-                        "success": t["success"].bool()},
+                        "success": out["success"].view(torch.bool)},
         }
         if score:
             side_effects = self._episode_side_effects()
             if side_effects:
                 info["episode"]["side_effects"] = side_effects
             if self.auto_reset:
-                self.reset_done()
+                obs = self.reset_done(out=obs_out)
         info["board"], info["goals"], info["agent_locs"] = self.board, self.goals, self.agent_locs
-        return self.get_obs(), reward, done, info
+        return obs, reward, done, info
 
     def _episode_side_effects(self):
         """
@@ -385,7 +491,7 @@ class BatchedSafeLifeEnv(object):
                 scores["total"] = total.tolist()
         return out
 
-    def reset_done(self, mask=None):
+    def reset_done(self, mask=None, out=None):
         """
         Reset the envs whose mask byte is set (default: the `done` flags of the last
         step) onto their next level, as BaseAlgo.act_on_envs does after a done
@@ -398,7 +504,74 @@ class BatchedSafeLifeEnv(object):
             _lib.check(self._lib.sl_env_reset(
                 self._batch_ref, mask.data_ptr(), None,
                 _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS, self._stream()))
-        return self.get_obs()
+        return self.get_obs(out)
+
+    # ------------------------------------------------------------ level supply
+    def levels_in_use(self):
+        """Pool slots that some env is playing right now (sorted numpy array; syncs)."""
+        return torch.unique(self._t["level_id"]).cpu().numpy()
+
+    def update_pool(self, slots, levels, force=False):
+        """
+        Replace the pool entries `slots` by `levels` (level dicts, same board shape)
+        while the env is live: the batched counterpart of a level iterator that
+        hands a fresh procgen level to every reset (safelife_env.py:203-218,
+        level_iterator.py:200-266) -- a host worker pool generates levels and
+        streams them into the slots the envs will reach next.  Stream-ordered
+        with the steps; takes effect from the next reset onto those slots.  Slots
+        being played are refused unless `force` (an env keeps its board, but
+        levels with more than two exits or their own points table read both from
+        the pool during the episode).
+        """
+        slots = np.asarray(slots, dtype=np.int64).ravel()
+        if len(slots) != len(levels):
+            raise ValueError("one level per slot")
+        if len(slots) == 0:
+            return
+        L = len(self.pool)
+        if slots.min() < 0 or slots.max() >= L or len(np.unique(slots)) != len(slots):
+            raise ValueError("slots must be distinct pool indices")
+        if not force and np.isin(slots, self.levels_in_use()).any():
+            raise ValueError("some of these slots are being played (see levels_in_use)")
+        frac = getattr(self.pool, "min_performance_fraction", 1.0)
+        new = LevelPool(levels, frac)
+        p = self.pool
+        if (new.H, new.W) != (p.H, p.W):
+            raise ValueError("new levels must have the pool's board shape")
+        if new.max_exits > p.max_exits:
+            raise ValueError("new levels have %d exits, the pool was built for %d" % (
+                new.max_exits, p.max_exits))
+        exits = np.full((len(slots), p.max_exits), -1, dtype=np.int32)
+        exits[:, :new.max_exits] = new.exits
+        host = {"pool_board": new.board, "pool_goals": new.goals, "pool_loc": new.loc,
+                "pool_table": new.table, "pool_exits": exits, "pool_init_points": new.init_points,
+                "pool_required": new.required, "pool_spawn_thr": new.spawn_thr}
+        for name, arr in (("board", new.board), ("goals", new.goals), ("loc", new.loc),
+                          ("table", new.table), ("exits", exits), ("init_points", new.init_points),
+                          ("required", new.required), ("spawn_thr", new.spawn_thr)):
+            getattr(p, name)[slots] = arr
+        for i, lv in zip(slots, levels):
+            p.levels[int(i)] = lv
+        idx = torch.from_numpy(slots).to(self.device)
+        with torch.cuda.device(self.device):
+            for name, arr in host.items():
+                if arr.dtype == np.uint16:
+                    src = _as_i16(arr)
+                elif arr.dtype == np.uint64:
+                    src = _as_i64(arr)
+                else:
+                    src = torch.from_numpy(np.ascontiguousarray(arr))
+                self._pool_t[name].index_copy_(0, idx, src.to(self.device))
+            # the promises made for the old pool must still hold (include/safelife_b200.h)
+            flags = self._batch.pool_flags
+            if not (p.table == p.table[0]).all():
+                flags &= ~_lib.SL_POOL_UNIFORM_TABLE
+            if flags & _lib.SL_POOL_STATIC_GOALS and not self._goals_static(self._pool_t["pool_goals"][idx]):
+                flags &= ~_lib.SL_POOL_STATIC_GOALS
+            for b in self._batches:
+                b.pool_flags = flags
+            if getattr(self, "_batch_host", None) is not None:
+                self._batch_host.pool_flags = flags
 
     def side_effect_cells(self, baseline):
         """

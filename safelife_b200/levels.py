@@ -148,7 +148,8 @@ class LevelPool(object):
                 raise ValueError("all levels of a pool must share one board shape")
         if shape[0] < 3 or shape[1] < 3:
             raise ValueError("Board must be at least 3x3.")
-        self.levels = levels
+        self.levels = list(levels)
+        self.min_performance_fraction = float(min_performance_fraction)
         self.H, self.W = shape
         n = len(levels)
         self.board = np.stack([np.asarray(lv["board"], dtype=np.uint16) for lv in levels])

@@ -27,7 +27,7 @@ def shard_range(n_total, rank, world):
 
 
 def shard_levels(levels, lo, hi):
-    """Level of global env i is levels[i % len(levels)] on every rank count."""
+    """First level of the envs [lo, hi): global env i starts on levels[i % len(levels)]."""
     return [levels[i % len(levels)] for i in range(lo, hi)]
 
 
@@ -45,7 +45,10 @@ def make_sharded_env(levels, n_total, seed=None, rank=None, world=None, **kwargs
     if world is None:
         world = dist.get_world_size() if dist.is_initialized() else 1
     lo, hi = shard_range(n_total, rank, world)
-    env = BatchedSafeLifeEnv(shard_levels(levels, lo, hi), hi - lo, **kwargs)
+    # the whole pool on every rank (a few MB); first level and level stride come from
+    # the GLOBAL env index and count, so the level sequence of an env does not depend
+    # on the number of ranks
+    env = BatchedSafeLifeEnv(levels, hi - lo, env_offset=lo, total_envs=n_total, **kwargs)
     env.set_rng_state(shard_rng_states(seed, n_total, lo, hi))
     env.global_range = (lo, hi)
     return env

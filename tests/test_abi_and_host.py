@@ -28,7 +28,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), name
     assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
-    assert handle.sl_abi_version() == 1
+    assert handle.sl_abi_version() == 2
 
 
 def test_struct_layout_matches_header():

@@ -137,7 +137,8 @@ def test_env_random_levels_vs_oracle(shape, kernel):
 def test_auto_reset_cycles_levels(kernel):
     levels = gu.levels_of(gu.load_traj("mazes"))
     L, n = len(levels), 5
-    from safelife_b200.env import BatchedSafeLifeEnv
+    import math
+    from safelife_b200.env import BatchedSafeLifeEnv, coprime_stride
     from safelife_b200 import _lib
     kernel, in_place = _mode(kernel)
     env = BatchedSafeLifeEnv(levels, n, time_limit=7, kernel=kernel, view_shape=(5, 5),
@@ -148,11 +149,12 @@ def test_auto_reset_cycles_levels(kernel):
     for t in range(7):
         obs, r, d, info = env.step(np.zeros(n, dtype=np.int64))
     assert d.all() and info["times_up"].all()
-    assert env._t["level_id"].tolist() == [(i + n) % L for i in range(n)]
+    assert env.level_stride == coprime_stride(n, L) and math.gcd(env.level_stride, L) == 1
+    assert env._t["level_id"].tolist() == [(i + env.level_stride) % L for i in range(n)]
     assert env._t["num_steps"].tolist() == [0] * n
     assert info["episode"]["length"].tolist() == [7] * n
     # boards are the fresh levels after update_exit_colors
-    ora = orc.OracleEnv([levels[(i + n) % L] for i in range(n)],
+    ora = orc.OracleEnv([levels[(i + env.level_stride) % L] for i in range(n)],
                         [orc.rng_from_seed(0)] * n, time_limit=7)
     assert np.array_equal(env.board.cpu().numpy(), ora.board)
     obs, r, d, info = env.step(np.ones(n, dtype=np.int64))
@@ -275,7 +277,7 @@ def test_pipelined_kernel_large_batches_vs_oracle(n, in_place):
     # envs that ran the full episode were auto-reset once: next level, fresh state
     lvl = env._t["level_id"].cpu().numpy()
     sel = idx[live]
-    assert np.array_equal(lvl[sel], (sel % 64 + n) % 64)
+    assert np.array_equal(lvl[sel], (sel % 64 + env.level_stride) % 64)
     fresh = orc.OracleEnv([base[l] for l in lvl[sel]], list(rng[sel]), time_limit=9)
     assert np.array_equal(env.board.cpu().numpy()[sel], fresh.board)
     assert np.array_equal(env.goals.cpu().numpy()[sel], fresh.goals)
@@ -350,3 +352,160 @@ def test_step_plan_and_launch_floor():
     assert "k_env_step_generic" in generic.step_plan()[0]
     assert _lib.lib().sl_launch_floor(small._batch_ref, small._stream()) == _lib.SL_OK
     torch.cuda.synchronize()
+
+
+# ---- the observation written by the step launch itself (sl_env_step_obs) ---------
+TRAIN_CHANNELS = (0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 25, 26, 27, 12, 13)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("shape,view,channels", [
+    ((25, 25), (25, 25), TRAIN_CHANNELS),          # the training observation
+    ((25, 25), (15, 15), tuple(range(16)) + (25, 26, 27)),   # the reference's defaults (19 channels)
+    ((26, 26), (25, 25), TRAIN_CHANNELS),
+    ((9, 7), (11, 40), (3, 1, 0, 9, 25)),          # view larger than the board (torus tiles), 5 channels
+    ((50, 50), (25, 25), TRAIN_CHANNELS),          # Wide geometry
+    ((40, 33), (7, 9), None),                      # raw uint32 view
+    ((25, 25), (5, 5), (4,)),                      # one channel
+    ((16, 16), (9, 9), tuple(range(32))),          # all 32 bits
+])
+def test_fused_observation_matches_oracle(shape, view, channels, kernel):
+    """step() returns the observation of the state it leaves behind, for every env,
+    with and without auto-reset; checked against the oracle's get_obs."""
+    H, W = shape
+    rs = np.random.default_rng(7 * H + W + len(view))
+    n, T = 40, 24
+    levels = _random_levels(rs, 12, H, W)
+    rng = np.stack([orc.rng_from_seed(i) for i in range(n)])
+    for auto in (False, True):
+        from safelife_b200.env import BatchedSafeLifeEnv
+        k, in_place = _mode(kernel)
+        from safelife_b200 import _lib
+        if k == 2 and not _lib.lib().sl_warp_kernel_supported(H, W):
+            pytest.skip("warp kernel does not handle %dx%d boards" % (H, W))
+        env = BatchedSafeLifeEnv(levels, n, time_limit=9, kernel=k, auto_reset=auto,
+                                 goals_in_place=in_place, view_shape=view, output_channels=channels)
+        env.set_rng_state(rng)
+        env.reset()
+        for t in range(T):
+            a = rs.integers(0, 9, n)
+            obs, r, d, info = env.step(a)
+            obs = obs.cpu().numpy()
+            board, goals = env.board.cpu().numpy(), env.goals.cpu().numpy()
+            loc, lvl = env.agent_locs.cpu().numpy()[:, 0], env._t["level_id"].cpu().numpy()
+            for i in range(n):
+                y0, x0 = (0, 0) if loc[i][0] < 0 else loc[i]
+                want = orc.get_obs(board[i], goals[i], (y0, x0), env.pool.exits[lvl[i]], view, channels)
+                assert np.array_equal(obs[i], want), (shape, view, kernel, auto, t, i)
+            # and it is what the stand-alone writer produces
+            assert np.array_equal(env.get_obs().cpu().numpy(), obs)
+            if not auto and t % 9 == 8:
+                env.reset_done()
+
+
+@pytest.mark.parametrize("in_place", [False, True])
+def test_fused_observation_pipelined_kernel(in_place):
+    """A batch large enough for k_env_step_pipe<..., obs fused> plus a ragged tail."""
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(5)
+    n = 592 * 8 * 2 + 8 * 3 + 5
+    base = _random_levels(rs, 32, 25, 25)
+    env = BatchedSafeLifeEnv(base, n, time_limit=6, auto_reset=True, kernel=2, goals_in_place=in_place,
+                             view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
+    ref = BatchedSafeLifeEnv(base, n, time_limit=6, auto_reset=True, kernel=2, goals_in_place=in_place,
+                             view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
+    plan, launches = env.step_plan(obs=True)
+    assert "k_env_step_pipe<" in plan and "obs fused" in plan and launches == 2
+    env.reset()
+    ref.reset()
+    for t in range(14):
+        a = torch.from_numpy(rs.integers(0, 9, n).astype(np.uint8)).cuda()
+        obs, r, d, info = env.step(a)
+        ref.step_physics(a, auto_reset=True)            # physics only, then the stand-alone writer
+        assert torch.equal(env.board, ref.board) and torch.equal(r, ref._t["reward"])
+        assert torch.equal(obs, ref.get_obs()), t
+
+
+def test_step_outputs_survive_the_next_step_and_obs_out():
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(11)
+    levels = _random_levels(rs, 8, 25, 25)
+    env = BatchedSafeLifeEnv(levels, 64, time_limit=50, auto_reset=True)
+    env.reset()
+    a = torch.from_numpy(rs.integers(0, 9, (3, 64)).astype(np.uint8)).cuda()
+    o0, r0, d0, i0 = env.step(a[0])
+    keep = [x.clone() for x in (o0, r0, d0, i0["times_up"], i0["episode"]["success"])]
+    o1, r1, d1, i1 = env.step(a[1])
+    for held, want in zip((o0, r0, d0, i0["times_up"], i0["episode"]["success"]), keep):
+        assert torch.equal(held, want)            # step t's tensors are intact after step t+1
+    assert o1.data_ptr() != o0.data_ptr() and r1.data_ptr() != r0.data_ptr()
+    buf = torch.zeros_like(o1)
+    o2, r2, d2, i2 = env.step(a[2], obs_out=buf)
+    assert o2.data_ptr() == buf.data_ptr() and torch.equal(buf, env.get_obs())
+    with pytest.raises(ValueError):
+        env.step(a[2], obs_out=torch.zeros(3, device="cuda"))
+
+
+@pytest.mark.parametrize("pool,n", [("append-still-25", 4096), ("prune-still-25", 16384),
+                                    ("append-spawn-25", 8192), ("navigation-50", 4096)])
+def test_consecutive_episodes_get_different_levels(pool, n):
+    """BASELINE batch sizes are multiples of the pool sizes: the level stride must not be 0."""
+    import math
+    path = os.path.join(gu.GOLDEN, "pools", pool + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("pool fixture missing")
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200.levels import load_levels
+    levels = load_levels(path)
+    L = len(levels)
+    assert n % L == 0
+    env = BatchedSafeLifeEnv(levels, n, time_limit=3, auto_reset=True)
+    assert env.level_stride != 0 and math.gcd(env.level_stride, L) == 1
+    env.reset()
+    seen = [env._t["level_id"].cpu().numpy().copy()]
+    for t in range(6):                               # two full episodes of 3 steps
+        env.step_physics(np.zeros(n, dtype=np.uint8), auto_reset=True)
+        if t % 3 == 2:
+            seen.append(env._t["level_id"].cpu().numpy().copy())
+    assert (seen[1] != seen[0]).all() and (seen[2] != seen[1]).all()
+    assert np.array_equal(seen[1], (seen[0] + env.level_stride) % L)
+
+
+def test_update_pool_hot_swap():
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(21)
+    levels = _random_levels(rs, 16, 25, 25, spawners=False)
+    for lv in levels:
+        lv["goals"] = (lv["goals"] & 0x0E00).astype(np.uint16)      # static goals
+        lv["points_table"] = orc.DEFAULT_POINTS_TABLE
+    n = 4
+    env = BatchedSafeLifeEnv(levels, n, time_limit=5, auto_reset=True, kernel=2)
+    env.reset()
+    stride = env.level_stride
+    nxt = [(i + stride) % 16 for i in range(n)]
+    with pytest.raises(ValueError):
+        env.update_pool([0], [levels[3]])                            # slot 0 is being played
+    fresh = _random_levels(rs, n, 25, 25, spawners=False)
+    for lv in fresh:
+        lv["points_table"] = orc.DEFAULT_POINTS_TABLE
+    fresh[1]["goals"] = (fresh[1]["goals"] | 1).astype(np.uint16)   # one with dynamic goals
+    env.update_pool(nxt, fresh)
+    assert not env._batch.pool_flags & 2                            # the static-goals promise is gone
+    a = np.zeros(n, dtype=np.uint8)
+    for t in range(5):
+        obs, r, d, info = env.step(a)
+    assert d.all()
+    ora = orc.OracleEnv(fresh, [orc.rng_from_seed(0)] * n, time_limit=5)
+    assert np.array_equal(env.board.cpu().numpy(), ora.board)
+    assert np.array_equal(env.goals.cpu().numpy(), ora.goals)
+    rng = env.rng_state
+    ora2 = orc.OracleEnv(fresh, list(rng), time_limit=5)
+    for t in range(4):
+        acts = rs.integers(0, 9, n)
+        r0, d0 = ora2.step(acts.astype(np.int64))
+        obs, r1, d1, info = env.step(acts)
+        assert np.array_equal(r1.cpu().numpy(), r0) and np.array_equal(env.board.cpu().numpy(), ora2.board)
+        assert np.array_equal(env.goals.cpu().numpy(), ora2.goals)
