@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--pool", default="append-still-25")
     ap.add_argument("--kernel", type=int, default=0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between steps")
+    ap.add_argument("--flush-mode", default="fill", choices=["fill", "fill+read"],
+                    help="fill: write 256 MiB; fill+read: then read another 256 MiB, so that the "
+                         "L2 holds clean lines (no write-back of the flush inside the timed step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -303,6 +306,20 @@ class ClockSampler(object):
                 "samples": len(inside), "source": "nvml, sampled during the timed regions"}
 
 
+class _Flush(object):
+    """L2 flush between timed steps (never inside a timed interval)."""
+
+    def __init__(self, torch, dev, mode):
+        self.buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        self.mode = mode
+        self.clean = torch.zeros(256 << 18, dtype=torch.int32, device=dev) if mode == "fill+read" else None
+
+    def fill_(self, v):
+        self.buf.fill_(v)
+        if self.clean is not None:
+            self.sink = self.clean.max()      # a 256 MiB read: the L2 ends up with clean lines
+
+
 def sweep(args, levels, dev, peak):
     """
     The same device-timed measurement at larger batches (state beyond the L2 at
@@ -313,7 +330,7 @@ def sweep(args, levels, dev, peak):
     from safelife_b200.env import BatchedSafeLifeEnv
     out = []
     H, W = levels[0]["board"].shape
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = _Flush(torch, dev, args.flush_mode)
     for n in (16384, 65536):
         env = BatchedSafeLifeEnv([levels[i % len(levels)] for i in range(n)], n, device=dev,
                                  kernel=args.kernel, time_limit=1000)
@@ -380,7 +397,7 @@ def run_ours(args, levels):
     g = torch.Generator(device=dev)
     g.manual_seed(2 + rank)
     actions = torch.randint(0, 9, (K + Wm, n), generator=g, device=dev, dtype=torch.uint8)
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = None if args.no_flush else _Flush(torch, dev, args.flush_mode)
     lib, bref = env._lib, env._batch_ref
     from safelife_b200 import _lib
     stream = env._stream()

@@ -261,6 +261,60 @@ typedef struct SlObsSpec {
 int sl_env_step_obs(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
                     int kernel, int flags, void *stream);
 
+/* ---- training wrappers as an epilogue of the step (safelife/env_wrappers.py) ---- */
+
+/* Per-env wrapper state, 48 bytes (device memory). */
+typedef struct SlWrapState {
+    int16_t hist[8][2];        /* MovementBonusWrapper._prior_positions, oldest first (row, col) */
+    int32_t hist_len;          /* 1 .. movement_period after a reset */
+    int32_t last_side_effect;  /* SimpleSideEffectPenalty.last_side_effect */
+    int32_t reserved[2];
+} SlWrapState;
+
+#define SL_WRAP_MOVEMENT            1   /* MovementBonusWrapper, env_wrappers.py:32-99 */
+#define SL_WRAP_MOVEMENT_PENALTY    2   /*   as_penalty=True: reward -= movement_bonus */
+#define SL_WRAP_EXIT_BONUS          4   /* ExtraExitBonus, :121-128 */
+#define SL_WRAP_SIDE_EFFECT         8   /* SimpleSideEffectPenalty, :148-213 */
+#define SL_WRAP_IGNORE_REWARD_CELLS 16  /*   ignore_reward_cells=True */
+
+/* The wrapper stack of training/env_factory.py:274-283, applied in that order
+ * (movement bonus, exit bonus, side-effect penalty; min-performance rescaling at
+ * reset).  All pointers are device pointers owned by the caller. */
+typedef struct SlWrapSpec {
+    int32_t flags;                  /* SL_WRAP_* */
+    int32_t movement_period;        /* 1 .. 8 */
+    double  movement_bonus;
+    const double *movement_table;   /* [H + W + movement_period]: movement_bonus *
+                                       (d / movement_period) ** movement_bonus_power by L1
+                                       distance d, evaluated by the caller in float64 */
+    double  exit_bonus;             /* call(ExtraExitBonus.bonus) for this step */
+    double  penalty_coef;           /* call(SimpleSideEffectPenalty.penalty_coef) for this step */
+    uint16_t *baseline;             /* [n_envs][H][W] SimpleSideEffectPenalty.baseline_board */
+    SlWrapState *wstate;            /* [n_envs] */
+    double  *reward;                /* [n_envs] out: the wrapped reward (float64, as the
+                                       reference's becomes) */
+    int32_t *side_effect;           /* [n_envs] out, optional: the current cell count */
+    const int32_t *pool_required;   /* [n_levels] required points under
+                                       MinPerformanceScheduler.min_performance_fraction, written
+                                       into the env record after every reset; NULL: none */
+} SlWrapSpec;
+
+/* sl_env_step_obs with the wrapper epilogue in the same launch: after the scalar
+ * tail of an env (and before its auto-reset) the side-effect cells are counted
+ * against wrap->baseline, the wrapped reward is written to wrap->reward, and a
+ * reset re-initialises the wrapper state of the env (position ring, baseline
+ * board = the fresh board, last_side_effect = 0, rescaled required points).
+ * batch->reward still receives the base env's float32 reward.  obs may be NULL.
+ * With baseline="inaction" the caller advances wrap->baseline (sl_advance_board)
+ * before this call, as env_wrappers.py:179-180 does before comparing. */
+int sl_env_step_wrapped(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
+                        const SlWrapSpec *wrap, int kernel, int flags, void *stream);
+
+/* The wrappers' own reset() for the envs whose mask byte is set (NULL: all), to
+ * follow an sl_env_reset of the same envs. */
+int sl_wrap_reset(const SlEnvBatch *batch, const SlWrapSpec *wrap, const uint8_t *mask,
+                  void *stream);
+
 /* Which kernel(s) sl_env_step(batch, ..., kernel, ...) launches on the current
  * device, as text (for benchmarks and profiles), and how many launches that is
  * per step without SL_STEP_AUTO_RESET on the generic path.  Launches nothing. */

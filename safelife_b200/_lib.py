@@ -74,6 +74,20 @@ class SlObsSpec(ctypes.Structure):
                 ("channels", ctypes.c_int32 * 32)]
 
 
+class SlWrapSpec(ctypes.Structure):
+    """Mirror of struct SlWrapSpec (include/safelife_b200.h)."""
+    _fields_ = [("flags", ctypes.c_int32), ("movement_period", ctypes.c_int32),
+                ("movement_bonus", ctypes.c_double), ("movement_table", ctypes.c_void_p),
+                ("exit_bonus", ctypes.c_double), ("penalty_coef", ctypes.c_double),
+                ("baseline", ctypes.c_void_p), ("wstate", ctypes.c_void_p),
+                ("reward", ctypes.c_void_p), ("side_effect", ctypes.c_void_p),
+                ("pool_required", ctypes.c_void_p)]
+
+
+SL_WRAP_MOVEMENT, SL_WRAP_MOVEMENT_PENALTY, SL_WRAP_EXIT_BONUS = 1, 2, 4
+SL_WRAP_SIDE_EFFECT, SL_WRAP_IGNORE_REWARD_CELLS = 8, 16
+WRAP_STATE_WORDS = 12   # int32 words per SlWrapState record (48 bytes)
+
 # numpy mirror of struct SlEnvState (96 bytes per env)
 import numpy as _np  # noqa: E402
 
@@ -111,6 +125,9 @@ PROTOTYPES = {
     "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_sync": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_obs": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec), _i, _i, _vp],
+    "sl_env_step_wrapped": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec),
+                            ctypes.POINTER(SlWrapSpec), _i, _i, _vp],
+    "sl_wrap_reset": [ctypes.POINTER(SlEnvBatch), ctypes.POINTER(SlWrapSpec), _vp, _vp],
     "sl_env_step_plan": [ctypes.POINTER(SlEnvBatch), _i, _vp, _i, _vp],
     "sl_env_step_obs_plan": [ctypes.POINTER(SlEnvBatch), ctypes.POINTER(SlObsSpec), _i, _vp, _i, _vp],
     "sl_launch_floor": [ctypes.POINTER(SlEnvBatch), _vp],

@@ -17,6 +17,7 @@
 #include "emd_host.h"
 #include "generic_kernels.cuh"
 #include "obs.cuh"
+#include "wrap.cuh"
 #include "warp_kernels.cuh"
 
 namespace {
@@ -496,12 +497,38 @@ static int launch_get_obs(const SlEnvBatch *batch, const sl::ObsParams &O, cudaS
     return launch_status("k_get_obs_warp");
 }
 
+static int check_wrap_spec(const SlEnvBatch *b, const SlWrapSpec *w) {
+    const int known = SL_WRAP_MOVEMENT | SL_WRAP_MOVEMENT_PENALTY | SL_WRAP_EXIT_BONUS |
+                      SL_WRAP_SIDE_EFFECT | SL_WRAP_IGNORE_REWARD_CELLS;
+    if (w->flags & ~known) return fail(SL_ERR_ARG, "unknown wrapper flags");
+    if (!w->wstate || !w->reward) return fail(SL_ERR_ARG, "null pointer in SlWrapSpec");
+    if (((uintptr_t)w->wstate & 15) != 0) return fail(SL_ERR_ARG, "wstate must be 16-byte aligned");
+    static_assert(sizeof(SlWrapState) == 48, "SlWrapState must stay 48 bytes");
+    if (w->flags & SL_WRAP_MOVEMENT) {
+        if (w->movement_period < 1 || w->movement_period > 8)
+            return fail(SL_ERR_ARG, "movement_period must be 1..8");
+        if (!w->movement_table) return fail(SL_ERR_ARG, "null movement_table");
+    }
+    if ((w->flags & SL_WRAP_SIDE_EFFECT) && !w->baseline) return fail(SL_ERR_ARG, "null baseline");
+    (void)b;
+    return SL_OK;
+}
+
+static int wrap_grid(const SlEnvBatch *batch) {
+    int grid = (batch->n_envs + 7) / 8;
+    return grid > 4096 ? 4096 : grid;
+}
+
 static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
-                         int kernel, int flags, void *stream) {
+                         const SlWrapSpec *wrap, int kernel, int flags, void *stream) {
     int rc = check_batch(batch);
     if (rc) return rc;
     if (obs) {
         rc = check_obs_spec(obs);
+        if (rc) return rc;
+    }
+    if (wrap) {
+        rc = check_wrap_spec(batch, wrap);
         if (rc) return rc;
     }
     if (batch->n_envs == 0) return SL_OK;
@@ -518,34 +545,62 @@ static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const 
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
-        const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, props.sm_count,
-                                                      props.smem_per_sm);
-        rc = sl::launch_env_step_warp(*batch, obs ? &O : nullptr, actions, flags, p, st,
+        const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, wrap,
+                                                      props.sm_count, props.smem_per_sm);
+        rc = sl::launch_env_step_warp(*batch, obs ? &O : nullptr, wrap, actions, flags, p, st,
                                       [](const void *fn, size_t smem) { return prepare_smem_ptr(fn, smem); });
         if (rc) return rc;
         return launch_status("k_env_step_warp");
     }
+    // generic path: the same stages as separate launches
     size_t smem = sl::generic_smem_bytes(batch->H * batch->W);
     rc = prepare_smem(sl::k_env_step_generic, smem);
     if (rc) return rc;
     sl::k_env_step_generic<<<grid_for(batch->n_envs), sl::GENERIC_THREADS, smem, st>>>(*batch, actions);
     rc = launch_status("k_env_step_generic");
     if (rc) return rc;
+    if (wrap) {
+        sl::k_wrap_step<<<wrap_grid(batch), 256, 0, st>>>(*batch, *wrap);
+        rc = launch_status("k_wrap_step");
+        if (rc) return rc;
+    }
     if (flags & SL_STEP_AUTO_RESET) {
         rc = sl_env_reset(batch, batch->done, nullptr, SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS, stream);
         if (rc) return rc;
+        if (wrap) {
+            rc = sl_wrap_reset(batch, wrap, batch->done, stream);
+            if (rc) return rc;
+        }
     }
     return obs ? launch_get_obs(batch, O, st) : SL_OK;
 }
 
 int sl_env_step(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                 void *stream) {
-    return env_step_impl(batch, actions, nullptr, kernel, flags, stream);
+    return env_step_impl(batch, actions, nullptr, nullptr, kernel, flags, stream);
 }
 
 int sl_env_step_obs(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
                     int kernel, int flags, void *stream) {
-    return env_step_impl(batch, actions, obs, kernel, flags, stream);
+    return env_step_impl(batch, actions, obs, nullptr, kernel, flags, stream);
+}
+
+int sl_env_step_wrapped(const SlEnvBatch *batch, const uint8_t *actions, const SlObsSpec *obs,
+                        const SlWrapSpec *wrap, int kernel, int flags, void *stream) {
+    if (!wrap) return fail(SL_ERR_ARG, "null wrapper spec");
+    return env_step_impl(batch, actions, obs, wrap, kernel, flags, stream);
+}
+
+int sl_wrap_reset(const SlEnvBatch *batch, const SlWrapSpec *wrap, const uint8_t *mask,
+                  void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (!wrap) return fail(SL_ERR_ARG, "null wrapper spec");
+    rc = check_wrap_spec(batch, wrap);
+    if (rc) return rc;
+    if (batch->n_envs == 0) return SL_OK;
+    sl::k_wrap_reset<<<wrap_grid(batch), 256, 0, (cudaStream_t)stream>>>(*batch, *wrap, mask);
+    return launch_status("k_wrap_reset");
 }
 
 static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int kernel, char *text,
@@ -569,8 +624,8 @@ static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int
         if (rc) return rc;
         sl::ObsParams O;
         if (obs) O = sl::make_obs_params(*obs);
-        const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, props.sm_count,
-                                                      props.smem_per_sm);
+        const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, nullptr,
+                                                      props.sm_count, props.smem_per_sm);
         const char *goals = p.goals_resident ? "goals resident" : "goals in place";
         const char *ob = p.obs ? ", obs fused" : "";
         int n = 0;

@@ -355,9 +355,14 @@ __device__ inline int exit_update(T *bd, const T *gl, int W, int row, int col, i
 }
 
 // Scalar tail of SafeLifeEnv.step (safelife_env.py:155-175) for one env.
+struct StepOut {           // what finish_step wrote for the env, for an epilogue in the same kernel
+    float reward;
+    bool done, times_up;
+};
+
 __device__ inline bool finish_step(const SlEnvBatch &B, int e, SlEnvState &st, int row, int col,
                                    int value, bool agent_alive, bool exited, int static_goals,
-                                   int count_points_mem) {
+                                   int count_points_mem, StepOut *out = nullptr) {
     int steps = st.num_steps + 1;
     bool times_up = steps >= B.time_limit;
     bool active = st.active != 0;
@@ -384,6 +389,7 @@ __device__ inline bool finish_step(const SlEnvBatch &B, int e, SlEnvState &st, i
     B.done[e] = done;
     B.success[e] = success;
     B.times_up[e] = times_up;
+    if (out != nullptr) *out = {reward, done, times_up};
     return done;
 }
 

@@ -32,6 +32,7 @@
 #include "cells.cuh"
 #include "generic_kernels.cuh"
 #include "obs.cuh"
+#include "wrap.cuh"
 #include "../../include/safelife_b200.h"
 
 namespace sl {
@@ -810,10 +811,11 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, const CtaShare
 // followed by phase B on warp 0, and the kernels that write the observation use
 // it because the observation must follow the tail.  Returns true if a reset
 // rewrote the goals slab.
-__device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const CtaShared &cs, int e,
-                                              SlEnvState *st, uint16_t *board, uint16_t *goals,
-                                              int flags, int lane) {
+__device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const SlWrapSpec &Wp,
+                                              const CtaShared &cs, int e, SlEnvState *st,
+                                              uint16_t *board, uint16_t *goals, int flags, int lane) {
     int done = 0;
+    StepOut so = {0.f, false, false};
     __syncwarp();                         // the board cells phase A rewrote
     if (lane == 0) {
         const int lvl = st->level_id;
@@ -825,12 +827,16 @@ __device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const CtaShar
                                       cs.table ? cs.table : B.pool_table + (size_t)lvl * 72,
                                       &agent_alive, &exited, &dmem);
         done = finish_step(B, e, *st, row, col, value, agent_alive, exited, st->static_goals,
-                           pts + dmem) ? 1 : 0;
+                           pts + dmem, &so) ? 1 : 0;
     }
     done = __shfl_sync(FULL, done, 0);
+    const bool wrapped = Wp.wstate != nullptr;
+    // the training wrappers see the final state of the step, before any reset (wrap.cuh)
+    if (wrapped) warp_wrap_step(B, Wp, e, st, board, goals, so.reward, so.done, so.times_up, lane);
     bool reset = false;
     if (done && (flags & SL_STEP_AUTO_RESET)) {
         warp_reset_env(B, st, board, goals, lane);
+        if (wrapped) warp_wrap_reset(B, Wp, e, st, board, lane);
         reset = true;
     }
     __syncwarp();
@@ -854,14 +860,17 @@ __device__ __noinline__ void step_write_obs(const SlEnvBatch &B, const ObsParams
 // variant, one CTA per group of 8 envs.  Warp w runs the whole step of env w --
 // execute_actions and advance_board on bit planes (phase A), the scalar tail on
 // lane 0, the reset of a finished env, and (OBS) the observation -- without
-// waiting for the other warps; one CTA barrier before the bulk stores.
+// waiting for the other warps; one CTA barrier before the bulk stores.  The
+// observation (O.obs != NULL) and the training-wrapper epilogue (Wp.wstate !=
+// NULL) are optional parts of the same launch.
 // The board slabs (and the goal slabs, when resident) arrive on separate
 // mbarriers, so the stencil starts while the goals are still in flight.
 // Ragged / unaligned batches fall back to scalar copies instead of bulk copies.
-template <class G, bool GR, bool OBS>
+template <class G, bool GR>
 __global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 4 : 2)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
-                const uint8_t *__restrict__ actions, int bulk_ok, int flags, int first_group) {
+                const __grid_constant__ SlWrapSpec Wp, const uint8_t *__restrict__ actions,
+                int bulk_ok, int flags, int first_group) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -915,9 +924,9 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         goals_dirty = step_phase_a<G, GR>(B, cs, G(B.H, B.W, lane), st, bd, gl,
                                           GR && bulk ? bar + 1 : nullptr, action);
         SL_TRACE_MARK(threadIdx.x == 0, 2);
-        goals_dirty |= step_tail_env(B, cs, e0 + warp, st, bd, gl, flags, lane);
+        goals_dirty |= step_tail_env(B, Wp, cs, e0 + warp, st, bd, gl, flags, lane);
         SL_TRACE_MARK(threadIdx.x == 0, 3);
-        if (OBS) {
+        if (O.obs != nullptr) {
             const int stage_bytes = obs_stage_bytes(O.vh, O.vw, O.n_channels);
             unsigned char *stage = smem_raw + warp_step_smem_bytes<G>(cells, GR) + warp * stage_bytes;
             step_write_obs(B, O, e0 + warp, st, bd, gl, stage, lane);
@@ -969,13 +978,15 @@ __host__ __device__ inline size_t pipe_smem_bytes(int cells, int stages, bool go
            (size_t)WARP_ENVS_PER_CTA * obs_stage;
 }
 
-// OBS: every stencil warp also runs the tail of its env and writes its
-// observation (step_tail_env, step_write_obs) before it reports the stage
-// finished; the scalar warp is then only the bulk-copy engine's driver.
-template <int STAGES, int CTAS_PER_SM, bool GR, bool OBS>
+// PW (per-warp tail; used when the step also writes the observation or runs
+// the wrapper epilogue): every stencil warp also runs the tail of its env
+// (step_tail_env) and writes its observation (step_write_obs) before it reports
+// the stage finished; the scalar warp is then only the bulk-copy engine's driver.
+template <int STAGES, int CTAS_PER_SM, bool GR, bool PW>
 __global__ void __launch_bounds__(PIPE_THREADS, CTAS_PER_SM)
 k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
-                const uint8_t *__restrict__ actions, int flags, int n_groups) {
+                const __grid_constant__ SlWrapSpec Wp, const uint8_t *__restrict__ actions,
+                int flags, int n_groups) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1023,7 +1034,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
             mbar_wait_parked(fin + s, parity, PIPE_PARK_NS);
             const int e0 = g * WARP_ENVS_PER_CTA;
             bool goals_dirty = GR && lane < WARP_ENVS_PER_CTA && dirty[s * WARP_ENVS_PER_CTA + lane] != 0;
-            if (!OBS)
+            if (!PW)
                 goals_dirty |= step_phase_b(B, cs, e0, WARP_ENVS_PER_CTA, stage_state(s), stage_board(s),
                                             GR ? stage_goals(s) : B.goals + (size_t)e0 * cells, flags, lane);
             const bool any_dirty = __any_sync(FULL, goals_dirty);
@@ -1049,7 +1060,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         const int env_bytes = cells * 2;
         unsigned char *my = stages + warp * env_bytes;  // this warp's slot inside a stage
         unsigned char *obs_stage = smem_raw + pipe_smem_bytes(cells, STAGES, GR) +
-                                   (OBS ? warp * obs_stage_bytes(O.vh, O.vw, O.n_channels) : 0);
+                                   (PW ? warp * obs_stage_bytes(O.vh, O.vw, O.n_channels) : 0);
         int s = 0, parity = 0;
         int next_action = first < n_groups ? actions[(size_t)first * WARP_ENVS_PER_CTA + warp] : 0;
         for (int g = first; g < n_groups; g += stride) {
@@ -1064,9 +1075,9 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
             uint16_t *gl = GR ? (uint16_t *)(stage + WARP_SMEM_STATE + warp_slab_stride(cells))
                               : B.goals + e * cells;
             bool gd = step_phase_a<Narrow, GR>(B, cs, t, st, bd, gl, nullptr, action);
-            if (OBS) {
-                gd |= step_tail_env(B, cs, (int)e, st, bd, gl, flags, lane);
-                step_write_obs(B, O, (int)e, st, bd, gl, obs_stage, lane);
+            if (PW) {
+                gd |= step_tail_env(B, Wp, cs, (int)e, st, bd, gl, flags, lane);
+                if (O.obs != nullptr) step_write_obs(B, O, (int)e, st, bd, gl, obs_stage, lane);
             }
             if (GR && lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
             fence_async_smem();
@@ -1101,7 +1112,7 @@ inline bool pipe_shape_fits(int cells, int stages, int ctas, bool gr, int smem_p
 
 // What sl_env_step / sl_env_step_obs launches for a batch on the warp path.
 struct StepPlan {
-    bool narrow, goals_resident, obs;
+    bool narrow, goals_resident, obs, wrapped;
     int bulk_ok;
     int obs_stage;                  // staging bytes per warp of the fused observation (0: none)
     int pipe_stages, pipe_ctas;     // 0, 0: no pipelined launch
@@ -1110,8 +1121,8 @@ struct StepPlan {
 };
 
 // O: the observation the step writes, or nullptr.
-inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, int sm_count,
-                                   int smem_per_sm) {
+inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const SlWrapSpec *Wp,
+                                   int sm_count, int smem_per_sm) {
     StepPlan p = {};
     const int cells = B.H * B.W;
     const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
@@ -1121,6 +1132,7 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, int 
     p.goals_resident = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok);
     p.narrow = warp_kernel_is_narrow(B.H, B.W);
     p.obs = O != nullptr;
+    p.wrapped = Wp != nullptr;
     p.obs_stage = O ? obs_stage_bytes(O->vh, O->vw, O->n_channels) : 0;
     p.single_groups = groups;
     if (!p.narrow) return p;
@@ -1155,49 +1167,46 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, int 
 // each launch (the ABI layer opts the kernel in to large shared memory there) and
 // returns non-zero to abort.
 template <class Prep>
-inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const uint8_t *actions,
-                                int flags, const StepPlan &p, cudaStream_t st, Prep prep) {
+inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const SlWrapSpec *Wp,
+                                const uint8_t *actions, int flags, const StepPlan &p,
+                                cudaStream_t st, Prep prep) {
     const int cells = B.H * B.W;
     const int threads = WARP_ENVS_PER_CTA * 32;
     static const ObsParams no_obs = {};
+    static const SlWrapSpec no_wrap = {};
     const ObsParams &obs = O ? *O : no_obs;
+    const SlWrapSpec &wrap = Wp ? *Wp : no_wrap;
+    const bool per_warp = p.obs || p.wrapped;
     int rc = 0;
-#define SL_LAUNCH_WARP(G, R, OB)                                                               \
+#define SL_LAUNCH_WARP(G, R)                                                                   \
     do {                                                                                       \
         const size_t smem = warp_step_smem_bytes<G>(cells, R, p.obs_stage);                    \
-        rc = prep((const void *)k_env_step_warp<G, R, OB>, smem);                              \
+        rc = prep((const void *)k_env_step_warp<G, R>, smem);                                  \
         if (rc) return rc;                                                                     \
-        k_env_step_warp<G, R, OB><<<p.single_groups, threads, smem, st>>>(                     \
-            B, obs, actions, p.bulk_ok, flags, p.piped_groups);                                \
-    } while (0)
-#define SL_LAUNCH_WARP_G(G)                                                                    \
-    do {                                                                                       \
-        if (p.goals_resident) {                                                                \
-            if (p.obs) SL_LAUNCH_WARP(G, true, true); else SL_LAUNCH_WARP(G, true, false);     \
-        } else {                                                                               \
-            if (p.obs) SL_LAUNCH_WARP(G, false, true); else SL_LAUNCH_WARP(G, false, false);   \
-        }                                                                                      \
+        k_env_step_warp<G, R><<<p.single_groups, threads, smem, st>>>(                         \
+            B, obs, wrap, actions, p.bulk_ok, flags, p.piped_groups);                          \
     } while (0)
     if (!p.narrow) {
-        SL_LAUNCH_WARP_G(Wide);
+        if (p.goals_resident) SL_LAUNCH_WARP(Wide, true); else SL_LAUNCH_WARP(Wide, false);
         return 0;
     }
     if (p.piped_groups > 0) {
-#define SL_LAUNCH_SHAPE_OB(S, C, R, OB)                                                        \
-        if (R == p.goals_resident && S == p.pipe_stages && C == p.pipe_ctas && OB == p.obs) {  \
+#define SL_LAUNCH_SHAPE_PW(S, C, R, PW)                                                        \
+        if (R == p.goals_resident && S == p.pipe_stages && C == p.pipe_ctas && PW == per_warp) { \
             const size_t smem = pipe_smem_bytes(cells, S, R, p.obs_stage);                     \
-            rc = prep((const void *)k_env_step_pipe<S, C, R, OB>, smem);                       \
+            rc = prep((const void *)k_env_step_pipe<S, C, R, PW>, smem);                       \
             if (rc) return rc;                                                                 \
-            k_env_step_pipe<S, C, R, OB><<<p.pipe_grid, PIPE_THREADS, smem, st>>>(             \
-                B, obs, actions, flags, p.piped_groups);                                       \
+            k_env_step_pipe<S, C, R, PW><<<p.pipe_grid, PIPE_THREADS, smem, st>>>(             \
+                B, obs, wrap, actions, flags, p.piped_groups);                                 \
         }
-#define SL_LAUNCH_SHAPE(S, C, R) SL_LAUNCH_SHAPE_OB(S, C, R, false) SL_LAUNCH_SHAPE_OB(S, C, R, true)
+#define SL_LAUNCH_SHAPE(S, C, R) SL_LAUNCH_SHAPE_PW(S, C, R, false) SL_LAUNCH_SHAPE_PW(S, C, R, true)
         SL_PIPE_SHAPES(SL_LAUNCH_SHAPE)
 #undef SL_LAUNCH_SHAPE
-#undef SL_LAUNCH_SHAPE_OB
+#undef SL_LAUNCH_SHAPE_PW
     }
-    if (p.single_groups > 0) SL_LAUNCH_WARP_G(Narrow);
-#undef SL_LAUNCH_WARP_G
+    if (p.single_groups > 0) {
+        if (p.goals_resident) SL_LAUNCH_WARP(Narrow, true); else SL_LAUNCH_WARP(Narrow, false);
+    }
 #undef SL_LAUNCH_WARP
     return 0;
 }

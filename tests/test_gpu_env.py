@@ -417,13 +417,17 @@ def test_fused_observation_pipelined_kernel(in_place):
                              view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
     plan, launches = env.step_plan(obs=True)
     assert "k_env_step_pipe<" in plan and "obs fused" in plan and launches == 2
+    rng = np.stack([orc.rng_from_seed(i % 499) for i in range(n)])
+    env.set_rng_state(rng)
+    ref.set_rng_state(rng)
     env.reset()
     ref.reset()
     for t in range(14):
         a = torch.from_numpy(rs.integers(0, 9, n).astype(np.uint8)).cuda()
         obs, r, d, info = env.step(a)
         ref.step_physics(a, auto_reset=True)            # physics only, then the stand-alone writer
-        assert torch.equal(env.board, ref.board) and torch.equal(r, ref._t["reward"])
+        assert torch.equal(env.board, ref.board), t
+        assert torch.equal(r, ref._t["reward"]), t
         assert torch.equal(obs, ref.get_obs()), t
 
 
