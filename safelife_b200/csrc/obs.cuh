@@ -72,67 +72,100 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits) {
     return w;
 }
 
-// Observation of env `e` by one warp.  `board` / `goals`: the env's planes (shared
-// or global memory; plain loads, so that planes rewritten by this warp's reset
-// are seen).  `stage`: this warp's staging array (ST[vh * vw + 18]); unused when
-// n_channels == 0.  (row0, col0): agent location, row0 < 0 if the level has none.
-template <typename ST>
+__device__ __forceinline__ uint32_t shl_lo16(uint32_t a, int n) { return n < 16 ? a << n : 0u; }
+
+// Observation of env `e` by one warp.  `board` / `goals`: the env's planes, in
+// shared (BSH / GSH) or global memory -- plain loads, so that planes rewritten by
+// this warp's reset are seen.  `stage`: this warp's staging array in shared memory
+// (ST[vh * vw + 18]); unused when n_channels == 0.  (row0, col0): agent location,
+// row0 < 0 if the level has none.
+template <typename ST, bool BSH, bool GSH>
 __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
                                                int row0, int col0, int level_id,
                                                const uint16_t *board, const uint16_t *goals,
                                                ST *stage, int lane) {
+    // everything the loops need, read once (O and B live in parameter space)
     const int H = B.H, W = B.W, vh = O.vh, vw = O.vw, vcells = vh * vw, C = O.n_channels;
+    const int n_runs = O.n_runs;
     const bool raw = C == 0;
     const int y0 = row0 < 0 ? 0 : row0, x0 = row0 < 0 ? 0 : col0;
-    const bool remove_white = O.remove_white != 0;
+    const uint32_t white = O.remove_white ? COLORS : 0xffffffffu;   // goal colour to blank
+    // address spaces the caller vouches for: lets the compiler use LDS / STS
+    if (BSH) __builtin_assume(__isShared(board));
+    if (GSH) __builtin_assume(__isShared(goals));
+    __builtin_assume(__isShared(stage));
     auto full_at = [&](int idx) -> uint32_t {
         uint32_t g = goals[idx] & COLORS;
-        if (remove_white && g == COLORS) g = 0;
-        return (uint32_t)board[idx] | (g << 16);
+        g = g == white ? 0u : g;
+        return __byte_perm(board[idx], g, 0x5410);   // board | g << 16
     };
     // channel runs: bits [src, src + len) of the cell go to bits [dst, dst + len) of the
     // mask -- one rotate and one and-or each; the first four runs live in registers
     uint32_t rot[4], sel[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const bool on = i < O.n_runs;
+        const bool on = i < n_runs;
         rot[i] = on ? (uint32_t)(O.run_dst[i] - O.run_src[i]) & 31u : 0u;
         sel[i] = on ? O.run_mask[i] << O.run_dst[i] : 0u;
     }
-    auto mask_of = [&](uint32_t v) -> uint32_t {
+    auto mask4 = [&](uint32_t v) -> uint32_t {
         uint32_t m = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) m |= __funnelshift_l(v, v, rot[i]) & sel[i];
-        for (int r = 4; r < O.n_runs; r++)
+        return m;
+    };
+    auto mask_of = [&](uint32_t v) -> uint32_t {     // any number of runs (the rare case)
+        uint32_t m = mask4(v);
+        for (int r = 4; r < n_runs; r++)
             m |= __funnelshift_l(v, v, (uint32_t)(O.run_dst[r] - O.run_src[r]) & 31u) &
                  (O.run_mask[r] << O.run_dst[r]);
         return m;
     };
+    auto stage_st = [&](int i, uint32_t m) { stage[i] = (ST)m; };
+    auto stage_ld = [&](int i) -> uint32_t { return stage[i]; };
     uint32_t *out32 = (uint32_t *)O.obs + (size_t)e * vcells;
     int sy0 = (y0 - vh / 2) % H;
     if (sy0 < 0) sy0 += H;
+    const int cells = H * W;
     for (int c0 = 0; c0 < vw; c0 += 32) {
         const int c = c0 + lane;
         int sx = (x0 - vw / 2 + c) % W;
         if (sx < 0) sx += W;
-        int sy = sy0;
         if (c < vw) {
+            int idx = sy0 * W + sx, left = H - sy0, o = c;   // `left` rows until the torus wraps
+            if (raw) {
+                for (int r = 0; r < vh; r++) {
+                    out32[o] = full_at(idx);
+                    o += vw;
+                    idx += W;
+                    if (--left == 0) { left = H; idx -= cells; }
+                }
+            } else if (n_runs <= 4) {
 #pragma unroll 5
-            for (int r = 0; r < vh; r++) {
-                const uint32_t v = full_at(sy * W + sx);
-                if (raw) out32[r * vw + c] = v;
-                else stage[r * vw + c] = (ST)mask_of(v);
-                sy = sy + 1 == H ? 0 : sy + 1;
+                for (int r = 0; r < vh; r++) {
+                    stage_st(o, mask4(full_at(idx)));
+                    o += vw;
+                    idx += W;
+                    if (--left == 0) { left = H; idx -= cells; }
+                }
+            } else {
+                for (int r = 0; r < vh; r++) {
+                    stage_st(o, mask_of(full_at(idx)));
+                    o += vw;
+                    idx += W;
+                    if (--left == 0) { left = H; idx -= cells; }
+                }
             }
         }
     }
-    if (!raw && lane < 18) stage[vcells + lane] = 0;
+    if (!raw && lane < 18) stage_st(vcells + lane, 0u);
     __syncwarp();
     // exit cells outside the view are clamped onto its perimeter; in index order,
     // so that the last one wins where two collide (helper_utils.py:64-74)
     if (lane == 0) {
         const int32_t *exits = B.pool_exits + (size_t)level_id * B.max_exits;
-        for (int k = 0; k < B.max_exits; k++) {
+        const int max_exits = B.max_exits;
+        for (int k = 0; k < max_exits; k++) {
             const int idx = exits[k];
             if (idx < 0) continue;
             const int iy = idx / W, ix = idx - iy * W;
@@ -142,7 +175,7 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
             jx = min(max(jx, 0), vw - 1);
             const uint32_t v = full_at(idx);
             if (raw) out32[jy * vw + jx] = v;
-            else stage[jy * vw + jx] = (ST)mask_of(v);
+            else stage_st(jy * vw + jx, mask_of(v));
         }
     }
     __syncwarp();
@@ -154,7 +187,7 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
     const int nchunks = (total - head) >> 4;
     auto bit_at = [&](int b) -> uint8_t {
         const int cell = b / C;
-        return (uint8_t)(((uint32_t)stage[cell] >> (b - cell * C)) & 1u);
+        return (uint8_t)((stage_ld(cell) >> (b - cell * C)) & 1u);
     };
     if (lane < head) o[lane] = bit_at(lane);
     {
@@ -164,22 +197,44 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
     uint4 *o16 = (uint4 *)(o + head);
     const int dcell = 512 / C, dk = 512 - dcell * C;     // 32 lanes x 16 bytes per round
     int cell = (head + 16 * lane) / C, k = (head + 16 * lane) - cell * C;
-    for (int q = lane; q < nchunks; q += 32) {
-        uint32_t bits = (uint32_t)stage[cell] >> k;
-        int nb = C - k, cc = cell + 1;
-        while (nb < 16) {
-            bits |= (uint32_t)stage[cc] << nb;
-            nb += C;
-            cc++;
+    if (C >= 8) {      // 16 stream bits span at most three cells
+#pragma unroll 2
+        for (int q = lane; q < nchunks; q += 32) {
+            const uint32_t a0 = stage_ld(cell), a1 = stage_ld(cell + 1), a2 = stage_ld(cell + 2);
+            const int nb = C - k;
+            o16[q] = expand16((a0 >> k) | shl_lo16(a1, nb) | shl_lo16(a2, nb + C));
+            cell += dcell;
+            k += dk;
+            if (k >= C) { k -= C; cell++; }
         }
-        o16[q] = expand16(bits);
-        cell += dcell;
-        k += dk;
-        if (k >= C) {
-            k -= C;
-            cell++;
+    } else {
+        for (int q = lane; q < nchunks; q += 32) {
+            uint32_t bits = stage_ld(cell) >> k;
+            int nb = C - k, cc = cell + 1;
+            while (nb < 16) {
+                bits |= stage_ld(cc) << nb;
+                nb += C;
+                cc++;
+            }
+            o16[q] = expand16(bits);
+            cell += dcell;
+            k += dk;
+            if (k >= C) { k -= C; cell++; }
         }
     }
+}
+
+// The writer for the plane placement at hand, staging type by channel count.
+template <bool BSH, bool GSH>
+__device__ __forceinline__ void warp_write_obs_any(const SlEnvBatch &B, const ObsParams &O, int e,
+                                                   const SlEnvState *st, const uint16_t *board,
+                                                   const uint16_t *goals, unsigned char *stage,
+                                                   int lane) {
+    const int row = st->loc_row, col = st->loc_col, lvl = st->level_id;
+    if (O.n_channels <= 16)
+        warp_write_obs<uint16_t, BSH, GSH>(B, O, e, row, col, lvl, board, goals, (uint16_t *)stage, lane);
+    else
+        warp_write_obs<uint32_t, BSH, GSH>(B, O, e, row, col, lvl, board, goals, (uint32_t *)stage, lane);
 }
 
 // Stand-alone SafeLifeEnv.get_obs: one warp per env, planes read from HBM.
@@ -192,14 +247,8 @@ k_get_obs_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Obs
     const int cells = B.H * B.W;
     unsigned char *stage = smem_raw + (size_t)warp * obs_stage_bytes(O.vh, O.vw, O.n_channels);
     for (int e = blockIdx.x * OBS_WARPS + warp; e < B.n_envs; e += gridDim.x * OBS_WARPS) {
-        const SlEnvState *st = B.state + e;
-        const uint16_t *board = B.board + (size_t)e * cells, *goals = B.goals + (size_t)e * cells;
-        if (O.n_channels <= 16)
-            warp_write_obs<uint16_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
-                                     (uint16_t *)stage, lane);
-        else
-            warp_write_obs<uint32_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
-                                     (uint32_t *)stage, lane);
+        warp_write_obs_any<false, false>(B, O, e, B.state + e, B.board + (size_t)e * cells,
+                                         B.goals + (size_t)e * cells, stage, lane);
         __syncwarp();
     }
 }

@@ -844,16 +844,13 @@ __device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const SlWrapS
 }
 
 // The observation of one env as the step leaves it (see obs.cuh); out of line so
-// that its registers do not weigh on the stencil.
+// that its registers do not weigh on the stencil.  The board slab is in shared
+// memory, the goals slab too when resident (GR).
+template <bool GR>
 __device__ __noinline__ void step_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
                                             const SlEnvState *st, const uint16_t *board,
                                             const uint16_t *goals, unsigned char *stage, int lane) {
-    if (O.n_channels <= 16)
-        warp_write_obs<uint16_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
-                                 (uint16_t *)stage, lane);
-    else
-        warp_write_obs<uint32_t>(B, O, e, st->loc_row, st->loc_col, st->level_id, board, goals,
-                                 (uint32_t *)stage, lane);
+    warp_write_obs_any<true, GR>(B, O, e, st, board, goals, stage, lane);
 }
 
 // SafeLifeEnv.step, one warp per env (safelife_env.py:148-201): single-pass
@@ -866,7 +863,7 @@ __device__ __noinline__ void step_write_obs(const SlEnvBatch &B, const ObsParams
 // The board slabs (and the goal slabs, when resident) arrive on separate
 // mbarriers, so the stencil starts while the goals are still in flight.
 // Ragged / unaligned batches fall back to scalar copies instead of bulk copies.
-template <class G, bool GR>
+template <class G, bool GR, bool PW>
 __global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 4 : 2)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
                 const __grid_constant__ SlWrapSpec Wp, const uint8_t *__restrict__ actions,
@@ -924,19 +921,44 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         goals_dirty = step_phase_a<G, GR>(B, cs, G(B.H, B.W, lane), st, bd, gl,
                                           GR && bulk ? bar + 1 : nullptr, action);
         SL_TRACE_MARK(threadIdx.x == 0, 2);
-        goals_dirty |= step_tail_env(B, Wp, cs, e0 + warp, st, bd, gl, flags, lane);
-        SL_TRACE_MARK(threadIdx.x == 0, 3);
-        if (O.obs != nullptr) {
-            const int stage_bytes = obs_stage_bytes(O.vh, O.vw, O.n_channels);
-            unsigned char *stage = smem_raw + warp_step_smem_bytes<G>(cells, GR) + warp * stage_bytes;
-            step_write_obs(B, O, e0 + warp, st, bd, gl, stage, lane);
+        if (PW) {
+            goals_dirty |= step_tail_env(B, Wp, cs, e0 + warp, st, bd, gl, flags, lane);
+            SL_TRACE_MARK(threadIdx.x == 0, 3);
+            if (O.obs != nullptr) {
+                const int stage_bytes = obs_stage_bytes(O.vh, O.vw, O.n_channels);
+                unsigned char *stage = smem_raw + warp_step_smem_bytes<G>(cells, GR) + warp * stage_bytes;
+                step_write_obs<GR>(B, O, e0 + warp, st, bd, gl, stage, lane);
+            }
         }
     } else if (GR && bulk) {
         mbar_wait(bar + 1, 0);
     }
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
     SL_TRACE_MARK(threadIdx.x == 0, 4);
-    const int any_goals_dirty = __syncthreads_or(goals_dirty);
+    int any_goals_dirty = __syncthreads_or(goals_dirty);
+    if (!PW) {
+        // the scalar tails of the group's 8 envs on 8 lanes of warp 0 (cheaper in issue
+        // slots than one tail per warp when nothing else follows the tail)
+        if (warp != 0) return;
+        any_goals_dirty |= step_phase_b(B, cs, e0, nenv, sstate, sboard, GR ? sgoals : ggoals, flags, lane);
+        fence_async_smem();
+        __syncwarp();
+        if (bulk) {
+            if (lane == 0) {
+                bulk_store(gboard, sboard, group_bytes);
+                if (GR && any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
+                bulk_store(gstate, sstate, state_bytes);
+                bulk_commit_and_wait_read();
+            }
+        } else {
+            for (int i = lane; i < (group_bytes >> 1); i += 32) gboard[i] = sboard[i];
+            if (GR && any_goals_dirty)
+                for (int i = lane; i < (group_bytes >> 1); i += 32) ggoals[i] = sgoals[i];
+            for (int i = lane; i < (state_bytes >> 1); i += 32)
+                ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
+        }
+        return;
+    }
     if (bulk) {
         if (threadIdx.x == 0) {
             bulk_store(gboard, sboard, group_bytes);
@@ -1077,7 +1099,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
             bool gd = step_phase_a<Narrow, GR>(B, cs, t, st, bd, gl, nullptr, action);
             if (PW) {
                 gd |= step_tail_env(B, Wp, cs, (int)e, st, bd, gl, flags, lane);
-                if (O.obs != nullptr) step_write_obs(B, O, (int)e, st, bd, gl, obs_stage, lane);
+                if (O.obs != nullptr) step_write_obs<GR>(B, O, (int)e, st, bd, gl, obs_stage, lane);
             }
             if (GR && lane == 0) dirty[s * WARP_ENVS_PER_CTA + warp] = gd;
             fence_async_smem();
@@ -1129,9 +1151,11 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, cons
     const int full_groups = B.n_envs / WARP_ENVS_PER_CTA;
     p.bulk_ok = (((uintptr_t)B.board | (uintptr_t)B.goals | (uintptr_t)B.state) & 15) == 0;
     static const bool in_place_ok = env_knob("SAFELIFE_B200_GOALS_IN_PLACE", 1) != 0;
-    p.goals_resident = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok);
-    p.narrow = warp_kernel_is_narrow(B.H, B.W);
     p.obs = O != nullptr;
+    // in place only pays while nobody needs every goal cell: the observation does, and
+    // then the goal slabs are better brought in by the bulk-copy engine with the boards
+    p.goals_resident = !((B.pool_flags & SL_POOL_STATIC_GOALS) && in_place_ok) || p.obs;
+    p.narrow = warp_kernel_is_narrow(B.H, B.W);
     p.wrapped = Wp != nullptr;
     p.obs_stage = O ? obs_stage_bytes(O->vh, O->vw, O->n_channels) : 0;
     p.single_groups = groups;
@@ -1178,13 +1202,17 @@ inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const S
     const SlWrapSpec &wrap = Wp ? *Wp : no_wrap;
     const bool per_warp = p.obs || p.wrapped;
     int rc = 0;
-#define SL_LAUNCH_WARP(G, R)                                                                   \
+#define SL_LAUNCH_WARP_PW(G, R, PW)                                                            \
     do {                                                                                       \
         const size_t smem = warp_step_smem_bytes<G>(cells, R, p.obs_stage);                    \
-        rc = prep((const void *)k_env_step_warp<G, R>, smem);                                  \
+        rc = prep((const void *)k_env_step_warp<G, R, PW>, smem);                              \
         if (rc) return rc;                                                                     \
-        k_env_step_warp<G, R><<<p.single_groups, threads, smem, st>>>(                         \
+        k_env_step_warp<G, R, PW><<<p.single_groups, threads, smem, st>>>(                     \
             B, obs, wrap, actions, p.bulk_ok, flags, p.piped_groups);                          \
+    } while (0)
+#define SL_LAUNCH_WARP(G, R)                                                                   \
+    do {                                                                                       \
+        if (per_warp) SL_LAUNCH_WARP_PW(G, R, true); else SL_LAUNCH_WARP_PW(G, R, false);      \
     } while (0)
     if (!p.narrow) {
         if (p.goals_resident) SL_LAUNCH_WARP(Wide, true); else SL_LAUNCH_WARP(Wide, false);
@@ -1208,6 +1236,7 @@ inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const S
         if (p.goals_resident) SL_LAUNCH_WARP(Narrow, true); else SL_LAUNCH_WARP(Narrow, false);
     }
 #undef SL_LAUNCH_WARP
+#undef SL_LAUNCH_WARP_PW
     return 0;
 }
 

@@ -225,6 +225,7 @@ class BatchedSafeLifeEnv(object):
             self._batch_refs.append(ctypes.byref(b))
         self._obs_specs = [self._make_obs_spec(o) for o in self._obs_bufs]
         self._flip = self._obs_i = 0
+        self._wrap = None       # wrappers.WrapRuntime once a training wrapper is stacked on top
         self._batch, self._batch_ref = self._batches[0], self._batch_refs[0]
         self._has_reset = False
         # `_t` also answers for the named views of the state record
@@ -325,6 +326,7 @@ class BatchedSafeLifeEnv(object):
             _lib.check(self._lib.sl_env_reset(
                 self._batch_ref, None, new_level.data_ptr() if new_level is not None else None,
                 0, self._stream()))
+            self._wrap_reset(None)
             self._has_reset = True
             self._scored = None
             return self.get_obs()
@@ -369,11 +371,24 @@ class BatchedSafeLifeEnv(object):
         self._actions.copy_(actions, non_blocking=True)
         bref, out = self._next_outputs()
         spec, obs = (None, None) if obs_out is False else self._next_obs(obs_out)
+        spec = None if spec is None else ctypes.byref(spec)
+        flags = _lib.SL_STEP_AUTO_RESET if auto_reset else 0
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.sl_env_step_obs(
-                bref, self._actions.data_ptr(), None if spec is None else ctypes.byref(spec),
-                self.kernel, _lib.SL_STEP_AUTO_RESET if auto_reset else 0, self._stream()))
+            if self._wrap is None:
+                _lib.check(self._lib.sl_env_step_obs(
+                    bref, self._actions.data_ptr(), spec, self.kernel, flags, self._stream()))
+            else:   # the training wrappers run as an epilogue of the same launch
+                self._wrap.before_step()
+                _lib.check(self._lib.sl_env_step_wrapped(
+                    bref, self._actions.data_ptr(), spec, self._wrap.fill_spec(self._flip),
+                    self.kernel, flags, self._stream()))
         return dict(out, obs=obs)
+
+    def _wrap_reset(self, mask):
+        if self._wrap is not None:
+            _lib.check(self._lib.sl_wrap_reset(
+                self._batch_ref, self._wrap.fill_spec(self._flip),
+                None if mask is None else mask.data_ptr(), self._stream()))
 
     def step_plan(self, obs=False):
         """
@@ -504,6 +519,7 @@ class BatchedSafeLifeEnv(object):
             _lib.check(self._lib.sl_env_reset(
                 self._batch_ref, mask.data_ptr(), None,
                 _lib.SL_RESET_NEXT_LEVEL | _lib.SL_RESET_KEEP_STATS, self._stream()))
+            self._wrap_reset(mask)
         return self.get_obs(out)
 
     # ------------------------------------------------------------ level supply
@@ -568,6 +584,8 @@ class BatchedSafeLifeEnv(object):
                 flags &= ~_lib.SL_POOL_UNIFORM_TABLE
             if flags & _lib.SL_POOL_STATIC_GOALS and not self._goals_static(self._pool_t["pool_goals"][idx]):
                 flags &= ~_lib.SL_POOL_STATIC_GOALS
+            if self._wrap is not None:
+                self._wrap._required_frac = None      # required points are per level
             for b in self._batches:
                 b.pool_flags = flags
             if getattr(self, "_batch_host", None) is not None:

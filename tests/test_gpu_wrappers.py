@@ -63,11 +63,13 @@ def test_reset_done_restarts_wrapper_state():
     obs = env.reset_done()
     assert obs.shape[0] == n
     assert base._t["num_steps"].tolist() == [0] * n
-    assert base._t["level_id"].tolist() == [(i + n) % len(levels) for i in range(n)]
+    assert base._t["level_id"].tolist() == [(i + base.level_stride) % len(levels) for i in range(n)]
     assert env.env.last_side_effect.tolist() == [0] * n
     assert (env.env.baseline_board == base._t["board"]).all()
     with pytest.raises(ValueError):
-        wrappers.MovementBonusWrapper(BatchedSafeLifeEnv(levels, 2, auto_reset=True))
+        wrappers.ContinuingEnv(BatchedSafeLifeEnv(levels, 2, auto_reset=True))
+    with pytest.raises(ValueError):
+        wrappers.MovementBonusWrapper(env)       # one of each kind per stack
 
 
 def test_batched_rollout_follows_act_on_envs():
@@ -96,8 +98,46 @@ def test_batched_rollout_follows_act_on_envs():
     assert done.all()
     obs, ids = runner.obs_for_envs()
     assert ids.tolist() == [[i, 1, 0] for i in range(n)]
-    fresh = orc.OracleEnv([levels[(i + n) % L] for i in range(n)], [orc.rng_from_seed(0)] * n)
+    fresh = orc.OracleEnv([levels[(i + env.level_stride) % L] for i in range(n)],
+                          [orc.rng_from_seed(0)] * n)
     for i in range(n):
         want = orc.get_obs(fresh.board[i], fresh.goals[i], fresh.loc[i], fresh.exits[i], (9, 9), None)
         assert np.array_equal(obs[i].cpu().numpy(), want)
     assert not torch.equal(obs, nxt)
+
+
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("baseline,ignore", [("starting-state", False), ("inaction", False),
+                                             ("starting-state", True)])
+def test_wrapped_auto_reset_equals_driven_resets(kernel, baseline, ignore):
+    """The in-kernel reset of the fused epilogue leaves the wrapper state exactly as a
+    reset_done() from outside does, on the warp path and on the generic path."""
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200 import wrappers
+    d = gu.load_npz("wrapped_v1.0.npz")
+    levels = gu.levels_of(d)
+    n, T = 2 * len(levels) + 3, 40
+    rs = np.random.default_rng(4)
+
+    def make(auto):
+        base = BatchedSafeLifeEnv(levels, n, auto_reset=auto, time_limit=9, view_shape=(7, 7),
+                                  kernel=kernel, seed=5)
+        return wrappers.training_stack(base, exit_difficulty=0.3, se_penalty=0.7,
+                                       se_baseline=baseline, ignore_reward_cells=ignore)
+    a, b = make(True), make(False)
+    oa, ob = a.reset(), b.reset()
+    assert torch.equal(oa, ob)
+    for t in range(T):
+        act = rs.integers(0, 9, n)
+        oa, ra, da, ia = a.step(act)
+        ob, rb, db, ib = b.step(act)
+        assert ra.dtype == torch.float64 and torch.equal(ra, rb), t
+        assert torch.equal(da, db), t
+        ob = b.reset_done()
+        assert torch.equal(oa, ob), t
+        assert torch.equal(a.unwrapped.board, b.unwrapped.board), t
+        assert torch.equal(a.unwrapped._wrap.wstate, b.unwrapped._wrap.wstate), t
+        assert torch.equal(a.unwrapped._wrap.baseline, b.unwrapped._wrap.baseline), t
+        assert torch.equal(a.unwrapped._t["required"], b.unwrapped._t["required"]), t
+    assert int(a.unwrapped._t["num_steps"].max()) < 9                   # episodes did restart
