@@ -74,17 +74,36 @@ def parse_args():
                          "L2 holds clean lines (no write-back of the flush inside the timed step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     return ap.parse_args()
 
 
+def kernel_source_hash():
+    """sha1 of the CUDA sources: the ncu traffic figures are only valid for the code they measured."""
+    import hashlib
+    h = hashlib.sha1()
+    src = os.path.join(ROOT, "safelife_b200", "csrc")
+    for name in sorted(os.listdir(src)):
+        with open(os.path.join(src, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def measured_traffic(plan, n, H, W):
-    """DRAM bytes per launch of the step kernel from the committed ncu capture, or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    kernel = plan.split("<")[0] + ("/in-place" if "in place" in plan else "/resident")
+    """
+    DRAM bytes (read + write) per launch of the kernel `plan` names, from the ncu
+    capture recorded in profiles/r2_traffic.json by tools/ncu_traffic.py -- or None
+    if there is no capture of this kernel at this batch, or if the CUDA sources have
+    changed since the capture (the file carries their hash).
+    """
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
-            entry = json.load(f)[kernel].get("%dx%dx%d" % (n, H, W))
+            data = json.load(f)
+        if data.get("source_sha1") != kernel_source_hash():
+            return None
+        entry = data["entries"].get("%s|%dx%dx%d" % (plan.split(" grid ")[0], n, H, W))
         return entry["dram_bytes_read"] + entry["dram_bytes_write"] if entry else None
     except (OSError, KeyError, ValueError):
         return None
@@ -320,11 +339,36 @@ class _Flush(object):
             self.sink = self.clean.max()      # a 256 MiB read: the L2 ends up with clean lines
 
 
+TRAIN_CHANNELS = (0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 25, 26, 27, 12, 13)   # env_factory.py:311-327
+
+
+def step_bytes(H, W, n, dyn, baseline=False):
+    """Algorithmic bytes of one launch: static goals 3*2HW + 64, dynamic 4*2HW + 64."""
+    extra = 2 * H * W if baseline else 0
+    return (n - dyn) * (6 * H * W + 64 + extra) + dyn * (8 * H * W + 64 + extra)
+
+
+def timed_steps(torch, launch, K, flush, first=0):
+    """Mean ms of `launch(t)` over K steps, one CUDA-event pair per step, L2 flushed before each."""
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    torch.cuda.synchronize()
+    for t in range(K):
+        if flush is not None:
+            flush.fill_(t & 0xFF)
+        ev[t][0].record()
+        launch(first + t)
+        ev[t][1].record()
+    torch.cuda.synchronize()
+    return sum(e[0].elapsed_time(e[1]) for e in ev) / K
+
+
 def sweep(args, levels, dev, peak):
     """
     The same device-timed measurement at larger batches (state beyond the L2 at
-    65536 envs), 60 steps each: where the kernel leaves the launch-latency regime.
+    65536 envs), 60 steps each: where the kernel leaves the launch-latency regime;
+    with and without the observation in the same launch.
     """
+    import ctypes
     import torch
     from safelife_b200 import _lib
     from safelife_b200.env import BatchedSafeLifeEnv
@@ -332,37 +376,174 @@ def sweep(args, levels, dev, peak):
     H, W = levels[0]["board"].shape
     flush = _Flush(torch, dev, args.flush_mode)
     for n in (16384, 65536):
-        env = BatchedSafeLifeEnv([levels[i % len(levels)] for i in range(n)], n, device=dev,
-                                 kernel=args.kernel, time_limit=1000)
+        env = BatchedSafeLifeEnv(levels, n, device=dev, kernel=args.kernel, time_limit=1000,
+                                 view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
         env.reset()
         K = 60
         actions = torch.randint(0, 9, (K + 5, n), device=dev, dtype=torch.uint8)
         stream = env._stream()
-        for t in range(5):
+        spec = ctypes.byref(env._obs_specs[0])
+
+        def physics(t):
             _lib.check(env._lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), args.kernel,
                                             _lib.SL_STEP_AUTO_RESET, stream))
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
-        torch.cuda.synchronize()
-        for t in range(K):
-            flush.fill_(t & 0xFF)
-            ev[t][0].record()
-            _lib.check(env._lib.sl_env_step(env._batch_ref, actions[5 + t].data_ptr(), args.kernel,
-                                            _lib.SL_STEP_AUTO_RESET, stream))
-            ev[t][1].record()
-        torch.cuda.synchronize()
-        ms = sum(e[0].elapsed_time(e[1]) for e in ev) / K
-        gbs = n * (6 * H * W + 64) / (ms * 1e-3) / 1e9
+
+        def with_obs(t):
+            _lib.check(env._lib.sl_env_step_obs(env._batch_ref, actions[t].data_ptr(), spec,
+                                                args.kernel, _lib.SL_STEP_AUTO_RESET, stream))
+        for t in range(5):
+            physics(t)
+            with_obs(t)
+        ms = timed_steps(torch, physics, K, flush, 5)
+        ms_obs = timed_steps(torch, with_obs, K, flush, 5)
+        nbytes = step_bytes(H, W, n, 0)
+        obs_bytes = nbytes + n * (2 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
         plan = env.step_plan()[0]
-        traffic = measured_traffic(plan, n, H, W)
         out.append({"envs": n, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3),
-                    "achieved_gbs": gbs, "frac": gbs / peak, "kernel": plan, "traffic": traffic})
+                    "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                    "kernel": plan, "traffic": measured_traffic(plan, n, H, W),
+                    "step_with_obs": {"ms": ms_obs, "env_steps_per_s": n / (ms_obs * 1e-3),
+                                      "achieved_gbs": obs_bytes / (ms_obs * 1e-3) / 1e9,
+                                      "frac": obs_bytes / (ms_obs * 1e-3) / 1e9 / peak,
+                                      "kernel": env.step_plan(obs=True)[0]}})
         del env
     return out
 
 
+def kernels_agree(torch, levels, dev, n=64, steps=16):
+    """
+    In-run parity spot check without the CPU oracle (which only the tests may use):
+    the warp bit-plane kernels against the independent generic CTA-per-env kernel
+    on the first n envs of the workload -- boards, goals, RNG and rewards bit for bit.
+    """
+    from safelife_b200.env import BatchedSafeLifeEnv, seed_rng_states
+    rng = seed_rng_states(11, n)
+    envs = []
+    for kernel in (0, 1):
+        e = BatchedSafeLifeEnv(levels, n, device=dev, kernel=kernel, time_limit=1000, auto_reset=True)
+        e.set_rng_state(rng)
+        e.reset()
+        envs.append(e)
+    acts = torch.randint(0, 9, (steps, n), device=dev, dtype=torch.uint8)
+    ok = True
+    for t in range(steps):
+        outs = [e.step_physics(acts[t], auto_reset=True) for e in envs]
+        ok &= bool(torch.equal(outs[0]["reward"], outs[1]["reward"]))
+    a, b = envs
+    ok &= bool(torch.equal(a.board, b.board)) and bool(torch.equal(a.goals, b.goals))
+    ok &= bool(torch.equal(a._t["rng"], b._t["rng"]))
+    return ok
+
+
+def other_configs(args, dev, world, rank, peak, barrier, allmax):
+    """
+    BASELINE.json configs 3, 4 and 5 as per-GPU shares: 16384 prune-still,
+    8192 append-spawn (65536 / 8) and 4096 navigation 50x50 (32768 / 8) envs per GPU.
+    At --gpus 8 the totals are exactly configs 4 and 5.  Config 5 steps with the
+    SimpleSideEffectPenalty cell count fused into the launch (sl_env_step_wrapped,
+    starting-state baseline) and adds the episode-end simulation of side_effect_score
+    (sl_side_effect_occupancy on one finished episode per pool level) in board-steps/s.
+    """
+    import torch
+    from safelife_b200 import _lib, wrappers
+    from safelife_b200.env import BatchedSafeLifeEnv, seed_rng_states
+    from safelife_b200.levels import load_levels
+    out = []
+    flush = None if args.no_flush else _Flush(torch, dev, args.flush_mode)
+    K = max(20, min(args.steps, 100))
+    for cfg, pool, n, penalty in ((3, "prune-still-25", 16384, False), (4, "append-spawn-25", 8192, False),
+                                  (5, "navigation-50", 4096, True)):
+        path = os.path.join(POOL_DIR, pool + ".npz")
+        if not os.path.exists(path):
+            continue
+        levels = load_levels(path)
+        H, W = levels[0]["board"].shape
+        env = BatchedSafeLifeEnv(levels, n, device=dev, kernel=args.kernel, time_limit=1000,
+                                 env_offset=rank * n, total_envs=n * world)
+        env.set_rng_state(seed_rng_states(4, n * world)[rank * n:(rank + 1) * n])
+        top = wrappers.SimpleSideEffectPenalty(env, penalty_coef=1.0) if penalty else env
+        top.reset()
+        actions = torch.randint(0, 9, (K + 5, n), device=dev, dtype=torch.uint8)
+        stream = env._stream()
+
+        def launch(t):
+            if penalty:
+                _lib.check(env._lib.sl_env_step_wrapped(
+                    env._batch_ref, actions[t].data_ptr(), None, env._wrap.fill_spec(0), args.kernel,
+                    _lib.SL_STEP_AUTO_RESET, stream))
+            else:
+                _lib.check(env._lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), args.kernel,
+                                                _lib.SL_STEP_AUTO_RESET, stream))
+        for t in range(5):
+            launch(t)
+        barrier()
+        ms = allmax(timed_steps(torch, launch, K, flush, 5))
+        dyn = int((env._t["static_goals"] == 2).sum())
+        nbytes = step_bytes(H, W, n, dyn, baseline=penalty)
+        entry = {
+            "config": cfg, "workload": "%d envs/GPU x %dx%d %s (%d levels)%s" % (
+                n, H, W, pool, len(levels), ", SimpleSideEffectPenalty fused" if penalty else ""),
+            "envs_total": n * world, "ms_per_step": ms, "value": n * world / (ms * 1e-3),
+            "unit": "env-steps/s", "kernel": env.step_plan()[0], "dynamic_goal_envs": dyn,
+            "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": nbytes},
+            "parity_spot_check": {"warp_kernels_equal_generic_kernel": kernels_agree(torch, levels, dev),
+                                  "note": "64 envs x 16 steps, bit for bit; oracle parity: tests/"},
+        }
+        if penalty:
+            # episode end (safelife_env.py:176-187): advance_board(init, num_steps) +
+            # 2 x life_occupancy(..., 1000) for one finished episode per pool level
+            L, samples, lead = len(levels), 1000, 500
+            init = env._pool_t["pool_board"].contiguous()
+            final = env._t["board"][:L].contiguous()
+            counts = torch.zeros((L, 2, H, W, 8), dtype=torch.int32, device=dev)
+            thr = env._pool_t["pool_spawn_thr"].contiguous()
+            steps_t = torch.full((L,), lead, dtype=torch.int32, device=dev)
+            rng = env._t["rng"][:L].clone().contiguous()
+
+            def occupancy(_t):
+                _lib.check(env._lib.sl_side_effect_occupancy(
+                    init.data_ptr(), final.data_ptr(), counts.data_ptr(), L, H, W, thr.data_ptr(),
+                    steps_t.data_ptr(), samples, rng.data_ptr(), stream))
+            occupancy(0)
+            occ_ms = allmax(timed_steps(torch, occupancy, 3, None))
+            entry["episode_end"] = {
+                "what": "side_effect_score simulation (sl_side_effect_occupancy): %d finished episodes "
+                        "per GPU, %d lead steps + 2 x %d counted steps each" % (L, lead, samples),
+                "ms": occ_ms, "board_steps_per_s": world * L * (lead + 2 * samples) / (occ_ms * 1e-3)}
+        out.append(entry)
+        del env, top
+    return out
+
+
+def graph_replay(torch, env, lib, actions, kernel, reps=10):
+    """K steps captured once in a CUDA graph (device-resident actions) and replayed."""
+    from safelife_b200 import _lib
+    Kg = min(50, actions.shape[0])
+    g = torch.cuda.CUDAGraph()
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        st = env._stream()
+        for k in range(Kg):
+            _lib.check(lib.sl_env_step(env._batch_ref, actions[k].data_ptr(), kernel,
+                                       _lib.SL_STEP_AUTO_RESET, st))
+    g.replay()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(reps):
+        g.replay()
+    ev[1].record()
+    torch.cuda.synchronize()
+    return ev[0].elapsed_time(ev[1]) / (reps * Kg), Kg
+
+
 def run_ours(args, levels):
+    import ctypes
     import torch
     import torch.distributed as dist
+    from safelife_b200 import _lib
     from safelife_b200.env import BatchedSafeLifeEnv, seed_rng_states
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -382,15 +563,22 @@ def run_ours(args, levels):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def allmax(x):
+        """max over ranks of a host float"""
+        if world == 1:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     n = args.envs
     lo = rank * n                      # contiguous env range of this rank (SURVEY 8e)
-    my_levels = [levels[(lo + i) % len(levels)] for i in range(n)]
     H, W = levels[0]["board"].shape
     # observations as the reference's training envs take them (env_factory.py:301-327):
-    # 25x25 view, 15 channels; timed separately below, not part of `value`
-    train_channels = (0, 1, 2, 3, 4, 7, 8, 9, 10, 11, 25, 26, 27, 12, 13)
-    env = BatchedSafeLifeEnv(my_levels, n, device=dev, kernel=args.kernel, time_limit=1000,
-                             view_shape=(25, 25), output_channels=train_channels)
+    # 25x25 view, 15 channels; `value` is the step path alone, `step_with_obs` adds them
+    env = BatchedSafeLifeEnv(levels, n, device=dev, kernel=args.kernel, time_limit=1000,
+                             view_shape=(25, 25), output_channels=TRAIN_CHANNELS,
+                             env_offset=lo, total_envs=n * world)
     env.set_rng_state(seed_rng_states(4, n * world)[lo:lo + n])   # global-index-derived streams
     env.reset()
     K, Wm = args.steps, args.warmup
@@ -399,7 +587,6 @@ def run_ours(args, levels):
     actions = torch.randint(0, 9, (K + Wm, n), generator=g, device=dev, dtype=torch.uint8)
     flush = None if args.no_flush else _Flush(torch, dev, args.flush_mode)
     lib, bref = env._lib, env._batch_ref
-    from safelife_b200 import _lib
     stream = env._stream()
     # generic kernel: the auto-reset is a second (masked) launch; warp kernels: fused
     fused = bool(lib.sl_warp_kernel_supported(H, W)) and args.kernel != 1
@@ -415,60 +602,61 @@ def run_ours(args, levels):
         step_kernels(t)
     barrier()
     # ---- value: device-timed, state resident in HBM, L2 flushed between steps ----
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.mark()
-    wall0 = time.perf_counter()
-    for t in range(K):
-        if flush is not None:
-            flush.fill_(t & 0xFF)
-        ev[t][0].record()
-        step_kernels(Wm + t)
-        ev[t][1].record()
-    barrier()
-    wall = time.perf_counter() - wall0
-    total_ms = sum(e[0].elapsed_time(e[1]) for e in ev)       # step incl. auto-reset
-    step_ms = total_ms
-    static = env._t["static_goals"].cpu().numpy()
-    dyn = int((static == 2).sum())
-    bytes_per_launch = (n - dyn) * (6 * H * W + 64) + dyn * (8 * H * W + 64)
+    step_ms = allmax(timed_steps(torch, step_kernels, K, flush, Wm))      # step incl. auto-reset
+    total_ms = step_ms * K
+    dyn = int((env._t["static_goals"] == 2).sum())
+    bytes_per_launch = step_bytes(H, W, n, dyn)
 
-    # ---- e2e: public API, host actions in, host reward/done out, every step ----
-    # (a) step_host: the kernel reads the pinned action buffer and writes reward /
-    #     done into pinned host memory itself (zero-copy over PCIe);
-    # (b) step_physics + explicit cudaMemcpyAsync of the same buffers.
+    # ---- e2e: public API, host buffers, WALL CLOCK around every call ----
+    # (a) step_host: the kernel reads the pinned action buffer and writes reward / done
+    #     into pinned host memory itself (zero-copy over PCIe); the call returns when
+    #     they are visible to the host;
+    # (b) step_physics + explicit cudaMemcpyAsync of the same buffers + stream sync.
+    # Before each call the L2 is flushed and the device drained, outside the clock.
     host_actions = np.random.default_rng(5 + rank).integers(0, 9, (K, n)).astype(np.uint8)
     env.enable_host_io()
-    e2e_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
+    timing, parts = np.zeros(2), np.zeros(2)
+    for t in range(3):
+        env.step_host(host_actions[t], auto_reset=True)
     barrier()
-    checksum = 0.0
+    checksum, e2e_s = 0.0, 0.0
     for t in range(K):
         if flush is not None:
             flush.fill_(t & 0xFF)
-        e2e_ev[t][0].record()
-        reward_np, done_np = env.step_host(host_actions[t], auto_reset=True)
-        e2e_ev[t][1].record()
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reward_np, done_np = env.step_host(host_actions[t], auto_reset=True, timing=timing)
         checksum += float(reward_np[0]) + float(done_np[-1])   # the host consumes the result
+        e2e_s += time.perf_counter() - t0
+        parts += timing
+    e2e_s = allmax(e2e_s)
     barrier()
-    e2e_ms = sum(e[0].elapsed_time(e[1]) for e in e2e_ev)
+    t0 = time.perf_counter()
+    for t in range(K):                                            # the same, back to back
+        reward_np, done_np = env.step_host(host_actions[t], auto_reset=True)
+        checksum += float(reward_np[0]) + float(done_np[-1])
+    e2e_b2b_s = allmax(time.perf_counter() - t0)
 
     pinned_actions = torch.from_numpy(host_actions).pin_memory()
     host_reward = torch.empty(n, dtype=torch.float32).pin_memory()
     host_done = torch.empty(n, dtype=torch.uint8).pin_memory()
-    cp_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(K)]
     barrier()
+    e2e_copy_s = 0.0
     for t in range(K):
         if flush is not None:
             flush.fill_(t & 0xFF)
-        cp_ev[t][0].record()
-        env.step_physics(pinned_actions[t], auto_reset=True)   # H2D inside
-        host_reward.copy_(env._t["reward"], non_blocking=True)
-        host_done.copy_(env._t["done"], non_blocking=True)
-        cp_ev[t][1].record()
-        cp_ev[t][1].synchronize()
-    barrier()
-    e2e_copy_ms = sum(e[0].elapsed_time(e[1]) for e in cp_ev)
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = env.step_physics(pinned_actions[t], auto_reset=True)   # H2D inside
+        host_reward.copy_(out["reward"], non_blocking=True)
+        host_done.copy_(out["done"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        checksum += float(host_reward[0]) + float(host_done[-1])
+        e2e_copy_s += time.perf_counter() - t0
+    e2e_copy_s = allmax(e2e_copy_s)
 
     # ---- supplementary: the rollout regime, K steps back to back with the state
     # L2-resident (no flush, one event pair); not the headline (timing rules) ----
@@ -481,91 +669,89 @@ def run_ours(args, levels):
     barrier()
     l2_ms = l2_ev[0].elapsed_time(l2_ev[1])
 
+    # ---- supplementary: the same steps captured once in a CUDA graph and replayed
+    # (device-resident actions: a policy that lives on the GPU) ----
+    try:
+        graph_ms, graph_k = graph_replay(torch, env, lib, actions, args.kernel)
+        graph = {"ms_per_step": graph_ms, "env_steps_per_s": n / (graph_ms * 1e-3), "steps_per_graph": graph_k,
+                 "note": "supplementary: sl_env_step captured %d times in one CUDA graph, replayed 10 "
+                         "times, no L2 flush; rank 0" % graph_k}
+    except Exception as exc:   # noqa: BLE001
+        graph = {"error": repr(exc)}
+    barrier()
+
     # ---- supplementary: the same event pair around an EMPTY kernel of the step's
     # launch shape, after the same flush: the part of ms_per_step that is not kernel ----
-    fl_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(min(K, 200))]
-    barrier()
-    for ev_pair in fl_ev:
-        if flush is not None:
-            flush.fill_(1)
-        ev_pair[0].record()
-        _lib.check(lib.sl_launch_floor(bref, stream))
-        ev_pair[1].record()
-    barrier()
-    floor_ms = sum(e[0].elapsed_time(e[1]) for e in fl_ev) / len(fl_ev)
+    floor_ms = timed_steps(torch, lambda t: _lib.check(lib.sl_launch_floor(bref, stream)),
+                           min(K, 200), flush)
 
     # ---- supplementary: the gym step as a user calls it -- physics + auto-reset +
     # observation in ONE launch (sl_env_step_obs), L2 flushed, device-timed ----
-    import ctypes
-    Ks = min(K, 200)
-    so_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(Ks)]
     obs_spec = ctypes.byref(env._obs_specs[0])
     obs_plan, obs_launches = env.step_plan(obs=True)
-    for t in range(3):
+
+    def step_obs(t):
         _lib.check(lib.sl_env_step_obs(bref, actions[t].data_ptr(), obs_spec, args.kernel,
                                        _lib.SL_STEP_AUTO_RESET, stream))
+    for t in range(3):
+        step_obs(t)
     barrier()
-    for t in range(Ks):
-        if flush is not None:
-            flush.fill_(t & 0xFF)
-        so_ev[t][0].record()
-        _lib.check(lib.sl_env_step_obs(bref, actions[Wm + t].data_ptr(), obs_spec, args.kernel,
-                                       _lib.SL_STEP_AUTO_RESET, stream))
-        so_ev[t][1].record()
-    barrier()
-    step_obs_ms = sum(e[0].elapsed_time(e[1]) for e in so_ev) / Ks
-    step_obs_bytes = bytes_per_launch + n * (2 * H * W + 25 * 25 * len(train_channels))
+    step_obs_ms = allmax(timed_steps(torch, step_obs, min(K, 200), flush, Wm))
+    obs_only_bytes = n * (2 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
+    step_obs_bytes = bytes_per_launch + obs_only_bytes
 
-    # ---- supplementary: SafeLifeEnv.get_obs for the whole batch (next row 8f-1) ----
-    Ko = min(K, 100)
-    obs_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(Ko)]
+    # ---- supplementary: SafeLifeEnv.get_obs alone (what reset() returns) ----
     env.get_obs()
     barrier()
-    for t in range(Ko):
-        if flush is not None:
-            flush.fill_(t & 0xFF)
-        obs_ev[t][0].record()
-        env.get_obs()
-        obs_ev[t][1].record()
-    barrier()
-    obs_ms = sum(e[0].elapsed_time(e[1]) for e in obs_ev) / Ko
-    obs_bytes = n * (4 * H * W + 25 * 25 * len(train_channels))
+    obs_ms = timed_steps(torch, lambda t: env.get_obs(), min(K, 100), flush)
+    obs_bytes = n * (4 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
     if sampler:
         sampler.mark()
     clocks = sampler.stop() if sampler else None
 
-    times = torch.tensor([total_ms, step_ms, e2e_ms, e2e_copy_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, step_ms, e2e_ms, e2e_copy_ms = (float(x) for x in times.cpu())
+    configs = None
+    if not args.no_configs:
+        peak_now, _ = peaks()
+        configs = other_configs(args, dev, world, rank, peak_now, barrier, allmax)
+
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = bytes_per_launch / (step_ms / K * 1e-3) / 1e9
+        achieved = bytes_per_launch / (step_ms * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": n * world * K / (total_ms * 1e-3), "unit": "env-steps/s",
-            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": total_ms / K,
+            "metric": METRIC, "value": n * world / (step_ms * 1e-3), "unit": "env-steps/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": step_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u16", "data": "synthetic",
             "config": {
                 "workload": "%d envs/GPU x %dx%d %s procgen pool (%d levels), uniform random "
                             "actions, time_limit 1000, auto-reset" % (n, H, W, args.pool, len(levels)),
                 "envs_per_gpu": n, "board": [H, W], "pool": args.pool, "kernel": args.kernel,
-                "l2": "state %.1f MB < L2; L2 flushed (256 MiB fill) between timed steps, flush "
-                      "not timed" % (n * (4 * H * W) / 1e6) if flush is not None else "not flushed",
-                "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks",
+                "l2": ("state %.1f MB < L2; L2 flushed (256 MiB %s) between timed steps, flush "
+                       "not timed" % (n * (4 * H * W) / 1e6, args.flush_mode)) if flush is not None
+                      else "not flushed",
+                "timing": "mean of per-step CUDA-event intervals on the launch stream, max over ranks",
                 "parallelism": "dp%d (independent env shards, no collective)" % world,
             },
             "clocks": clocks,
-            "e2e": {"value": n * world * K / (e2e_ms * 1e-3), "unit": "env-steps/s",
+            "e2e": {"value": n * world * K / e2e_s, "unit": "env-steps/s",
                     "h2d_bytes_per_step": n, "d2h_bytes_per_step": 7 * n,
+                    "timing": "wall clock (time.perf_counter) around every step_host call incl. the "
+                              "host's read of the result; L2 flushed and device drained before each "
+                              "call, outside the clock; max over ranks",
+                    "us_per_step": 1e6 * e2e_s / K,
+                    "host_us": {"launch": parts[0] / K, "wait": parts[1] / K,
+                                "note": "inside sl_env_step_host: validation + launch, then the spin on "
+                                        "the pinned completion word"},
                     "api": "BatchedSafeLifeEnv.step_host(auto_reset=True): uint8 actions in pinned "
                            "host memory read by the kernel, float32 reward + uint8 done/success/"
                            "times_up written to pinned host memory by the kernel (zero-copy over "
-                           "PCIe), event sync and host read every step",
+                           "PCIe), completion word written in stream order, host read every step",
+                    "back_to_back": {"value": n * world * K / e2e_b2b_s, "us_per_step": 1e6 * e2e_b2b_s / K,
+                                     "note": "the same calls with no flush between them (state stays in L2)"},
                     "memcpy_variant": {
-                        "value": n * world * K / (e2e_copy_ms * 1e-3),
+                        "value": n * world * K / e2e_copy_s, "us_per_step": 1e6 * e2e_copy_s / K,
                         "api": "step_physics + cudaMemcpyAsync H2D actions, D2H reward + done, "
-                               "host sync every step"}},
+                               "stream sync and host read every step; wall clock, flushed"}},
             "gpu_launches": launches_per_step * K,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -573,31 +759,34 @@ def run_ours(args, levels):
                 "kernel": plan,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_per_launch,
-                "kernel_ms": step_ms / K, "dynamic_goal_envs": dyn,
+                "kernel_ms": step_ms, "dynamic_goal_envs": dyn,
             },
-            "wall_s_timed_region": wall,
             "launch_floor_ms": floor_ms,
             "step_with_obs": {
-                "ms": step_obs_ms, "env_steps_per_s": n / (step_obs_ms * 1e-3),
+                "ms": step_obs_ms, "env_steps_per_s": n * world / (step_obs_ms * 1e-3),
                 "kernel": obs_plan, "launches_per_step": obs_launches,
                 "bytes_per_launch": step_obs_bytes,
                 "achieved_gbs": step_obs_bytes / (step_obs_ms * 1e-3) / 1e9,
                 "frac": step_obs_bytes / (step_obs_ms * 1e-3) / 1e9 / peak,
+                "traffic": measured_traffic(obs_plan, n, H, W),
                 "note": "supplementary: SafeLifeEnv.step as the gym API returns it -- physics, "
                         "auto-reset and the uint8[N,25,25,15] training observation written by one "
                         "launch (sl_env_step_obs); bytes = step bytes + goals read + obs written; "
-                        "L2 flushed; rank 0"},
+                        "L2 flushed; max over ranks"},
             "obs": {
                 "ms": obs_ms, "bytes_per_launch": obs_bytes,
                 "achieved_gbs": obs_bytes / (obs_ms * 1e-3) / 1e9,
-                "note": "supplementary: k_get_obs_warp (stand-alone), uint8[N,25,25,15] training observations "
-                        "(read board + goals, write obs), L2 flushed; rank 0"},
+                "note": "supplementary: k_get_obs_warp (stand-alone, what reset() returns), "
+                        "uint8[N,25,25,15] (read board + goals, write obs), L2 flushed; rank 0"},
             "back_to_back": {
                 "ms_per_step": l2_ms / K, "env_steps_per_s": n * K / (l2_ms * 1e-3),
                 "note": "supplementary: %d steps queued back to back, no L2 flush (state %s the "
                         "126 MB L2), one event pair; rank 0" % (
                             K, "fits" if n * 4 * H * W < 100e6 else "exceeds")},
+            "graph_replay": graph,
         }
+        if configs is not None:
+            line["configs"] = configs
         if not args.no_sweep and world == 1:
             line["sweep"] = sweep(args, levels, dev, peak)
         if not args.no_cpu_baseline and world == 1:

@@ -335,6 +335,13 @@ int sl_launch_floor(const SlEnvBatch *batch, void *stream);
  * them in place and the results are valid on return. */
 int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                      void *stream);
+/* The same; if timing_us is not NULL it receives the host-side cost of the call
+ * in microseconds: [0] validation + launch, [1] wait until the results are
+ * visible in host memory.  The wait spins on a word of pinned memory that a
+ * stream memory operation writes after the kernel (cudaStreamSynchronize if the
+ * driver does not offer one, or with SAFELIFE_B200_HOST_WAIT=0). */
+int sl_env_step_host(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                     void *stream, double *timing_us);
 
 /* SafeLifeEnv.reset (safelife_env.py:203-218) for every env whose mask byte is
  * non-zero (mask NULL = all envs): copy a level from the pool, then

@@ -124,6 +124,7 @@ PROTOTYPES = {
     "sl_wrapped_label_host": [_vp, _vp, _i, _i, _i],
     "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_sync": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
+    "sl_env_step_host": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _vp],
     "sl_env_step_obs": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec), _i, _i, _vp],
     "sl_env_step_wrapped": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec),
                             ctypes.POINTER(SlWrapSpec), _i, _i, _vp],

@@ -3,8 +3,10 @@
 // Argument checking mirrors the reference binding's error behaviour
 // (safelife/speedups_src/module.c: ValueError for shape problems -> SL_ERR_ARG);
 // nothing here throws or keeps simulation state between calls.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <time.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -673,12 +675,93 @@ int sl_launch_floor(const SlEnvBatch *batch, void *stream) {
     return launch_status("k_launch_floor");
 }
 
-int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
-                     void *stream) {
+namespace {
+// Completion flag for host-driven loops: after the step's launch a stream memory
+// operation writes a sequence number into pinned host memory
+// (cuStreamWriteValue32, resolved at run time: the library does not link libcuda),
+// and the host spins on that word instead of going through cudaStreamSynchronize.
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct HostFlag {
+    volatile uint32_t *word = nullptr;
+    uint32_t seq = 0;
+    int dev = -1;
+    WriteValue32Fn write = nullptr;
+    bool tried = false;
+
+    bool ready() {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) return false;
+        if (tried && cur == dev) return write != nullptr;
+        tried = true;
+        dev = cur;
+        write = nullptr;
+        if (sl::env_knob("SAFELIFE_B200_HOST_WAIT", 1) == 0) return false;   // 0: cudaStreamSynchronize
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess || fn == nullptr) {
+            cudaGetLastError();
+            return false;
+        }
+        if (word == nullptr) {
+            void *p = nullptr;
+            if (cudaHostAlloc(&p, 64, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            word = (volatile uint32_t *)p;
+            *word = 0;
+        }
+        write = (WriteValue32Fn)fn;
+        return true;
+    }
+};
+thread_local HostFlag g_host_flag;
+
+double now_us() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+
+int wait_for_stream(cudaStream_t st) {
+    HostFlag &f = g_host_flag;
+    if (f.ready()) {
+        const uint32_t seq = ++f.seq;
+        if (f.write((CUstream)st, (CUdeviceptr)(uintptr_t)f.word, seq, 0) == CUDA_SUCCESS) {
+            // the kernel's stores into pinned memory are ordered before the flag
+            // (stream memory operations fence by default)
+            unsigned spins = 0;
+            while (*f.word != seq) {
+                __builtin_ia32_pause();
+                if ((++spins & 0xfffffu) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;
+            }
+            if (*f.word == seq) return SL_OK;
+        }
+    }
+    SL_CUDA(cudaStreamSynchronize(st));
+    return SL_OK;
+}
+}  // namespace
+
+int sl_env_step_host(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                     void *stream, double *timing_us) {
+    const double t0 = timing_us ? now_us() : 0.0;
     int rc = sl_env_step(batch, actions, kernel, flags, stream);
     if (rc) return rc;
-    SL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const double t1 = timing_us ? now_us() : 0.0;
+    rc = wait_for_stream((cudaStream_t)stream);
+    if (rc) return rc;
+    if (timing_us) {
+        timing_us[0] = t1 - t0;
+        timing_us[1] = now_us() - t1;
+    }
     return SL_OK;
+}
+
+int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                     void *stream) {
+    return sl_env_step_host(batch, actions, kernel, flags, stream, nullptr);
 }
 
 int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *new_level,

@@ -59,7 +59,7 @@ inline ObsParams make_obs_params(const SlObsSpec &s) {
 __host__ __device__ inline int obs_stage_bytes(int vh, int vw, int n_channels) {
     if (n_channels == 0) return 0;
     const int elt = n_channels <= 16 ? 2 : 4;
-    return ((vh * vw + 18) * elt + 15) & ~15;
+    return ((vh * vw + 34) * elt + 15) & ~15;
 }
 
 // spread 16 bits into 16 bytes (bit i -> byte i = 0 / 1)
@@ -72,12 +72,13 @@ __device__ __forceinline__ uint4 expand16(uint32_t bits) {
     return w;
 }
 
-__device__ __forceinline__ uint32_t shl_lo16(uint32_t a, int n) { return n < 16 ? a << n : 0u; }
+// a << n with n >= 32 giving 0 (one funnel shift with a clamped amount)
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t a, int n) { return __funnelshift_lc(0u, a, n); }
 
 // Observation of env `e` by one warp.  `board` / `goals`: the env's planes, in
 // shared (BSH / GSH) or global memory -- plain loads, so that planes rewritten by
 // this warp's reset are seen.  `stage`: this warp's staging array in shared memory
-// (ST[vh * vw + 18]); unused when n_channels == 0.  (row0, col0): agent location,
+// (ST[vh * vw + 34]); unused when n_channels == 0.  (row0, col0): agent location,
 // row0 < 0 if the level has none.
 template <typename ST, bool BSH, bool GSH>
 __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
@@ -126,39 +127,29 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
     uint32_t *out32 = (uint32_t *)O.obs + (size_t)e * vcells;
     int sy0 = (y0 - vh / 2) % H;
     if (sy0 < 0) sy0 += H;
-    const int cells = H * W;
     for (int c0 = 0; c0 < vw; c0 += 32) {
         const int c = c0 + lane;
         int sx = (x0 - vw / 2 + c) % W;
         if (sx < 0) sx += W;
         if (c < vw) {
-            int idx = sy0 * W + sx, left = H - sy0, o = c;   // `left` rows until the torus wraps
-            if (raw) {
-                for (int r = 0; r < vh; r++) {
-                    out32[o] = full_at(idx);
-                    o += vw;
-                    idx += W;
-                    if (--left == 0) { left = H; idx -= cells; }
-                }
-            } else if (n_runs <= 4) {
+            // rows in runs that end where the torus wraps: no per-row wrap test
+            int idx = sy0 * W + sx, o = c, r = 0, run = min(vh, H - sy0);
+            while (r < vh) {
+                if (raw) {
+                    for (int i = 0; i < run; i++, o += vw, idx += W) out32[o] = full_at(idx);
+                } else if (n_runs <= 4) {
 #pragma unroll 5
-                for (int r = 0; r < vh; r++) {
-                    stage_st(o, mask4(full_at(idx)));
-                    o += vw;
-                    idx += W;
-                    if (--left == 0) { left = H; idx -= cells; }
+                    for (int i = 0; i < run; i++, o += vw, idx += W) stage_st(o, mask4(full_at(idx)));
+                } else {
+                    for (int i = 0; i < run; i++, o += vw, idx += W) stage_st(o, mask_of(full_at(idx)));
                 }
-            } else {
-                for (int r = 0; r < vh; r++) {
-                    stage_st(o, mask_of(full_at(idx)));
-                    o += vw;
-                    idx += W;
-                    if (--left == 0) { left = H; idx -= cells; }
-                }
+                r += run;
+                idx = sx;                       // wrapped to source row 0
+                run = min(vh - r, H);
             }
         }
     }
-    if (!raw && lane < 18) stage_st(vcells + lane, 0u);
+    if (!raw) stage_st(vcells + lane, 0u);     // zero padding the expansion may touch
     __syncwarp();
     // exit cells outside the view are clamped onto its perimeter; in index order,
     // so that the last one wins where two collide (helper_utils.py:64-74)
@@ -184,25 +175,31 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
     const int total = vcells * C;
     uint8_t *o = (uint8_t *)O.obs + (size_t)e * total;
     const int head = min(total, (int)((16u - (unsigned)((uintptr_t)o & 15u)) & 15u));
-    const int nchunks = (total - head) >> 4;
+    // every lane expands 32 consecutive stream bits into two 16-byte stores per round
+    const int head32 = head;
+    const int nchunks = (total - head32) >> 5;
     auto bit_at = [&](int b) -> uint8_t {
         const int cell = b / C;
         return (uint8_t)((stage_ld(cell) >> (b - cell * C)) & 1u);
     };
-    if (lane < head) o[lane] = bit_at(lane);
+    if (lane < head32) o[lane] = bit_at(lane);
     {
-        const int b = head + (nchunks << 4) + lane;
+        const int b = head32 + (nchunks << 5) + lane;      // fewer than 32 bytes are left over
         if (b < total) o[b] = bit_at(b);
     }
-    uint4 *o16 = (uint4 *)(o + head);
-    const int dcell = 512 / C, dk = 512 - dcell * C;     // 32 lanes x 16 bytes per round
-    int cell = (head + 16 * lane) / C, k = (head + 16 * lane) - cell * C;
-    if (C >= 8) {      // 16 stream bits span at most three cells
+    uint4 *o16 = (uint4 *)(o + head32);
+    const int dcell = 1024 / C, dk = 1024 - dcell * C;     // 32 lanes x 32 bytes per round
+    int cell = (head32 + 32 * lane) / C, k = (head32 + 32 * lane) - cell * C;
+    if (C >= 11) {     // 32 stream bits span at most four cells
 #pragma unroll 2
         for (int q = lane; q < nchunks; q += 32) {
-            const uint32_t a0 = stage_ld(cell), a1 = stage_ld(cell + 1), a2 = stage_ld(cell + 2);
+            const uint32_t a0 = stage_ld(cell), a1 = stage_ld(cell + 1), a2 = stage_ld(cell + 2),
+                           a3 = stage_ld(cell + 3);
             const int nb = C - k;
-            o16[q] = expand16((a0 >> k) | shl_lo16(a1, nb) | shl_lo16(a2, nb + C));
+            const uint32_t bits = (a0 >> k) | shl_clamp(a1, nb) | shl_clamp(a2, nb + C) |
+                                  shl_clamp(a3, nb + 2 * C);
+            o16[2 * q] = expand16(bits);
+            o16[2 * q + 1] = expand16(bits >> 16);
             cell += dcell;
             k += dk;
             if (k >= C) { k -= C; cell++; }
@@ -211,12 +208,13 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
         for (int q = lane; q < nchunks; q += 32) {
             uint32_t bits = stage_ld(cell) >> k;
             int nb = C - k, cc = cell + 1;
-            while (nb < 16) {
+            while (nb < 32) {
                 bits |= stage_ld(cc) << nb;
                 nb += C;
                 cc++;
             }
-            o16[q] = expand16(bits);
+            o16[2 * q] = expand16(bits);
+            o16[2 * q + 1] = expand16(bits >> 16);
             cell += dcell;
             k += dk;
             if (k >= C) { k -= C; cell++; }

@@ -424,15 +424,20 @@ class BatchedSafeLifeEnv(object):
         self._batch_host_ref = ctypes.byref(self._batch_host)
         self._host_np = {k: v.numpy() for k, v in self._host.items()}
         self._host_actions_ptr = self._host["actions"].data_ptr()
+        self._host_stream = self._stream()
         return self._host_np
 
-    def step_host(self, actions, auto_reset=None):
+    def step_host(self, actions, auto_reset=None, timing=None):
         """
         One step with HOST buffers end to end: `actions` (array-like [N], values
         0..8) are placed in the pinned action buffer, the kernel reads them and
         writes reward / done / success / times_up straight into pinned host memory,
-        and the call returns after the step has completed.  Returns numpy views
-        (reward float32[N], done uint8[N]) that the next call overwrites.
+        and the call returns once they are visible there (sl_env_step_host: the host
+        spins on a word of pinned memory written in stream order after the kernel).
+        Returns numpy views (reward float32[N], done uint8[N]) that the next call
+        overwrites.  `timing`: optional float64[2] numpy array receiving the
+        microseconds spent in the launch and in the wait.  Runs on the stream that
+        was current when enable_host_io() was called.
         """
         if getattr(self, "_host", None) is None:
             self.enable_host_io()
@@ -441,15 +446,16 @@ class BatchedSafeLifeEnv(object):
             np.copyto(h["actions"], actions, casting="unsafe")
         auto = self.auto_reset if auto_reset is None else auto_reset
         flags = _lib.SL_STEP_AUTO_RESET if auto else 0
+        tptr = None if timing is None else timing.ctypes.data
         # host-driven loop: keep the per-step Python overhead out of the way (the
         # device context manager costs more than the kernel launch)
         if torch.cuda.current_device() == self.device.index:
-            status = self._lib.sl_env_step_sync(self._batch_host_ref, self._host_actions_ptr,
-                                                self.kernel, flags, self._stream())
+            status = self._lib.sl_env_step_host(self._batch_host_ref, self._host_actions_ptr,
+                                                self.kernel, flags, self._host_stream, tptr)
         else:
             with torch.cuda.device(self.device):
-                status = self._lib.sl_env_step_sync(self._batch_host_ref, self._host_actions_ptr,
-                                                    self.kernel, flags, self._stream())
+                status = self._lib.sl_env_step_host(self._batch_host_ref, self._host_actions_ptr,
+                                                    self.kernel, flags, self._host_stream, tptr)
         if status:
             _lib.check(status)
         return h["reward"], h["done"]

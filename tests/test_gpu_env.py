@@ -513,3 +513,60 @@ def test_update_pool_hot_swap():
         obs, r1, d1, info = env.step(acts)
         assert np.array_equal(r1.cpu().numpy(), r0) and np.array_equal(env.board.cpu().numpy(), ora2.board)
         assert np.array_equal(env.goals.cpu().numpy(), ora2.goals)
+
+
+def test_step_is_cuda_graph_capturable():
+    """sl_env_step_obs (physics + auto-reset + observation) captured in a CUDA graph and
+    replayed equals the same steps launched one by one."""
+    import ctypes
+    import torch
+    from safelife_b200 import _lib
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(17)
+    levels = _random_levels(rs, 16, 25, 25)
+    n, K = 256, 6
+    rng = np.stack([orc.rng_from_seed(i) for i in range(n)])
+    envs = []
+    for _ in range(2):
+        e = BatchedSafeLifeEnv(levels, n, time_limit=7, auto_reset=True, view_shape=(25, 25),
+                               output_channels=TRAIN_CHANNELS)
+        e.set_rng_state(rng)
+        e.reset()
+        envs.append(e)
+    a, b = envs
+    acts = torch.from_numpy(rs.integers(0, 9, (K, n)).astype(np.uint8)).cuda()
+    obs = torch.zeros((K,) + tuple(a._obs_bufs[0].shape), dtype=torch.uint8, device="cuda")
+    specs = [a._make_obs_spec(obs[k]) for k in range(K)]
+    a.step(acts[0])                       # warm-up launch outside the capture (sets the
+    b.step(acts[0])                       # kernel's shared-memory attribute once)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for k in range(K):
+            _lib.check(a._lib.sl_env_step_obs(a._batch_ref, acts[k].data_ptr(), ctypes.byref(specs[k]),
+                                              0, _lib.SL_STEP_AUTO_RESET, a._stream()))
+    for rep in range(3):                  # 18 steps: crosses episode boundaries (time_limit 7)
+        g.replay()
+        for k in range(K):
+            o, r, d, info = b.step(acts[k])
+            assert torch.equal(o, obs[k]), (rep, k)
+        torch.cuda.synchronize()
+        assert torch.equal(a.board, b.board) and torch.equal(a._t["rng"], b._t["rng"]), rep
+        assert torch.equal(a._t["ep_reward"], b._t["ep_reward"]), rep
+
+
+def test_step_host_reports_timing_and_both_wait_modes():
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(23)
+    levels = _random_levels(rs, 8, 25, 25)
+    env = BatchedSafeLifeEnv(levels, 128, time_limit=20, auto_reset=True, seed=3)
+    ref = BatchedSafeLifeEnv(levels, 128, time_limit=20, auto_reset=True, seed=3)
+    env.set_rng_state(ref.rng_state)
+    env.reset()
+    ref.reset()
+    timing = np.zeros(2)
+    for t in range(30):
+        a = rs.integers(0, 9, 128)
+        r, d = env.step_host(a, timing=timing)
+        out = ref.step_physics(a, auto_reset=True)
+        assert np.array_equal(r, out["reward"].cpu().numpy()) and np.array_equal(d, out["done"].cpu().numpy())
+        assert timing[0] > 0 and timing[1] >= 0
