@@ -342,6 +342,14 @@ int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel
  * driver does not offer one, or with SAFELIFE_B200_HOST_WAIT=0). */
 int sl_env_step_host(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                      void *stream, double *timing_us);
+/* The two halves of sl_env_step_host for callers that keep several batches in
+ * flight (one stream each) and overlap the host's work on one batch with the
+ * device's on another: submit launches the step and queues, in stream order, a
+ * write of `seq` into the pinned host word `flag`; wait spins until the word
+ * holds `seq`, at which point the step's outputs in pinned memory are valid. */
+int sl_env_step_submit(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                       void *stream, uint32_t *flag, uint32_t seq);
+int sl_host_wait(const uint32_t *flag, uint32_t seq, void *stream);
 
 /* SafeLifeEnv.reset (safelife_env.py:203-218) for every env whose mask byte is
  * non-zero (mask NULL = all envs): copy a level from the pool, then

@@ -125,6 +125,8 @@ PROTOTYPES = {
     "sl_env_step": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_sync": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp],
     "sl_env_step_host": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _vp],
+    "sl_env_step_submit": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _vp, ctypes.c_uint32],
+    "sl_host_wait": [_vp, ctypes.c_uint32, _vp],
     "sl_env_step_obs": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec), _i, _i, _vp],
     "sl_env_step_wrapped": [ctypes.POINTER(SlEnvBatch), _vp, ctypes.POINTER(SlObsSpec),
                             ctypes.POINTER(SlWrapSpec), _i, _i, _vp],

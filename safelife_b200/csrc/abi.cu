@@ -21,6 +21,7 @@
 #include "obs.cuh"
 #include "wrap.cuh"
 #include "warp_kernels.cuh"
+#include "tile_kernels.cuh"
 
 namespace {
 
@@ -225,7 +226,8 @@ int sl_debug_trace(void *buf) {
 }
 #endif
 
-int sl_warp_kernel_supported(int H, int W) { return sl::warp_kernel_supports(H, W) ? 1 : 0; }
+static int fast_step_path(int H, int W);
+int sl_warp_kernel_supported(int H, int W) { return fast_step_path(H, W) != 0 ? 1 : 0; }
 
 int sl_advance_board(const uint16_t *in, uint16_t *out, int n, int H, int W, float spawn_prob,
                      int n_steps, uint64_t *rng, void *stream) {
@@ -474,6 +476,18 @@ static int check_batch(const SlEnvBatch *b) {
     return SL_OK;
 }
 
+// Which fast step path handles H x W boards: 1 = one warp per env (narrow, <= 32 x 32),
+// 2 = several warps per env on 30 x 30 tiles, 3 = one warp per env on 64-bit rows
+// (<= 64 x 64; superseded by the tiles, kept behind SAFELIFE_B200_WIDE=1 for A/B runs),
+// 0 = none (generic CTA-per-env kernel).
+static int fast_step_path(int H, int W) {
+    if (sl::warp_kernel_supports(H, W) && sl::warp_kernel_is_narrow(H, W)) return 1;
+    static const bool wide = sl::env_knob("SAFELIFE_B200_WIDE", 0) != 0;
+    if (wide && sl::warp_kernel_supports(H, W)) return 3;
+    if (sl::tile_kernel_supports(H, W)) return 2;
+    return 0;
+}
+
 static int check_obs_spec(const SlObsSpec *o) {
     if (o->vh < 1 || o->vw < 1 || o->n_channels < 0) return fail(SL_ERR_ARG, "bad view shape");
     if (o->n_channels > 32) return fail(SL_ERR_ARG, "at most 32 output channels (bits of the uint32 view)");
@@ -537,12 +551,26 @@ static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const 
     if (!actions) return fail(SL_ERR_ARG, "null actions");
     if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
     cudaStream_t st = (cudaStream_t)stream;
-    bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
+    const int path = fast_step_path(batch->H, batch->W);
+    bool warp_ok = path != 0;
     if (kernel == 2 && !warp_ok)
-        return fail(SL_ERR_ARG, "warp kernel needs 3 <= H, W <= %d", sl::WARP_MAX_DIM);
+        return fail(SL_ERR_ARG, "no warp kernel for %d x %d boards", batch->H, batch->W);
     if (flags & ~SL_STEP_AUTO_RESET) return fail(SL_ERR_ARG, "unknown step flags");
     sl::ObsParams O;
     if (obs) O = sl::make_obs_params(*obs);
+    if ((kernel == 2 || kernel == 0) && path == 2) {
+        static const sl::ObsParams no_obs = {};
+        static const SlWrapSpec no_wrap = {};
+        const sl::TileShape sh = sl::tile_shape(batch->H, batch->W);
+        const int stage = obs ? sl::obs_stage_bytes(O.vh, O.vw, O.n_channels) : 0;
+        const size_t smem = sl::tile_step_smem_bytes(batch->H, batch->W, stage);
+        rc = prepare_smem(sl::k_env_step_tile, smem);
+        if (rc) return rc;
+        const int bulk_ok = (((uintptr_t)batch->board | (uintptr_t)batch->goals | (uintptr_t)batch->state) & 15) == 0;
+        sl::k_env_step_tile<<<(batch->n_envs + sh.epc - 1) / sh.epc, sh.epc * sh.TW * 32, smem, st>>>(
+            *batch, obs ? O : no_obs, wrap ? *wrap : no_wrap, actions, bulk_ok, flags);
+        return launch_status("k_env_step_tile");
+    }
     if (kernel == 2 || (kernel == 0 && warp_ok)) {
         DeviceProps props;
         rc = device_props(&props);
@@ -616,11 +644,17 @@ static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int
     if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
     char buf[320];
     int launches = 0;
-    const bool warp_ok = sl::warp_kernel_supports(batch->H, batch->W);
+    const int path = fast_step_path(batch->H, batch->W);
+    const bool warp_ok = path != 0;
     if (batch->n_envs == 0) {
         snprintf(buf, sizeof buf, "nothing to launch");
+    } else if ((kernel == 2 || kernel == 0) && path == 2) {
+        const sl::TileShape sh = sl::tile_shape(batch->H, batch->W);
+        snprintf(buf, sizeof buf, "k_env_step_tile<%d x %d tiles, %d envs/CTA%s> grid %d", sh.TR, sh.TC,
+                 sh.epc, obs ? ", obs fused" : "", (batch->n_envs + sh.epc - 1) / sh.epc);
+        launches = 1;
     } else if (kernel == 2 || (kernel == 0 && warp_ok)) {
-        if (!warp_ok) return fail(SL_ERR_ARG, "warp kernel needs 3 <= H, W <= %d", sl::WARP_MAX_DIM);
+        if (!warp_ok) return fail(SL_ERR_ARG, "no warp kernel for %d x %d boards", batch->H, batch->W);
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
@@ -743,6 +777,37 @@ int wait_for_stream(cudaStream_t st) {
     return SL_OK;
 }
 }  // namespace
+
+int sl_env_step_submit(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
+                       void *stream, uint32_t *flag, uint32_t seq) {
+    if (!flag) return fail(SL_ERR_ARG, "null completion word");
+    int rc = sl_env_step(batch, actions, kernel, flags, stream);
+    if (rc) return rc;
+    HostFlag &f = g_host_flag;
+    if (f.ready() && f.write((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, seq, 0) == CUDA_SUCCESS)
+        return SL_OK;
+    // no stream memory operations: complete synchronously and publish the word ourselves
+    SL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *(volatile uint32_t *)flag = seq;
+    return SL_OK;
+}
+
+int sl_host_wait(const uint32_t *flag, uint32_t seq, void *stream) {
+    if (!flag) return fail(SL_ERR_ARG, "null completion word");
+    const volatile uint32_t *word = flag;
+    unsigned spins = 0;
+    while (*word != seq) {
+        __builtin_ia32_pause();
+        if ((++spins & 0xfffffu) == 0) {
+            cudaError_t q = cudaStreamQuery((cudaStream_t)stream);
+            if (q != cudaErrorNotReady && q != cudaSuccess)
+                return fail(SL_ERR_CUDA, "stream failed while waiting: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && *word != seq)
+                return fail(SL_ERR_ARG, "stream is idle but the completion word is %u, not %u", *word, seq);
+        }
+    }
+    return SL_OK;
+}
 
 int sl_env_step_host(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                      void *stream, double *timing_us) {

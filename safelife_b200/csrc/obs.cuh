@@ -80,11 +80,15 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t a, int n) { return __funn
 // this warp's reset are seen.  `stage`: this warp's staging array in shared memory
 // (ST[vh * vw + 34]); unused when n_channels == 0.  (row0, col0): agent location,
 // row0 < 0 if the level has none.
-template <typename ST, bool BSH, bool GSH>
+// Several warps may share one env (the tiled kernels): warp `part` of `nparts`
+// gathers a block of the view's rows and expands every nparts-th round of output
+// bytes; `sync()` is a barrier over all of them (__syncwarp for a single warp).
+template <typename ST, bool BSH, bool GSH, class SyncFn>
 __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
                                                int row0, int col0, int level_id,
                                                const uint16_t *board, const uint16_t *goals,
-                                               ST *stage, int lane) {
+                                               ST *stage, int lane, int part, int nparts,
+                                               SyncFn sync) {
     // everything the loops need, read once (O and B live in parameter space)
     const int H = B.H, W = B.W, vh = O.vh, vw = O.vw, vcells = vh * vw, C = O.n_channels;
     const int n_runs = O.n_runs;
@@ -125,7 +129,9 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
     auto stage_st = [&](int i, uint32_t m) { stage[i] = (ST)m; };
     auto stage_ld = [&](int i) -> uint32_t { return stage[i]; };
     uint32_t *out32 = (uint32_t *)O.obs + (size_t)e * vcells;
-    int sy0 = (y0 - vh / 2) % H;
+    // this warp's block of view rows [rb, re)
+    const int rb = (int)((long long)vh * part / nparts), re = (int)((long long)vh * (part + 1) / nparts);
+    int sy0 = (y0 - vh / 2 + rb) % H;
     if (sy0 < 0) sy0 += H;
     for (int c0 = 0; c0 < vw; c0 += 32) {
         const int c = c0 + lane;
@@ -133,8 +139,8 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
         if (sx < 0) sx += W;
         if (c < vw) {
             // rows in runs that end where the torus wraps: no per-row wrap test
-            int idx = sy0 * W + sx, o = c, r = 0, run = min(vh, H - sy0);
-            while (r < vh) {
+            int idx = sy0 * W + sx, o = rb * vw + c, r = rb, run = min(re - rb, H - sy0);
+            while (r < re) {
                 if (raw) {
                     for (int i = 0; i < run; i++, o += vw, idx += W) out32[o] = full_at(idx);
                 } else if (n_runs <= 4) {
@@ -145,15 +151,15 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
                 }
                 r += run;
                 idx = sx;                       // wrapped to source row 0
-                run = min(vh - r, H);
+                run = min(re - r, H);
             }
         }
     }
-    if (!raw) stage_st(vcells + lane, 0u);     // zero padding the expansion may touch
-    __syncwarp();
+    if (!raw && part == 0) stage_st(vcells + lane, 0u);     // zero padding the expansion may touch
+    sync();
     // exit cells outside the view are clamped onto its perimeter; in index order,
     // so that the last one wins where two collide (helper_utils.py:64-74)
-    if (lane == 0) {
+    if (lane == 0 && part == 0) {
         const int32_t *exits = B.pool_exits + (size_t)level_id * B.max_exits;
         const int max_exits = B.max_exits;
         for (int k = 0; k < max_exits; k++) {
@@ -169,7 +175,7 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
             else stage_st(jy * vw + jx, mask_of(v));
         }
     }
-    __syncwarp();
+    sync();
     if (raw) return;
     // expansion: output byte b of the env = bit (b % C) of cell (b / C)
     const int total = vcells * C;
@@ -182,57 +188,64 @@ __device__ __forceinline__ void warp_write_obs(const SlEnvBatch &B, const ObsPar
         const int cell = b / C;
         return (uint8_t)((stage_ld(cell) >> (b - cell * C)) & 1u);
     };
-    if (lane < head32) o[lane] = bit_at(lane);
-    {
+    if (part == 0) {
+        if (lane < head32) o[lane] = bit_at(lane);
         const int b = head32 + (nchunks << 5) + lane;      // fewer than 32 bytes are left over
         if (b < total) o[b] = bit_at(b);
     }
     uint4 *o16 = (uint4 *)(o + head32);
-    const int dcell = 1024 / C, dk = 1024 - dcell * C;     // 32 lanes x 32 bytes per round
-    int cell = (head32 + 32 * lane) / C, k = (head32 + 32 * lane) - cell * C;
-    if (C >= 11) {     // 32 stream bits span at most four cells
-#pragma unroll 2
-        for (int q = lane; q < nchunks; q += 32) {
-            const uint32_t a0 = stage_ld(cell), a1 = stage_ld(cell + 1), a2 = stage_ld(cell + 2),
-                           a3 = stage_ld(cell + 3);
-            const int nb = C - k;
-            const uint32_t bits = (a0 >> k) | shl_clamp(a1, nb) | shl_clamp(a2, nb + C) |
-                                  shl_clamp(a3, nb + 2 * C);
-            o16[2 * q] = expand16(bits);
-            o16[2 * q + 1] = expand16(bits >> 16);
-            cell += dcell;
-            k += dk;
-            if (k >= C) { k -= C; cell++; }
-        }
-    } else {
-        for (int q = lane; q < nchunks; q += 32) {
-            uint32_t bits = stage_ld(cell) >> k;
-            int nb = C - k, cc = cell + 1;
-            while (nb < 32) {
-                bits |= stage_ld(cc) << nb;
-                nb += C;
-                cc++;
+    // 32 lanes x 32 bytes per round, rounds dealt out over the parts
+    const int round_bytes = 1024 * nparts;
+    const int dcell = round_bytes / C, dk = round_bytes - dcell * C;
+    const int first = head32 + 32 * (32 * part + lane);
+    int cell = first / C, k = first - cell * C;
+    // Each lane gathers the 32 stream bits of its own 32-byte span; two shuffles then
+    // hand the 16-bit halves out so that each of the round's two store instructions
+    // covers 512 contiguous bytes (a lane storing its own two halves would leave every
+    // 32-byte sector half written by each instruction).
+    const int n16 = 2 * nchunks;
+    for (int q0 = 32 * part; q0 < nchunks; q0 += 32 * nparts) {
+        uint32_t bits = 0;
+        if (q0 + lane < nchunks) {
+            if (C >= 11) {     // 32 stream bits span at most four cells
+                const uint32_t a0 = stage_ld(cell), a1 = stage_ld(cell + 1), a2 = stage_ld(cell + 2),
+                               a3 = stage_ld(cell + 3);
+                const int nb = C - k;
+                bits = (a0 >> k) | shl_clamp(a1, nb) | shl_clamp(a2, nb + C) | shl_clamp(a3, nb + 2 * C);
+            } else {
+                bits = stage_ld(cell) >> k;
+                int nb = C - k, cc = cell + 1;
+                while (nb < 32) {
+                    bits |= stage_ld(cc) << nb;
+                    nb += C;
+                    cc++;
+                }
             }
-            o16[2 * q] = expand16(bits);
-            o16[2 * q + 1] = expand16(bits >> 16);
             cell += dcell;
             k += dk;
             if (k >= C) { k -= C; cell++; }
         }
+        const uint32_t v1 = __shfl_sync(0xffffffffu, bits, lane >> 1);
+        const uint32_t v2 = __shfl_sync(0xffffffffu, bits, 16 + (lane >> 1));
+        const int sh = (lane & 1) * 16, c1 = 2 * q0 + lane, c2 = c1 + 32;
+        if (c1 < n16) o16[c1] = expand16(v1 >> sh);
+        if (c2 < n16) o16[c2] = expand16(v2 >> sh);
     }
 }
 
 // The writer for the plane placement at hand, staging type by channel count.
-template <bool BSH, bool GSH>
+template <bool BSH, bool GSH, class SyncFn>
 __device__ __forceinline__ void warp_write_obs_any(const SlEnvBatch &B, const ObsParams &O, int e,
                                                    const SlEnvState *st, const uint16_t *board,
                                                    const uint16_t *goals, unsigned char *stage,
-                                                   int lane) {
+                                                   int lane, int part, int nparts, SyncFn sync) {
     const int row = st->loc_row, col = st->loc_col, lvl = st->level_id;
     if (O.n_channels <= 16)
-        warp_write_obs<uint16_t, BSH, GSH>(B, O, e, row, col, lvl, board, goals, (uint16_t *)stage, lane);
+        warp_write_obs<uint16_t, BSH, GSH>(B, O, e, row, col, lvl, board, goals, (uint16_t *)stage,
+                                           lane, part, nparts, sync);
     else
-        warp_write_obs<uint32_t, BSH, GSH>(B, O, e, row, col, lvl, board, goals, (uint32_t *)stage, lane);
+        warp_write_obs<uint32_t, BSH, GSH>(B, O, e, row, col, lvl, board, goals, (uint32_t *)stage,
+                                           lane, part, nparts, sync);
 }
 
 // Stand-alone SafeLifeEnv.get_obs: one warp per env, planes read from HBM.
@@ -246,7 +259,8 @@ k_get_obs_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Obs
     unsigned char *stage = smem_raw + (size_t)warp * obs_stage_bytes(O.vh, O.vw, O.n_channels);
     for (int e = blockIdx.x * OBS_WARPS + warp; e < B.n_envs; e += gridDim.x * OBS_WARPS) {
         warp_write_obs_any<false, false>(B, O, e, B.state + e, B.board + (size_t)e * cells,
-                                         B.goals + (size_t)e * cells, stage, lane);
+                                         B.goals + (size_t)e * cells, stage, lane, 0, 1,
+                                         [] { __syncwarp(); });
         __syncwarp();
     }
 }

@@ -1,0 +1,432 @@
+// tile_kernels.cuh -- boards beyond 32x32: several warps per env.
+//
+// A board is cut into TR x TC tiles of at most 30 x 30 interior cells; one warp
+// owns one tile.  Lane l of the warp holds board row r0 - 1 + l as ONE 32-bit
+// word whose bit j is column c0 - 1 + j: lanes 1..hr / bits 1..wc are the tile's
+// interior, lane 0 / lane hr + 1 and bit 0 / bit wc + 1 a halo ring read (with
+// the torus wrap) from the neighbouring tiles' cells in the shared-memory slab.
+// Inside a tile the 3x3 aggregate of advance_board.c:34-125 needs no wrap logic
+// at all -- horizontal neighbours are plain shifts, vertical ones come from the
+// adjacent lanes -- and no exchange with other warps: every warp transposes its
+// own halo.  Compared with one warp per env on 64-bit rows (two rows per lane)
+// this halves the registers per thread, spreads the per-changed-cell loops of a
+// busy board (navigation: dozens of changes per step) over four times as many
+// lanes, and lets the warps of one env run concurrently.
+//
+// What the warps of an env do share goes through a few bytes of shared memory
+// and named barriers (one barrier id per env of the CTA):
+//   * the reference's raster-order spawn draws (advance_board.c:115): every tile
+//     publishes its candidate count per row; a candidate's draw index is the
+//     number of candidates in earlier rows, plus those of the same row in tiles
+//     to its left, plus its rank in its own word.  Every warp then runs the
+//     (cheap) PCG64 leapfrog over ALL draws of the board and keeps the outcomes
+//     of its own candidates, so no outcome has to travel;
+//   * the change of sum(points_table * alive_counts), added up with one shared
+//     atomic per warp;
+//   * "did the goals change" for GameWithGoals._static_goals.
+// The scalar tail of the step, the wrapper epilogue and a reset are run by the
+// env's first warp (the shared code of warp_kernels.cuh); the observation is
+// written by all of them, rows of the view dealt out round-robin.
+#pragma once
+#include <cuda_runtime.h>
+#include "cells.cuh"
+#include "generic_kernels.cuh"
+#include "obs.cuh"
+#include "wrap.cuh"
+#include "warp_kernels.cuh"
+
+namespace sl {
+
+constexpr int TILE_DIM = 30;            // interior rows / columns of one tile
+constexpr int TILE_MAX_WARPS = 16;      // warps of one env (4 x 4 tiles: boards up to 120 x 120)
+constexpr int TILE_CTA_WARPS = 8;       // target CTA size in warps
+
+struct TileShape {
+    int TR, TC, TW;      // tile rows, tile columns, warps per env
+    int epc;             // envs per CTA
+};
+
+__host__ __device__ inline TileShape tile_shape(int H, int W) {
+    TileShape s;
+    s.TR = (H + TILE_DIM - 1) / TILE_DIM;
+    s.TC = (W + TILE_DIM - 1) / TILE_DIM;
+    s.TW = s.TR * s.TC;
+    s.epc = s.TW >= TILE_CTA_WARPS ? 1 : TILE_CTA_WARPS / s.TW;
+    return s;
+}
+
+inline bool tile_kernel_supports(int H, int W) {
+    if (H < 3 || W < 3) return false;
+    const TileShape s = tile_shape(H, W);
+    return s.TW <= TILE_MAX_WARPS && s.epc <= 15;     // named barriers 1..15
+}
+
+// Extent of part `i` of `n` when `len` cells are dealt out as evenly as possible.
+__host__ __device__ inline void tile_span(int len, int n, int i, int *begin, int *size) {
+    const int base = len / n, extra = len % n;
+    *begin = i * base + (i < extra ? i : extra);
+    *size = base + (i < extra ? 1 : 0);
+}
+
+struct Tile {
+    typedef uint32_t P;
+    int H, W, lane;
+    int r0, hr, c0, wc;        // interior origin and extent
+    int y;                     // board row this lane holds (wrapped; any valid row for idle lanes)
+    uint32_t imask;            // interior bits of this lane's word
+    bool seam_l, seam_r;       // the left / right halo column wraps around the torus
+
+    __device__ __forceinline__ Tile(int H_, int W_, int TR, int TC, int tile, int lane_)
+        : H(H_), W(W_), lane(lane_) {
+        tile_span(H, TR, tile / TC, &r0, &hr);
+        tile_span(W, TC, tile % TC, &c0, &wc);
+        int yy = r0 - 1 + lane;
+        if (lane > hr + 1) yy = r0;
+        y = yy < 0 ? yy + H : (yy >= H ? yy - H : yy);
+        imask = (lane >= 1 && lane <= hr) ? (((1u << wc) - 1u) << 1) : 0u;
+        seam_l = c0 == 0;
+        seam_r = c0 + wc == W;
+    }
+    __device__ __forceinline__ P mask() const { return imask; }
+    __device__ __forceinline__ P west(P x) const { return x << 1; }
+    __device__ __forceinline__ P east(P x) const { return x >> 1; }
+    __device__ __forceinline__ P north(P x) const { return __shfl_up_sync(FULL, x, 1); }
+    __device__ __forceinline__ P south(P x) const { return __shfl_down_sync(FULL, x, 1); }
+    // flat index of the cell behind bit j of this lane's word
+    __device__ __forceinline__ int cell_base() const { return y * W + c0 - 1; }
+
+    // halo bits of the plane of cell bit `bit` from the two wrap cells of the row
+    __device__ __forceinline__ uint32_t fix(uint32_t x, uint32_t vl, uint32_t vr, int bit) const {
+        if (seam_l) x = (x & ~1u) | ((vl >> bit) & 1u);
+        if (seam_r) x = (x & ~(1u << (wc + 1))) | (((vr >> bit) & 1u) << (wc + 1));
+        return x;
+    }
+    __device__ __forceinline__ LowPlanesT<P> load_low(const uint16_t *slab) const {
+        const uint16_t *row = slab + y * W;
+        uint32_t x[8];
+        planes32<0x6240>(row + c0 - 1, x);
+        const uint32_t vl = seam_l ? row[W - 1] : 0u, vr = seam_r ? row[0] : 0u;
+        return {fix(x[0], vl, vr, 0), fix(x[3], vl, vr, 3), x[4], fix(x[5], vl, vr, 5),
+                fix(x[6], vl, vr, 6), fix(x[7], vl, vr, 7)};      // FROZEN matters for the own cell only
+    }
+    __device__ __forceinline__ HighPlanesT<P> load_high(const uint16_t *slab) const {
+        const uint16_t *row = slab + y * W;
+        uint32_t x[8];
+        planes32<0x7351>(row + c0 - 1, x);
+        const uint32_t vl = seam_l ? row[W - 1] : 0u, vr = seam_r ? row[0] : 0u;
+        return {fix(x[0], vl, vr, 8), fix(x[1], vl, vr, 9), fix(x[2], vl, vr, 10), fix(x[3], vl, vr, 11)};
+    }
+};
+
+// ---- what the warps of one env share ------------------------------------------
+struct TileSync {
+    uint8_t cand[TILE_MAX_WARPS][32];   // spawn candidates per tile and lane (row)
+    int delta;                          // change of sum(table * alive_counts)
+    int goal_flags;                     // 1: some goal cell changed, 2: a spawner is left in the goals
+    int pad[2];
+};
+
+__device__ __forceinline__ void env_barrier(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// Draw indices of this warp's candidates.  `cnt`: candidates in this lane's word;
+// returns the index of its first one, *total = all candidates of the board.
+__device__ __forceinline__ int tile_draw_offsets(const TileSync *sy, const TileShape &sh, int tile,
+                                                 int lane, int cnt, int *total) {
+    const int tr = tile / sh.TC, tc = tile % sh.TC;
+    int row_tot = 0, left = 0, earlier = 0, all = 0;
+    for (int t = 0; t < sh.TW; t++) {
+        const int c = sy->cand[t][lane];
+        all += c;
+        if (t / sh.TC == tr) {
+            row_tot += c;
+            if (t % sh.TC < tc) left += c;
+        } else if (t / sh.TC < tr) {
+            earlier += c;
+        }
+    }
+    int incl = row_tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += v;
+    }
+    (void)cnt;
+    *total = __reduce_add_sync(FULL, all);
+    return __reduce_add_sync(FULL, earlier) + incl - row_tot + left;
+}
+
+// Outcomes of this warp's candidates out of the board's `total` draws (every warp
+// of the env runs all rounds; see the header).  The state advances by `total`.
+__device__ __forceinline__ uint32_t tile_spawn_draws(u128 &state, const SpawnCtx &ctx, uint64_t thr,
+                                                     uint32_t cand, int next, int total) {
+    uint32_t todo = cand, got = 0;
+    for (int base = 0; base < total; base += 32) {
+        const u128 sn = add128(mul128(ctx.la, state), ctx.ginc);   // state after lane + 1 more steps
+        const uint32_t ok = __ballot_sync(FULL, (pcg_output(sn) >> 11) < thr);
+        while (todo != 0 && next < base + 32) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            got |= ((ok >> (next - base)) & 1u) << j;
+            next++;
+        }
+        const int last = min(31, total - base - 1);
+        state.hi = __shfl_sync(FULL, sn.hi, last);
+        state.lo = __shfl_sync(FULL, sn.lo, last);
+    }
+    return got;
+}
+
+// Points of a cell that the rule just changed, against the goal cell under it:
+// such a cell is never FROZEN before or after, so it is always counted
+// (advance_board.c:192-207) and only its colour column matters.
+__device__ __forceinline__ int changed_cell_points(uint32_t now, uint32_t before, uint32_t goal,
+                                                   const int32_t *table, bool dead_counts) {
+    const int g9 = (int)((goal & COLORS) >> COLOR_SHIFT) * 9;
+    int d = 0;
+    if (now & ALIVE) d += table[g9 + ((now & COLORS) >> COLOR_SHIFT)];
+    else if (dead_counts) d += table[g9 + 8];
+    if (before & ALIVE) d -= table[g9 + ((before & COLORS) >> COLOR_SHIFT)];
+    else if (dead_counts) d -= table[g9 + 8];
+    return d;
+}
+
+// Write this tile's changed board cells back into the slab; returns what they add
+// to sum(table * alive_counts), priced with the goals as they are in `goals`.
+__device__ __forceinline__ int tile_apply_board(const Tile &t, const RowDeltaT<uint32_t> &d,
+                                                uint32_t spawned, uint16_t *board,
+                                                const uint16_t *goals, const int32_t *table,
+                                                bool dead_counts) {
+    const uint32_t fresh = d.born | spawned, destr = (d.dn & d.born) | spawned;
+    uint32_t m = d.die | fresh;
+    const int base = t.cell_base();
+    int delta = 0;
+    while (m != 0) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t v = fresh_cell(fresh, destr, d.tR, d.tG, d.tB, j);
+        delta += changed_cell_points(v, board[base + j], goals[base + j], table, dead_counts);
+        board[base + j] = (uint16_t)v;
+    }
+    return delta;
+}
+
+// The same for the goals plane; a goal cell whose colour changes re-prices the
+// board cell on top of it (`board` is already the new board).
+__device__ __forceinline__ int tile_apply_goals(const Tile &t, const RowDeltaT<uint32_t> &d,
+                                                uint32_t spawned, uint16_t *goals,
+                                                const uint16_t *board, const int32_t *table,
+                                                bool dead_counts) {
+    const uint32_t fresh = d.born | spawned, destr = (d.dn & d.born) | spawned;
+    uint32_t m = d.die | fresh;
+    const int base = t.cell_base();
+    int delta = 0;
+    while (m != 0) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t v = fresh_cell(fresh, destr, d.tR, d.tG, d.tB, j);
+        const uint32_t old = goals[base + j];
+        if ((old ^ v) & COLORS) {
+            const uint32_t cell = board[base + j];
+            delta += cell_points(cell, v, table, dead_counts) - cell_points(cell, old, table, dead_counts);
+        }
+        goals[base + j] = (uint16_t)v;
+    }
+    return delta;
+}
+
+// ---- shared memory of the tiled step kernel -------------------------------------
+constexpr int TILE_SMEM_HEAD = 32;      // two mbarriers
+
+__host__ __device__ inline int tile_group_stride(int epc, int cells) { return (epc * cells * 2 + 15) & ~15; }
+__host__ __device__ inline size_t tile_step_smem_bytes(int H, int W, int obs_stage) {
+    const TileShape sh = tile_shape(H, W);
+    const size_t sync = ((size_t)sh.epc * sizeof(TileSync) + 15) & ~(size_t)15;
+    return TILE_SMEM_HEAD + WARP_SMEM_TABLE + sync + (size_t)sh.epc * 96 +
+           2 * (size_t)tile_group_stride(sh.epc, H * W) + 256 + (size_t)sh.epc * obs_stage;
+}
+
+// Observation of one env by the TW warps of the env (obs.cuh): blocks of view rows
+// for the gather, then, after an env barrier, rounds of output bytes.
+__device__ __noinline__ void tile_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
+                                            const SlEnvState *st, const uint16_t *board,
+                                            const uint16_t *goals, unsigned char *stage, int part,
+                                            int nparts, int bar_id, int env_threads, int lane) {
+    warp_write_obs_any<true, true>(B, O, e, st, board, goals, stage, lane, part, nparts,
+                                   [&] { env_barrier(bar_id, env_threads); });
+}
+
+// SafeLifeEnv.step (safelife_env.py:148-201), tiled: TW warps per env, epc envs per CTA.
+__global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 2)      // 64 registers: four 8-warp CTAs per SM
+k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
+                const __grid_constant__ SlWrapSpec Wp, const uint8_t *__restrict__ actions,
+                int bulk_ok, int flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int H = B.H, W = B.W, cells = H * W;
+    const TileShape sh = tile_shape(H, W);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int es = warp / sh.TW, tile = warp - es * sh.TW;       // env slot of the CTA, tile of the env
+    const int e0 = blockIdx.x * sh.epc;
+    const int nenv = min(sh.epc, B.n_envs - e0);
+    const int e = e0 + es;
+    const int group_bytes = nenv * cells * 2, state_bytes = nenv * 96;
+    const int env_threads = sh.TW * 32, bar_id = 1 + es;
+
+    uint64_t *bar = (uint64_t *)smem_raw;                   // [0] state + boards, [1] goals
+    int32_t *stable = (int32_t *)(smem_raw + TILE_SMEM_HEAD);
+    TileSync *sync_all = (TileSync *)(smem_raw + TILE_SMEM_HEAD + WARP_SMEM_TABLE);
+    const size_t sync_bytes = ((size_t)sh.epc * sizeof(TileSync) + 15) & ~(size_t)15;
+    SlEnvState *sstate = (SlEnvState *)((unsigned char *)sync_all + sync_bytes);
+    uint16_t *sboard = (uint16_t *)((unsigned char *)sstate + sh.epc * 96);
+    uint16_t *sgoals = sboard + tile_group_stride(sh.epc, cells) / 2;
+    uint16_t *gboard = B.board + (size_t)e0 * cells;
+    uint16_t *ggoals = B.goals + (size_t)e0 * cells;
+    SlEnvState *gstate = B.state + e0;
+    const bool bulk = bulk_ok && (group_bytes & 15) == 0;
+
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            mbar_init(bar, 1);
+            mbar_init(bar + 1, 1);
+            mbar_expect_tx(bar, (uint32_t)(group_bytes + state_bytes));
+            bulk_load(sstate, gstate, state_bytes, bar);
+            bulk_load(sboard, gboard, group_bytes, bar);
+            mbar_expect_tx(bar + 1, (uint32_t)group_bytes);
+            bulk_load(sgoals, ggoals, group_bytes, bar + 1);
+        }
+    } else {
+        copy_slabs(sstate, gstate, state_bytes);
+        copy_slabs(sboard, gboard, group_bytes);
+        copy_slabs(sgoals, ggoals, group_bytes);
+    }
+    CtaShared cs;
+    cs.scratch = nullptr;
+    cs.lock = nullptr;
+    cs.table = stage_table(B, stable);
+    if (tile == 0 && lane == 0 && es < sh.epc) {
+        sync_all[es].delta = 0;
+        sync_all[es].goal_flags = 0;
+    }
+    __syncthreads();                      // mbarrier init / fallback copy / table / sync records
+    if (bulk) mbar_wait(bar, 0);
+
+    bool goals_dirty = false;
+    if (es < nenv) {
+        TileSync *sy = sync_all + es;
+        SlEnvState *st = sstate + es;
+        uint16_t *board = sboard + es * cells, *goals = sgoals + es * cells;
+        const Tile t(H, W, sh.TR, sh.TC, tile, lane);
+        const uint64_t thr = st->spawn_thr;
+        u128 state = {st->rng[0], st->rng[1]};
+        const u128 inc = {st->rng[2], st->rng[3]};
+        const uint64_t state_lo0 = state.lo;
+        int sg = st->static_goals;
+        const int32_t *table = cs.table ? cs.table : B.pool_table + (size_t)st->level_id * 72;
+        const bool dead_counts = st->empty_points != 0;
+        const SpawnCtx ctx = make_spawn_ctx(lane, inc);
+        int delta = 0;
+
+        // execute_actions (advance_board.c:217-300) by the env's first warp: lane 0
+        // acts, lanes 0-3 account for the (at most four) cells it can touch
+        uint32_t before = 0, after = 0;
+        int idx = 0;
+        if (tile == 0) {
+            int row = st->loc_row, col = st->loc_col;
+            const int action = actions[e];
+            if (row >= 0 && action != 0) {
+                const ActionCells ac = action_cells(H, W, row, col, action);
+                idx = lane == 0 ? ac.i0 : (lane == 1 ? ac.i1 : (lane == 2 ? ac.i2 : ac.i3));
+                const bool mine = lane < 4 && !(lane == 3 && ac.i3 == ac.i2);
+                if (mine) before = board[idx];
+                __syncwarp();
+                if (lane == 0) {
+                    agent_action_at(board, ac, row, col, action);
+                    st->loc_row = row;
+                    st->loc_col = col;
+                }
+                __syncwarp();
+                after = mine ? board[idx] : 0u;
+            }
+        }
+        env_barrier(bar_id, env_threads);              // the board as the agent left it
+
+        // advance_board on the tile
+        {
+            const LowPlanesT<uint32_t> p = t.load_low(board);
+            const RowDeltaT<uint32_t> d = stencil_planes(t, p, [&] { return t.load_high(board); });
+            sy->cand[tile][lane] = (uint8_t)__popc(d.cand);
+            if (bulk) mbar_wait(bar + 1, 0);            // goal slabs: needed for pricing from here on
+            env_barrier(bar_id, env_threads);          // counts published; every warp has read the slab
+            int total;
+            const int next = tile_draw_offsets(sy, sh, tile, lane, 0, &total);
+            const uint32_t spawned = total ? tile_spawn_draws(state, ctx, thr, d.cand, next, total) : 0u;
+            delta += tile_apply_board(t, d, spawned, board, goals, table, dead_counts);
+        }
+        if (after != before)
+            delta += cell_points(after, goals[idx], table, dead_counts) -
+                     cell_points(before, goals[idx], table, dead_counts);
+        if (sg != 1) {   // goals advance from the same stream (safelife_game.py:753-761)
+            const LowPlanesT<uint32_t> gp = t.load_low(goals);
+            const RowDeltaT<uint32_t> gd = stencil_planes(t, gp, [&] { return t.load_high(goals); });
+            env_barrier(bar_id, env_threads);          // the draws of the board have been consumed
+            sy->cand[tile][lane] = (uint8_t)__popc(gd.cand);
+            env_barrier(bar_id, env_threads);          // goal planes read and board priced everywhere
+            int total;
+            const int next = tile_draw_offsets(sy, sh, tile, lane, 0, &total);
+            const uint32_t gspawned = total ? tile_spawn_draws(state, ctx, thr, gd.cand, next, total) : 0u;
+            delta += tile_apply_goals(t, gd, gspawned, goals, board, table, dead_counts);
+            const uint32_t gchanged = gd.die | gd.born | gspawned;
+            const bool any_changed = __any_sync(FULL, gchanged != 0);
+            const bool spawner_left = __any_sync(FULL, (gp.S & t.imask & ~gchanged) != 0);
+            if (lane == 0 && (any_changed || spawner_left))
+                atomicOr(&sy->goal_flags, (any_changed ? 1 : 0) | (spawner_left ? 2 : 0));
+        }
+        delta = __reduce_add_sync(FULL, delta);
+        if (lane == 0 && delta != 0) atomicAdd(&sy->delta, delta);
+        env_barrier(bar_id, env_threads);              // every tile applied and accounted for
+
+        if (tile == 0) {
+            // scalar tail, wrapper epilogue and reset by the env's first warp
+            if (lane == 0) {
+                st->count_points += sy->delta;
+                if (sg != 1) {
+                    // static iff nothing changed and no spawner is left (safelife_game.py:756-760)
+                    if (sg == 0) sg = sy->goal_flags ? 2 : 1;
+                    st->static_goals = (uint8_t)sg;
+                }
+                if (state.lo != state_lo0) {   // the LCG is a bijection: lo changes iff draws happened
+                    st->rng[0] = state.hi;
+                    st->rng[1] = state.lo;
+                }
+            }
+            goals_dirty = (sg != 1) && (sy->goal_flags & 1);
+            goals_dirty |= step_tail_env(B, Wp, cs, e, st, board, goals, flags, lane);
+        }
+        if (O.obs != nullptr) {
+            env_barrier(bar_id, env_threads);          // the board as the step leaves it
+            // the view rows / output chunks of the env dealt out over its warps
+            const int stage_bytes = obs_stage_bytes(O.vh, O.vw, O.n_channels);
+            unsigned char *stage = smem_raw + tile_step_smem_bytes(H, W, 0) + (size_t)es * stage_bytes;
+            tile_write_obs(B, O, e, st, board, goals, stage, tile, sh.TW, bar_id, env_threads, lane);
+        }
+    } else if (bulk) {
+        mbar_wait(bar + 1, 0);
+    }
+    fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
+    const int any_goals_dirty = __syncthreads_or(goals_dirty);
+    if (bulk) {
+        if (threadIdx.x == 0) {
+            bulk_store(gboard, sboard, group_bytes);
+            if (any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
+            bulk_store(gstate, sstate, state_bytes);
+            bulk_commit_and_wait_read();
+        }
+    } else {
+        copy_slabs(gboard, sboard, group_bytes);
+        if (any_goals_dirty) copy_slabs(ggoals, sgoals, group_bytes);
+        copy_slabs(gstate, sstate, state_bytes);
+    }
+}
+
+}  // namespace sl

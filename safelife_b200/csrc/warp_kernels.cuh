@@ -315,7 +315,7 @@ __device__ __forceinline__ RowDeltaT<typename G::P> stencil_planes(
 
     P any_p = any3x3(t, p.P_), any_i = any3x3(t, p.I), any_s = any3x3(t, p.S);
     RowDeltaT<P> d;
-    d.die = p.A & ~(p.F | any_p | is3 | is4);
+    d.die = p.A & ~(p.F | any_p | is3 | is4) & t.mask();   // (tiles carry halo cells in their planes)
     P open = ~p.A & ~p.F & ~any_i & t.mask();   // dead, not frozen, not inhibited
     d.born = open & is3;
     d.cand = open & ~is3 & any_s;
@@ -850,7 +850,7 @@ template <bool GR>
 __device__ __noinline__ void step_write_obs(const SlEnvBatch &B, const ObsParams &O, int e,
                                             const SlEnvState *st, const uint16_t *board,
                                             const uint16_t *goals, unsigned char *stage, int lane) {
-    warp_write_obs_any<true, GR>(B, O, e, st, board, goals, stage, lane);
+    warp_write_obs_any<true, GR>(B, O, e, st, board, goals, stage, lane, 0, 1, [] { __syncwarp(); });
 }
 
 // SafeLifeEnv.step, one warp per env (safelife_env.py:148-201): single-pass

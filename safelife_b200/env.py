@@ -460,6 +460,76 @@ class BatchedSafeLifeEnv(object):
             _lib.check(status)
         return h["reward"], h["done"]
 
+    # ---- host-driven loops with several groups of envs in flight -----------------
+    def enable_host_groups(self, groups=2):
+        """
+        Split the batch into `groups` contiguous groups that step independently, each
+        on a stream of its own, for host-side policies: while the host reads the
+        results of one group and chooses its next actions, the device steps another
+        (the asynchronous mode of vectorised env libraries).  Returns a list of dicts
+        of numpy views (actions, reward, done, success, times_up) into pinned host
+        memory, one per group; use host_submit(g) / host_wait(g).  Until
+        host_sync_groups() the other methods of the env must not be used.
+        """
+        if getattr(self, "_host", None) is None:
+            self.enable_host_io()
+        n = self.num_envs
+        if groups < 1 or n % (8 * groups) != 0:
+            raise ValueError("num_envs must be a multiple of 8 * groups")
+        per = n // groups
+        cells = self.pool.H * self.pool.W
+        self._flags = torch.zeros(16 * groups, dtype=torch.int32).pin_memory()
+        self._groups = []
+        with torch.cuda.device(self.device):
+            for g in range(groups):
+                lo = g * per
+                fields = {name: getattr(self._batch_host, name) for name, _ in _lib.SlEnvBatch._fields_}
+                fields["n_envs"] = per
+                fields["board"] += lo * cells * 2
+                fields["goals"] += lo * cells * 2
+                fields["state"] += lo * 96
+                fields["reward"] += lo * 4
+                for k in ("done", "success", "times_up"):
+                    fields[k] += lo
+                batch = _lib.SlEnvBatch(**fields)
+                stream = torch.cuda.Stream(device=self.device)
+                self._groups.append({
+                    "batch": batch, "ref": ctypes.byref(batch), "stream": stream,
+                    "stream_ptr": ctypes.c_void_p(stream.cuda_stream), "seq": 0,
+                    "flag": self._flags.data_ptr() + 64 * g,
+                    "actions_ptr": self._host_actions_ptr + lo,
+                    "views": {k: v[lo:lo + per] for k, v in self._host_np.items()},
+                })
+                stream.wait_stream(torch.cuda.current_stream(self.device))
+        return [g["views"] for g in self._groups]
+
+    def host_submit(self, g, actions=None, auto_reset=None):
+        """Launch one step of group g (actions: array-like [N / groups], or already in the view)."""
+        grp = self._groups[g]
+        if actions is not None:
+            np.copyto(grp["views"]["actions"], actions, casting="unsafe")
+        auto = self.auto_reset if auto_reset is None else auto_reset
+        grp["seq"] = (grp["seq"] + 1) & 0x7fffffff
+        status = self._lib.sl_env_step_submit(grp["ref"], grp["actions_ptr"], self.kernel,
+                                              _lib.SL_STEP_AUTO_RESET if auto else 0,
+                                              grp["stream_ptr"], grp["flag"], grp["seq"])
+        if status:
+            _lib.check(status)
+
+    def host_wait(self, g):
+        """Wait for the step of group g; returns its (reward, done) numpy views."""
+        grp = self._groups[g]
+        status = self._lib.sl_host_wait(grp["flag"], grp["seq"], grp["stream_ptr"])
+        if status:
+            _lib.check(status)
+        return grp["views"]["reward"], grp["views"]["done"]
+
+    def host_sync_groups(self):
+        """Drain every group's stream; afterwards the env can be used as a whole again."""
+        for grp in getattr(self, "_groups", []):
+            grp["stream"].synchronize()
+            torch.cuda.current_stream(self.device).wait_stream(grp["stream"])
+
     def step(self, actions, obs_out=None):
         """
         SafeLifeEnv.step for every env: ONE launch writes the new state, reward / done
