@@ -570,3 +570,36 @@ def test_step_host_reports_timing_and_both_wait_modes():
         out = ref.step_physics(a, auto_reset=True)
         assert np.array_equal(r, out["reward"].cpu().numpy()) and np.array_equal(d, out["done"].cpu().numpy())
         assert timing[0] > 0 and timing[1] >= 0
+
+
+def test_host_groups_pipeline_matches_whole_batch_steps():
+    """enable_host_groups: two half batches stepping on their own streams give exactly the
+    results of whole-batch steps with the same actions."""
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(29)
+    levels = _random_levels(rs, 8, 25, 25)
+    n, T = 128, 25
+    a = BatchedSafeLifeEnv(levels, n, time_limit=11, auto_reset=True, seed=3)
+    b = BatchedSafeLifeEnv(levels, n, time_limit=11, auto_reset=True, seed=3)
+    b.set_rng_state(a.rng_state)
+    a.reset()
+    b.reset()
+    views = a.enable_host_groups(2)
+    assert len(views) == 2 and views[1]["reward"].shape == (n // 2,)
+    acts = rs.integers(0, 9, (T, n)).astype(np.uint8)
+    half = n // 2
+    for g in range(2):
+        a.host_submit(g, acts[0][g * half:(g + 1) * half])
+    for t in range(T):
+        out = b.step_physics(acts[t], auto_reset=True)
+        want_r, want_d = out["reward"].cpu().numpy(), out["done"].cpu().numpy()
+        for g in range(2):
+            r, d = a.host_wait(g)
+            assert np.array_equal(r, want_r[g * half:(g + 1) * half]), (t, g)
+            assert np.array_equal(d, want_d[g * half:(g + 1) * half]), (t, g)
+            if t + 1 < T:
+                a.host_submit(g, acts[t + 1][g * half:(g + 1) * half])
+    a.host_sync_groups()
+    assert np.array_equal(a.board.cpu().numpy(), b.board.cpu().numpy())
+    with pytest.raises(ValueError):
+        a.enable_host_groups(3)
