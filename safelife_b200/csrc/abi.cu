@@ -563,12 +563,12 @@ static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const 
         static const SlWrapSpec no_wrap = {};
         const sl::TileShape sh = sl::tile_shape(batch->H, batch->W);
         const int stage = obs ? sl::obs_stage_bytes(O.vh, O.vw, O.n_channels) : 0;
-        const size_t smem = sl::tile_step_smem_bytes(batch->H, batch->W, stage);
+        const size_t smem = sl::tile_step_smem_bytes(sh.epc, batch->H * batch->W, stage);
         rc = prepare_smem(sl::k_env_step_tile, smem);
         if (rc) return rc;
         const int bulk_ok = (((uintptr_t)batch->board | (uintptr_t)batch->goals | (uintptr_t)batch->state) & 15) == 0;
         sl::k_env_step_tile<<<(batch->n_envs + sh.epc - 1) / sh.epc, sh.epc * sh.TW * 32, smem, st>>>(
-            *batch, obs ? O : no_obs, wrap ? *wrap : no_wrap, actions, bulk_ok, flags);
+            *batch, obs ? O : no_obs, wrap ? *wrap : no_wrap, sh, actions, bulk_ok, flags);
         return launch_status("k_env_step_tile");
     }
     if (kernel == 2 || (kernel == 0 && warp_ok)) {

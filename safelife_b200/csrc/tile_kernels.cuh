@@ -41,51 +41,83 @@ constexpr int TILE_DIM = 30;            // interior rows / columns of one tile
 constexpr int TILE_MAX_WARPS = 16;      // warps of one env (4 x 4 tiles: boards up to 120 x 120)
 constexpr int TILE_CTA_WARPS = 8;       // target CTA size in warps
 
-struct TileShape {
-    int TR, TC, TW;      // tile rows, tile columns, warps per env
-    int epc;             // envs per CTA
+// Shape of the tiling, computed once on the host (the kernels never divide).
+struct TileParams {
+    int32_t TR, TC, TW;      // tile rows, tile columns, warps per env
+    int32_t epc;             // envs per CTA
+    int16_t row_begin[6], col_begin[6];     // first interior row / column of each tile row / column, + end
+    uint8_t env_of_warp[TILE_MAX_WARPS], tile_of_warp[TILE_MAX_WARPS];
+    uint8_t tr_of_tile[TILE_MAX_WARPS], tc_of_tile[TILE_MAX_WARPS];
 };
+typedef TileParams TileShape;
 
-__host__ __device__ inline TileShape tile_shape(int H, int W) {
-    TileShape s;
+inline TileParams tile_shape(int H, int W) {
+    TileParams s = {};
     s.TR = (H + TILE_DIM - 1) / TILE_DIM;
     s.TC = (W + TILE_DIM - 1) / TILE_DIM;
     s.TW = s.TR * s.TC;
     s.epc = s.TW >= TILE_CTA_WARPS ? 1 : TILE_CTA_WARPS / s.TW;
+    if (s.TR > 4 || s.TC > 4) return s;          // not supported (see tile_kernel_supports)
+    for (int i = 0; i <= s.TR; i++) s.row_begin[i] = (int16_t)(i * (H / s.TR) + (i < H % s.TR ? i : H % s.TR));
+    for (int i = 0; i <= s.TC; i++) s.col_begin[i] = (int16_t)(i * (W / s.TC) + (i < W % s.TC ? i : W % s.TC));
+    for (int w = 0; w < TILE_MAX_WARPS; w++) {
+        s.env_of_warp[w] = (uint8_t)(w / s.TW);
+        s.tile_of_warp[w] = (uint8_t)(w % s.TW);
+        s.tr_of_tile[w] = (uint8_t)(w / s.TC);
+        s.tc_of_tile[w] = (uint8_t)(w % s.TC);
+    }
     return s;
 }
 
 inline bool tile_kernel_supports(int H, int W) {
     if (H < 3 || W < 3) return false;
-    const TileShape s = tile_shape(H, W);
-    return s.TW <= TILE_MAX_WARPS && s.epc <= 15;     // named barriers 1..15
+    const int TR = (H + TILE_DIM - 1) / TILE_DIM, TC = (W + TILE_DIM - 1) / TILE_DIM;
+    return TR <= 4 && TC <= 4;                    // at most 16 warps per env, boards up to 120 x 120
 }
 
-// Extent of part `i` of `n` when `len` cells are dealt out as evenly as possible.
-__host__ __device__ inline void tile_span(int len, int n, int i, int *begin, int *size) {
-    const int base = len / n, extra = len % n;
-    *begin = i * base + (i < extra ? i : extra);
-    *size = base + (i < extra ? 1 : 0);
+// Planes of one byte of 32 cells (see planes32) whose first and last cell come from
+// elsewhere: the halo columns of a tile that wrap around the torus.
+template <unsigned SEL>
+__device__ __forceinline__ void planes32_ends(const uint16_t *cells, const uint16_t *first,
+                                              const uint16_t *last, uint32_t (&x)[8]) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t a = pack16(k == 0 ? *first : cells[k], cells[k + 16]);
+        const uint32_t b = pack16(cells[k + 8], k == 7 ? *last : cells[k + 24]);
+        x[k] = __byte_perm(a, b, SEL);
+    }
+    transpose8(x);
 }
 
+// One tile.  The 32-cell window of a lane starts `boff` cells left of the tile's
+// first interior column: boff = 1 (left halo in bit 0) unless only the RIGHT halo
+// column wraps around the torus, in which case the window is right-aligned (right
+// halo in bit 31).  Either way a wrapping halo cell sits at a fixed end of the
+// window and is fetched by address (planes32_ends); only a board of a single tile
+// column (both halos wrap) patches its right halo bit by bit.
 struct Tile {
     typedef uint32_t P;
     int H, W, lane;
-    int r0, hr, c0, wc;        // interior origin and extent
+    int r0, hr, c0, wc, boff;
     int y;                     // board row this lane holds (wrapped; any valid row for idle lanes)
     uint32_t imask;            // interior bits of this lane's word
-    bool seam_l, seam_r;       // the left / right halo column wraps around the torus
+    bool seam_l, seam_r, patch_r;
 
-    __device__ __forceinline__ Tile(int H_, int W_, int TR, int TC, int tile, int lane_)
+    __device__ __forceinline__ Tile(int H_, int W_, const TileParams &tp, int tile, int lane_)
         : H(H_), W(W_), lane(lane_) {
-        tile_span(H, TR, tile / TC, &r0, &hr);
-        tile_span(W, TC, tile % TC, &c0, &wc);
+        const int tr = tp.tr_of_tile[tile], tc = tp.tc_of_tile[tile];
+        r0 = tp.row_begin[tr];
+        hr = tp.row_begin[tr + 1] - r0;
+        c0 = tp.col_begin[tc];
+        wc = tp.col_begin[tc + 1] - c0;
+        seam_l = c0 == 0;
+        seam_r = c0 + wc == W;
+        boff = (seam_r && !seam_l) ? 31 - wc : 1;
+        patch_r = seam_r && seam_l;
         int yy = r0 - 1 + lane;
         if (lane > hr + 1) yy = r0;
         y = yy < 0 ? yy + H : (yy >= H ? yy - H : yy);
-        imask = (lane >= 1 && lane <= hr) ? (((1u << wc) - 1u) << 1) : 0u;
-        seam_l = c0 == 0;
-        seam_r = c0 + wc == W;
+        imask = (lane >= 1 && lane <= hr) ? (((1u << wc) - 1u) << boff) : 0u;
     }
     __device__ __forceinline__ P mask() const { return imask; }
     __device__ __forceinline__ P west(P x) const { return x << 1; }
@@ -93,28 +125,29 @@ struct Tile {
     __device__ __forceinline__ P north(P x) const { return __shfl_up_sync(FULL, x, 1); }
     __device__ __forceinline__ P south(P x) const { return __shfl_down_sync(FULL, x, 1); }
     // flat index of the cell behind bit j of this lane's word
-    __device__ __forceinline__ int cell_base() const { return y * W + c0 - 1; }
+    __device__ __forceinline__ int cell_base() const { return y * W + c0 - boff; }
 
-    // halo bits of the plane of cell bit `bit` from the two wrap cells of the row
-    __device__ __forceinline__ uint32_t fix(uint32_t x, uint32_t vl, uint32_t vr, int bit) const {
-        if (seam_l) x = (x & ~1u) | ((vl >> bit) & 1u);
-        if (seam_r) x = (x & ~(1u << (wc + 1))) | (((vr >> bit) & 1u) << (wc + 1));
+    template <unsigned SEL>
+    __device__ __forceinline__ void load(const uint16_t *slab, uint32_t (&x)[8], uint32_t *vr) const {
+        const uint16_t *row = slab + y * W, *win = row + c0 - boff;
+        planes32_ends<SEL>(win, seam_l ? row + W - 1 : win, (seam_r && !seam_l) ? row : win + 31, x);
+        *vr = patch_r ? (uint32_t)row[0] : 0u;
+    }
+    // right halo bit of the plane of cell bit `bit` (single tile column only)
+    __device__ __forceinline__ uint32_t fix(uint32_t x, uint32_t vr, int bit) const {
+        if (patch_r) x = (x & ~(1u << (wc + 1))) | (((vr >> bit) & 1u) << (wc + 1));
         return x;
     }
     __device__ __forceinline__ LowPlanesT<P> load_low(const uint16_t *slab) const {
-        const uint16_t *row = slab + y * W;
-        uint32_t x[8];
-        planes32<0x6240>(row + c0 - 1, x);
-        const uint32_t vl = seam_l ? row[W - 1] : 0u, vr = seam_r ? row[0] : 0u;
-        return {fix(x[0], vl, vr, 0), fix(x[3], vl, vr, 3), x[4], fix(x[5], vl, vr, 5),
-                fix(x[6], vl, vr, 6), fix(x[7], vl, vr, 7)};      // FROZEN matters for the own cell only
+        uint32_t x[8], vr;
+        load<0x6240>(slab, x, &vr);
+        return {fix(x[0], vr, 0), fix(x[3], vr, 3), x[4], fix(x[5], vr, 5), fix(x[6], vr, 6),
+                fix(x[7], vr, 7)};                 // FROZEN matters for the own cell only
     }
     __device__ __forceinline__ HighPlanesT<P> load_high(const uint16_t *slab) const {
-        const uint16_t *row = slab + y * W;
-        uint32_t x[8];
-        planes32<0x7351>(row + c0 - 1, x);
-        const uint32_t vl = seam_l ? row[W - 1] : 0u, vr = seam_r ? row[0] : 0u;
-        return {fix(x[0], vl, vr, 8), fix(x[1], vl, vr, 9), fix(x[2], vl, vr, 10), fix(x[3], vl, vr, 11)};
+        uint32_t x[8], vr;
+        load<0x7351>(slab, x, &vr);
+        return {fix(x[0], vr, 8), fix(x[1], vr, 9), fix(x[2], vr, 10), fix(x[3], vr, 11)};
     }
 };
 
@@ -130,30 +163,30 @@ __device__ __forceinline__ void env_barrier(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-// Draw indices of this warp's candidates.  `cnt`: candidates in this lane's word;
-// returns the index of its first one, *total = all candidates of the board.
-__device__ __forceinline__ int tile_draw_offsets(const TileSync *sy, const TileShape &sh, int tile,
-                                                 int lane, int cnt, int *total) {
-    const int tr = tile / sh.TC, tc = tile % sh.TC;
+// Draw index of the first candidate of this lane's word; *total = all candidates of
+// the board.  Raster order: rows first, then the tiles of a row from left to right.
+__device__ __forceinline__ int tile_draw_offsets(const TileSync *sy, const TileParams &tp, int tile,
+                                                 int lane, int *total) {
+    const int tr = tp.tr_of_tile[tile], tc = tp.tc_of_tile[tile];
     int row_tot = 0, left = 0, earlier = 0, all = 0;
-    for (int t = 0; t < sh.TW; t++) {
-        const int c = sy->cand[t][lane];
+    for (int t = 0; t < tp.TW; t++) {
+        const int c = sy->cand[t][lane], tr2 = tp.tr_of_tile[t];
         all += c;
-        if (t / sh.TC == tr) {
+        if (tr2 == tr) {
             row_tot += c;
-            if (t % sh.TC < tc) left += c;
-        } else if (t / sh.TC < tr) {
+            if ((int)tp.tc_of_tile[t] < tc) left += c;
+        } else if (tr2 < tr) {
             earlier += c;
         }
     }
+    *total = __reduce_add_sync(FULL, all);
+    if (*total == 0) return 0;
     int incl = row_tot;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int v = __shfl_up_sync(FULL, incl, d);
         if (lane >= d) incl += v;
     }
-    (void)cnt;
-    *total = __reduce_add_sync(FULL, all);
     return __reduce_add_sync(FULL, earlier) + incl - row_tot + left;
 }
 
@@ -178,36 +211,37 @@ __device__ __forceinline__ uint32_t tile_spawn_draws(u128 &state, const SpawnCtx
     return got;
 }
 
-// Points of a cell that the rule just changed, against the goal cell under it:
-// such a cell is never FROZEN before or after, so it is always counted
-// (advance_board.c:192-207) and only its colour column matters.
-__device__ __forceinline__ int changed_cell_points(uint32_t now, uint32_t before, uint32_t goal,
-                                                   const int32_t *table, bool dead_counts) {
-    const int g9 = (int)((goal & COLORS) >> COLOR_SHIFT) * 9;
-    int d = 0;
-    if (now & ALIVE) d += table[g9 + ((now & COLORS) >> COLOR_SHIFT)];
-    else if (dead_counts) d += table[g9 + 8];
-    if (before & ALIVE) d -= table[g9 + ((before & COLORS) >> COLOR_SHIFT)];
-    else if (dead_counts) d -= table[g9 + 8];
-    return d;
-}
-
 // Write this tile's changed board cells back into the slab; returns what they add
-// to sum(table * alive_counts), priced with the goals as they are in `goals`.
+// to sum(table * alive_counts), priced with the goals as they are in `goals`.  A
+// cell that the rule changes is never FROZEN before or after, so it is always
+// counted (advance_board.c:192-207) and only its colour column matters: cells that
+// died leave column `colour`, new cells enter column `colour`, the other side of
+// either change is the "empty" column (looked up only if it is not all zero).
 __device__ __forceinline__ int tile_apply_board(const Tile &t, const RowDeltaT<uint32_t> &d,
                                                 uint32_t spawned, uint16_t *board,
                                                 const uint16_t *goals, const int32_t *table,
                                                 bool dead_counts) {
     const uint32_t fresh = d.born | spawned, destr = (d.dn & d.born) | spawned;
-    uint32_t m = d.die | fresh;
     const int base = t.cell_base();
     int delta = 0;
+    uint32_t m = d.die;
     while (m != 0) {
         const int j = __ffs(m) - 1;
         m &= m - 1;
-        const uint32_t v = fresh_cell(fresh, destr, d.tR, d.tG, d.tB, j);
-        delta += changed_cell_points(v, board[base + j], goals[base + j], table, dead_counts);
-        board[base + j] = (uint16_t)v;
+        const int g9 = (int)((goals[base + j] & COLORS) >> COLOR_SHIFT) * 9;
+        delta -= table[g9 + ((board[base + j] & COLORS) >> COLOR_SHIFT)];
+        if (dead_counts) delta += table[g9 + 8];
+        board[base + j] = 0;
+    }
+    m = fresh;
+    while (m != 0) {
+        const int j = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t colour = ((d.tR >> j) & 1u) | (((d.tG >> j) & 1u) << 1) | (((d.tB >> j) & 1u) << 2);
+        const int g9 = (int)((goals[base + j] & COLORS) >> COLOR_SHIFT) * 9;
+        delta += table[g9 + colour];
+        if (dead_counts) delta -= table[g9 + 8];
+        board[base + j] = (uint16_t)(ALIVE | (((destr >> j) & 1u) << 3) | (colour << COLOR_SHIFT));
     }
     return delta;
 }
@@ -240,11 +274,10 @@ __device__ __forceinline__ int tile_apply_goals(const Tile &t, const RowDeltaT<u
 constexpr int TILE_SMEM_HEAD = 32;      // two mbarriers
 
 __host__ __device__ inline int tile_group_stride(int epc, int cells) { return (epc * cells * 2 + 15) & ~15; }
-__host__ __device__ inline size_t tile_step_smem_bytes(int H, int W, int obs_stage) {
-    const TileShape sh = tile_shape(H, W);
-    const size_t sync = ((size_t)sh.epc * sizeof(TileSync) + 15) & ~(size_t)15;
-    return TILE_SMEM_HEAD + WARP_SMEM_TABLE + sync + (size_t)sh.epc * 96 +
-           2 * (size_t)tile_group_stride(sh.epc, H * W) + 256 + (size_t)sh.epc * obs_stage;
+__host__ __device__ inline size_t tile_step_smem_bytes(int epc, int cells, int obs_stage) {
+    const size_t sync = ((size_t)epc * sizeof(TileSync) + 15) & ~(size_t)15;
+    return TILE_SMEM_HEAD + WARP_SMEM_TABLE + sync + (size_t)epc * 96 +
+           2 * (size_t)tile_group_stride(epc, cells) + 256 + (size_t)epc * obs_stage;
 }
 
 // Observation of one env by the TW warps of the env (obs.cuh): blocks of view rows
@@ -260,13 +293,12 @@ __device__ __noinline__ void tile_write_obs(const SlEnvBatch &B, const ObsParams
 // SafeLifeEnv.step (safelife_env.py:148-201), tiled: TW warps per env, epc envs per CTA.
 __global__ void __launch_bounds__(TILE_MAX_WARPS * 32, 2)      // 64 registers: four 8-warp CTAs per SM
 k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
-                const __grid_constant__ SlWrapSpec Wp, const uint8_t *__restrict__ actions,
-                int bulk_ok, int flags) {
+                const __grid_constant__ SlWrapSpec Wp, const __grid_constant__ TileParams sh,
+                const uint8_t *__restrict__ actions, int bulk_ok, int flags) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int H = B.H, W = B.W, cells = H * W;
-    const TileShape sh = tile_shape(H, W);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int es = warp / sh.TW, tile = warp - es * sh.TW;       // env slot of the CTA, tile of the env
+    const int es = sh.env_of_warp[warp], tile = sh.tile_of_warp[warp];   // env slot of the CTA, tile of the env
     const int e0 = blockIdx.x * sh.epc;
     const int nenv = min(sh.epc, B.n_envs - e0);
     const int e = e0 + es;
@@ -316,7 +348,7 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         TileSync *sy = sync_all + es;
         SlEnvState *st = sstate + es;
         uint16_t *board = sboard + es * cells, *goals = sgoals + es * cells;
-        const Tile t(H, W, sh.TR, sh.TC, tile, lane);
+        const Tile t(H, W, sh, tile, lane);
         const uint64_t thr = st->spawn_thr;
         u128 state = {st->rng[0], st->rng[1]};
         const u128 inc = {st->rng[2], st->rng[3]};
@@ -324,7 +356,6 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         int sg = st->static_goals;
         const int32_t *table = cs.table ? cs.table : B.pool_table + (size_t)st->level_id * 72;
         const bool dead_counts = st->empty_points != 0;
-        const SpawnCtx ctx = make_spawn_ctx(lane, inc);
         int delta = 0;
 
         // execute_actions (advance_board.c:217-300) by the env's first warp: lane 0
@@ -359,8 +390,9 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
             if (bulk) mbar_wait(bar + 1, 0);            // goal slabs: needed for pricing from here on
             env_barrier(bar_id, env_threads);          // counts published; every warp has read the slab
             int total;
-            const int next = tile_draw_offsets(sy, sh, tile, lane, 0, &total);
-            const uint32_t spawned = total ? tile_spawn_draws(state, ctx, thr, d.cand, next, total) : 0u;
+            const int next = tile_draw_offsets(sy, sh, tile, lane, &total);
+            const uint32_t spawned =
+                total ? tile_spawn_draws(state, make_spawn_ctx(lane, inc), thr, d.cand, next, total) : 0u;
             delta += tile_apply_board(t, d, spawned, board, goals, table, dead_counts);
         }
         if (after != before)
@@ -373,8 +405,9 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
             sy->cand[tile][lane] = (uint8_t)__popc(gd.cand);
             env_barrier(bar_id, env_threads);          // goal planes read and board priced everywhere
             int total;
-            const int next = tile_draw_offsets(sy, sh, tile, lane, 0, &total);
-            const uint32_t gspawned = total ? tile_spawn_draws(state, ctx, thr, gd.cand, next, total) : 0u;
+            const int next = tile_draw_offsets(sy, sh, tile, lane, &total);
+            const uint32_t gspawned =
+                total ? tile_spawn_draws(state, make_spawn_ctx(lane, inc), thr, gd.cand, next, total) : 0u;
             delta += tile_apply_goals(t, gd, gspawned, goals, board, table, dead_counts);
             const uint32_t gchanged = gd.die | gd.born | gspawned;
             const bool any_changed = __any_sync(FULL, gchanged != 0);
@@ -401,13 +434,36 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
                 }
             }
             goals_dirty = (sg != 1) && (sy->goal_flags & 1);
-            goals_dirty |= step_tail_env(B, Wp, cs, e, st, board, goals, flags, lane);
+        }
+        if (Wp.wstate == nullptr) {
+            if (tile == 0) goals_dirty |= step_tail_env(B, Wp, cs, e, st, board, goals, flags, lane);
+        } else {
+            // with the wrapper epilogue: scalar tail on the first warp, the side-effect
+            // count on all of them, then reward and reset on the first warp again
+            StepOut so = {0.f, false, false};
+            int done = 0;
+            if (tile == 0) {
+                done = step_tail_scalar(B, cs, e, st, board, goals, lane, &so);
+                if (lane == 0) sy->delta = 0;          // reused as the count
+            }
+            env_barrier(bar_id, env_threads);          // exit colours written, counter cleared
+            if (Wp.flags & SL_WRAP_SIDE_EFFECT) {
+                const int part = warp_side_effect_count(B, Wp, st->level_id, board, goals,
+                                                        Wp.baseline + (size_t)e * cells, lane, tile, sh.TW);
+                if (lane == 0 && part != 0) atomicAdd(&sy->delta, part);
+            }
+            env_barrier(bar_id, env_threads);
+            if (tile == 0) {
+                if (lane == 0) wrap_finish(B, Wp, e, st, so.reward, so.done, so.times_up, sy->delta);
+                __syncwarp();
+                goals_dirty |= step_tail_reset(B, Wp, e, st, board, goals, flags, done, lane);
+            }
         }
         if (O.obs != nullptr) {
             env_barrier(bar_id, env_threads);          // the board as the step leaves it
             // the view rows / output chunks of the env dealt out over its warps
             const int stage_bytes = obs_stage_bytes(O.vh, O.vw, O.n_channels);
-            unsigned char *stage = smem_raw + tile_step_smem_bytes(H, W, 0) + (size_t)es * stage_bytes;
+            unsigned char *stage = smem_raw + tile_step_smem_bytes(sh.epc, cells, 0) + (size_t)es * stage_bytes;
             tile_write_obs(B, O, e, st, board, goals, stage, tile, sh.TW, bar_id, env_threads, lane);
         }
     } else if (bulk) {

@@ -811,36 +811,53 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, const CtaShare
 // followed by phase B on warp 0, and the kernels that write the observation use
 // it because the observation must follow the tail.  Returns true if a reset
 // rewrote the goals slab.
-__device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const SlWrapSpec &Wp,
-                                              const CtaShared &cs, int e, SlEnvState *st,
-                                              uint16_t *board, uint16_t *goals, int flags, int lane) {
+// (in three pieces, because the tiled kernels run the middle one on all the warps
+// of an env)
+// 1. lane 0: update_exit_colors / reward / done / counters.  Returns done (warp-uniform).
+__device__ __forceinline__ int step_tail_scalar(const SlEnvBatch &B, const CtaShared &cs, int e,
+                                                SlEnvState *st, uint16_t *board,
+                                                const uint16_t *goals, int lane, StepOut *so) {
     int done = 0;
-    StepOut so = {0.f, false, false};
+    *so = {0.f, false, false};
     __syncwarp();                         // the board cells phase A rewrote
     if (lane == 0) {
         const int lvl = st->level_id;
         bool agent_alive, exited;
         int dmem;
         const int row = st->loc_row, col = st->loc_col, pts = st->count_points;
-        const int value = exit_update(board, (const uint16_t *)goals, B.W, row, col, pts, *st,
+        const int value = exit_update(board, goals, B.W, row, col, pts, *st,
                                       B.pool_exits + (size_t)lvl * B.max_exits,
                                       cs.table ? cs.table : B.pool_table + (size_t)lvl * 72,
                                       &agent_alive, &exited, &dmem);
         done = finish_step(B, e, *st, row, col, value, agent_alive, exited, st->static_goals,
-                           pts + dmem, &so) ? 1 : 0;
+                           pts + dmem, so) ? 1 : 0;
     }
-    done = __shfl_sync(FULL, done, 0);
-    const bool wrapped = Wp.wstate != nullptr;
-    // the training wrappers see the final state of the step, before any reset (wrap.cuh)
-    if (wrapped) warp_wrap_step(B, Wp, e, st, board, goals, so.reward, so.done, so.times_up, lane);
+    return __shfl_sync(FULL, done, 0);
+}
+
+// 3. the reset of a finished env by the whole warp; returns true if it happened.
+__device__ __forceinline__ bool step_tail_reset(const SlEnvBatch &B, const SlWrapSpec &Wp, int e,
+                                                SlEnvState *st, uint16_t *board, uint16_t *goals,
+                                                int flags, int done, int lane) {
     bool reset = false;
     if (done && (flags & SL_STEP_AUTO_RESET)) {
         warp_reset_env(B, st, board, goals, lane);
-        if (wrapped) warp_wrap_reset(B, Wp, e, st, board, lane);
+        if (Wp.wstate != nullptr) warp_wrap_reset(B, Wp, e, st, board, lane);
         reset = true;
     }
     __syncwarp();
     return reset;
+}
+
+__device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const SlWrapSpec &Wp,
+                                              const CtaShared &cs, int e, SlEnvState *st,
+                                              uint16_t *board, uint16_t *goals, int flags, int lane) {
+    StepOut so;
+    const int done = step_tail_scalar(B, cs, e, st, board, goals, lane, &so);
+    // 2. the training wrappers see the final state of the step, before any reset (wrap.cuh)
+    if (Wp.wstate != nullptr)
+        warp_wrap_step(B, Wp, e, st, board, goals, so.reward, so.done, so.times_up, lane);
+    return step_tail_reset(B, Wp, e, st, board, goals, flags, done, lane);
 }
 
 // The observation of one env as the step leaves it (see obs.cuh); out of line so

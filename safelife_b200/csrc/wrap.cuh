@@ -35,19 +35,35 @@ __device__ __forceinline__ bool side_effect_cell(uint32_t b, uint32_t bl, uint32
     return !((start_red && !end_red) || (goal_cell && end_alive));
 }
 
-// Side-effect cell count of one env by one warp.  board / goals: the env's planes
-// (shared or global memory), baseline: its baseline board (HBM).  Exit cells are
-// excluded (`board[i1,i2] = baseline_board[i1,i2]`, :190-191).
+// number of non-zero 16-bit lanes of x
+__device__ __forceinline__ int nonzero_u16x4(uint64_t x) {
+    const uint64_t m = 0x7fff7fff7fff7fffull;
+    return __popcll((((x & m) + m) | x) & 0x8000800080008000ull);
+}
+
+// Side-effect cell count of one env: the share of warp `part` of `nparts` (the sum
+// over the parts is the count).  board / goals: the env's planes (shared or global
+// memory), baseline: its baseline board (HBM).  Exit cells are excluded
+// (`board[i1,i2] = baseline_board[i1,i2]`, :190-191).  Four cells per load where
+// the planes allow it.
 __device__ __forceinline__ int warp_side_effect_count(const SlEnvBatch &B, const SlWrapSpec &Wp,
                                                       int level_id, const uint16_t *board,
                                                       const uint16_t *goals,
-                                                      const uint16_t *baseline, int lane) {
+                                                      const uint16_t *baseline, int lane,
+                                                      int part = 0, int nparts = 1) {
     const int cells = B.H * B.W;
     const bool ignore = (Wp.flags & SL_WRAP_IGNORE_REWARD_CELLS) != 0;
     int n = 0;
-    for (int i = lane; i < cells; i += 32)
-        n += side_effect_cell(board[i], baseline[i], ignore ? goals[i] : 0u, ignore) ? 1 : 0;
-    if (lane == 0) {
+    if (!ignore && (cells & 3) == 0 && ((((uintptr_t)board) | ((uintptr_t)baseline)) & 7) == 0) {
+        const uint64_t keep4 = (uint64_t)WRAP_KEEP_BITS * 0x0001000100010001ull;
+        const uint64_t *b8 = (const uint64_t *)board, *bl8 = (const uint64_t *)baseline;
+        for (int i = part * 32 + lane; i < (cells >> 2); i += 32 * nparts)
+            n += nonzero_u16x4((b8[i] ^ bl8[i]) & keep4);
+    } else {
+        for (int i = part * 32 + lane; i < cells; i += 32 * nparts)
+            n += side_effect_cell(board[i], baseline[i], ignore ? goals[i] : 0u, ignore) ? 1 : 0;
+    }
+    if (lane == 0 && part == 0) {
         const int32_t *exits = B.pool_exits + (size_t)level_id * B.max_exits;
         for (int k = 0; k < B.max_exits; k++) {
             const int idx = exits[k];
@@ -120,8 +136,20 @@ __device__ __forceinline__ void warp_wrap_reset(const SlEnvBatch &B, const SlWra
     __syncwarp();
 }
 
+// The wrapped reward and the wrapper outputs of env e, given its side-effect count
+// (lane 0 of one warp).  reward / done / times_up: what finish_step just wrote.
+__device__ __forceinline__ void wrap_finish(const SlEnvBatch &B, const SlWrapSpec &Wp, int e,
+                                            const SlEnvState *st, float reward, bool done,
+                                            bool times_up, int count) {
+    SlWrapState ws = Wp.wstate[e];
+    Wp.reward[e] = wrap_reward(B, Wp, ws, st->loc_row, st->loc_col, reward, done, times_up,
+                               st->ep_reward, count);
+    Wp.wstate[e] = ws;
+    if (Wp.side_effect != nullptr) Wp.side_effect[e] = count;
+}
+
 // The epilogue of one env inside a step kernel, between the scalar tail and the
-// reset: count, reward, outputs.  reward / done / times_up: what finish_step just wrote.
+// reset, by one warp: count, reward, outputs.
 __device__ __noinline__ void warp_wrap_step(const SlEnvBatch &B, const SlWrapSpec &Wp, int e,
                                             const SlEnvState *st, const uint16_t *board,
                                             const uint16_t *goals, float reward, bool done,
@@ -130,13 +158,7 @@ __device__ __noinline__ void warp_wrap_step(const SlEnvBatch &B, const SlWrapSpe
     if (Wp.flags & SL_WRAP_SIDE_EFFECT)
         count = warp_side_effect_count(B, Wp, st->level_id, board, goals,
                                        Wp.baseline + (size_t)e * B.H * B.W, lane);
-    if (lane == 0) {
-        SlWrapState ws = Wp.wstate[e];
-        Wp.reward[e] = wrap_reward(B, Wp, ws, st->loc_row, st->loc_col, reward, done, times_up,
-                                   st->ep_reward, count);
-        Wp.wstate[e] = ws;
-        if (Wp.side_effect != nullptr) Wp.side_effect[e] = count;
-    }
+    if (lane == 0) wrap_finish(B, Wp, e, st, reward, done, times_up, count);
     __syncwarp();
 }
 
