@@ -141,6 +141,34 @@ int check_board_args(const void *p, int n, int H, int W) {
 
 int grid_for(int n) { return n < 1 ? 1 : (n > (1 << 20) ? (1 << 20) : n); }
 
+// Which fast step path handles H x W boards: 1 = one warp per env (narrow, <= 32 x 32),
+// 2 = several warps per env on 30 x 30 tiles, 3 = one warp per env on 64-bit rows
+// (<= 64 x 64; superseded by the tiles, kept behind SAFELIFE_B200_WIDE=1 for A/B runs),
+// 0 = none (generic CTA-per-env kernel).
+int fast_step_path(int H, int W) {
+    if (sl::warp_kernel_supports(H, W) && sl::warp_kernel_is_narrow(H, W)) return 1;
+    static const bool wide = sl::env_knob("SAFELIFE_B200_WIDE", 0) != 0;
+    if (wide && sl::warp_kernel_supports(H, W)) return 3;
+    if (sl::tile_kernel_supports(H, W)) return 2;
+    return 0;
+}
+
+int launch_multistep_tile(int mode, const uint16_t *in, const uint16_t *in2, uint16_t *out,
+                          int32_t *counts, int n, int H, int W, uint64_t thr_all,
+                          const uint64_t *thr_each, int n_steps, const int32_t *lead_steps,
+                          uint64_t *rng, int sm_count, cudaStream_t st) {
+    const sl::TileParams sh = sl::tile_shape(H, W);
+    const size_t smem = sl::tile_multistep_smem_bytes(sh.epc, sh.TW, H * W);
+    int rc = prepare_smem(sl::k_multistep_tile, smem);
+    if (rc) return rc;
+    int grid = (n + sh.epc - 1) / sh.epc;
+    const int cap = sm_count * 4;
+    if (grid > cap) grid = cap;
+    sl::k_multistep_tile<<<grid, sh.epc * sh.TW * 32, smem, st>>>(
+        sh, mode, in, in2, out, counts, n, H, W, thr_all, thr_each, n_steps, lead_steps, rng);
+    return launch_status("k_multistep_tile");
+}
+
 int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int H, int W,
                  float spawn_prob, int n_steps, uint64_t *rng, cudaStream_t st) {
     int rc = check_board_args(in, n, H, W);
@@ -156,7 +184,15 @@ int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int 
                                 rng, props.sm_count, st);
         return launch_status("k_advance_warp");
     }
-    if (sl::warp_kernel_supports(H, W)) {      // up to 64x64: planes in registers, two rows per lane
+    if (fast_step_path(H, W) == 2) {          // beyond 32x32: several warps per board, planes in registers
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        return launch_multistep_tile(counts ? 1 : 0, in, nullptr, out, counts, n, H, W,
+                                     spawn_threshold(spawn_prob), nullptr, n_steps, nullptr, rng,
+                                     props.sm_count, st);
+    }
+    if (sl::warp_kernel_supports(H, W)) {      // up to 64x64 on one warp (SAFELIFE_B200_WIDE=1): two rows per lane
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
@@ -226,7 +262,6 @@ int sl_debug_trace(void *buf) {
 }
 #endif
 
-static int fast_step_path(int H, int W);
 int sl_warp_kernel_supported(int H, int W) { return fast_step_path(H, W) != 0 ? 1 : 0; }
 
 int sl_advance_board(const uint16_t *in, uint16_t *out, int n, int H, int W, float spawn_prob,
@@ -258,6 +293,13 @@ int sl_side_effect_occupancy(const uint16_t *init_board, const uint16_t *final_b
         sl::launch_side_effect_warp(init_board, final_board, counts, n, H, W, spawn_thr, num_steps,
                                     num_samples, rng, props.sm_count, st);
         return launch_status("k_side_effect_warp");
+    }
+    if (fast_step_path(H, W) == 2) {
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        return launch_multistep_tile(2, init_board, final_board, nullptr, counts, n, H, W, 0, spawn_thr,
+                                     num_samples, num_steps, rng, props.sm_count, st);
     }
     if (sl::warp_kernel_supports(H, W)) {
         DeviceProps props;
@@ -474,18 +516,6 @@ static int check_batch(const SlEnvBatch *b) {
          !b->pool_spawn_thr || (b->max_exits > 0 && !b->pool_exits)))
         return fail(SL_ERR_ARG, "null pointer in SlEnvBatch");
     return SL_OK;
-}
-
-// Which fast step path handles H x W boards: 1 = one warp per env (narrow, <= 32 x 32),
-// 2 = several warps per env on 30 x 30 tiles, 3 = one warp per env on 64-bit rows
-// (<= 64 x 64; superseded by the tiles, kept behind SAFELIFE_B200_WIDE=1 for A/B runs),
-// 0 = none (generic CTA-per-env kernel).
-static int fast_step_path(int H, int W) {
-    if (sl::warp_kernel_supports(H, W) && sl::warp_kernel_is_narrow(H, W)) return 1;
-    static const bool wide = sl::env_knob("SAFELIFE_B200_WIDE", 0) != 0;
-    if (wide && sl::warp_kernel_supports(H, W)) return 3;
-    if (sl::tile_kernel_supports(H, W)) return 2;
-    return 0;
 }
 
 static int check_obs_spec(const SlObsSpec *o) {

@@ -485,4 +485,279 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// n-step advance / life occupancy / the simulation part of side_effect_score on
+// tiles: advance_board_nstep (advance_board.c:128-149), life_occupancy
+// (:153-189) and side_effects.py:101-111 for boards beyond 32x32.  As in the
+// one-warp-per-board kernels the planes stay in registers for all the steps; what
+// changes is that a board is spread over TW warps, so after every step the warps
+// refresh their halo ring from their neighbours through shared memory: first
+// the halo rows (a neighbour's whole boundary word), then, with the halo rows in
+// place, the halo columns (one ballot per plane and side, which brings the
+// corners along).  A small batch of large boards (the finished episodes of a
+// step) therefore occupies TW times as many warps as before.
+// ---------------------------------------------------------------------------
+struct TileHalo {
+    uint32_t row[2][9];     // [top / bottom interior row][plane]
+    uint32_t col[2][9];     // [first / last interior column][plane], bit l = lane l
+};
+
+struct TileBoard {
+    LowPlanesT<uint32_t> lp;
+    HighPlanesT<uint32_t> hp;
+    uint32_t agent, kept;
+};
+
+__device__ __forceinline__ TileBoard tile_board_load(const Tile &t, const uint16_t *slab) {
+    TileBoard b;
+    uint32_t x[8], vr;
+    t.load<0x6240>(slab, x, &vr);
+    b.lp = {t.fix(x[0], vr, 0), t.fix(x[3], vr, 3), x[4], t.fix(x[5], vr, 5), t.fix(x[6], vr, 6),
+            t.fix(x[7], vr, 7)};
+    b.agent = x[1] & t.imask;
+    b.lp.F &= t.imask;
+    b.hp = t.load_high(slab);
+    b.kept = t.imask;
+    return b;
+}
+
+// The nine planes whose neighbours the rule reads, by index.
+__device__ __forceinline__ uint32_t &tile_plane(TileBoard &b, int p) {
+    switch (p) {
+        case 0: return b.lp.A;
+        case 1: return b.lp.D;
+        case 2: return b.lp.P_;
+        case 3: return b.lp.I;
+        case 4: return b.lp.S;
+        case 5: return b.hp.E;
+        case 6: return b.hp.R;
+        case 7: return b.hp.G;
+        default: return b.hp.B;
+    }
+}
+
+// Halo refresh after a step.  `mine`: this tile's exchange record, up / down / left /
+// right: its neighbours' (possibly itself on a single tile row / column).
+__device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, TileHalo *mine,
+                                                   const TileHalo *up, const TileHalo *down,
+                                                   const TileHalo *left, const TileHalo *right,
+                                                   int bar_id, int env_threads) {
+    const int lane = t.lane;
+#pragma unroll
+    for (int p = 0; p < 9; p++) {
+        const uint32_t x = tile_plane(b, p);
+        if (lane == 1) mine->row[0][p] = x;
+        if (lane == t.hr) mine->row[1][p] = x;
+    }
+    env_barrier(bar_id, env_threads);
+#pragma unroll
+    for (int p = 0; p < 9; p++) {
+        uint32_t &x = tile_plane(b, p);
+        if (lane == 0) x = up->row[1][p];
+        if (lane == t.hr + 1) x = down->row[0][p];
+    }
+    const int first = t.boff, last = t.boff + t.wc - 1;
+#pragma unroll
+    for (int p = 0; p < 9; p++) {
+        const uint32_t x = tile_plane(b, p);
+        const uint32_t c0 = __ballot_sync(FULL, (x >> first) & 1u), c1 = __ballot_sync(FULL, (x >> last) & 1u);
+        if (lane == 0) {
+            mine->col[0][p] = c0;
+            mine->col[1][p] = c1;
+        }
+    }
+    env_barrier(bar_id, env_threads);
+    const uint32_t keep = ~((1u << (first - 1)) | (1u << (last + 1)));
+#pragma unroll
+    for (int p = 0; p < 9; p++) {
+        uint32_t &x = tile_plane(b, p);
+        const uint32_t l = (left->col[1][p] >> lane) & 1u, r = (right->col[0][p] >> lane) & 1u;
+        x = (x & keep) | (l << (first - 1)) | (r << (last + 1));
+    }
+}
+
+// One advance_board step on the register image of a tile (halos valid on entry and
+// on exit).  `draws`: the board may draw at all (an RNG was given and it has a spawner).
+__device__ __forceinline__ void tile_board_step(const Tile &t, TileBoard &b, u128 &state,
+                                                const u128 &inc, uint64_t thr, bool draws,
+                                                TileSync *sy, const TileParams &tp, int tile,
+                                                TileHalo *mine, const TileHalo *up,
+                                                const TileHalo *down, const TileHalo *left,
+                                                const TileHalo *right, int bar_id, int env_threads) {
+    LowPlanesT<uint32_t> &lp = b.lp;
+    HighPlanesT<uint32_t> &hp = b.hp;
+    const RowDeltaT<uint32_t> d = stencil_planes(t, lp, [&] { return hp; });
+    uint32_t spawned = 0u;
+    if (draws) {
+        sy->cand[tile][t.lane] = (uint8_t)__popc(d.cand);
+        env_barrier(bar_id, env_threads);
+        int total;
+        const int next = tile_draw_offsets(sy, tp, tile, t.lane, &total);
+        if (total) spawned = tile_spawn_draws(state, make_spawn_ctx(t.lane, inc), thr, d.cand, next, total);
+    }
+    const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
+    lp.A = (lp.A & keep) | fresh;
+    lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
+    hp.R = (hp.R & keep) | (d.tR & fresh);
+    hp.G = (hp.G & keep) | (d.tG & fresh);
+    hp.B = (hp.B & keep) | (d.tB & fresh);
+    lp.P_ &= keep; lp.I &= keep; lp.S &= keep; hp.E &= keep; b.agent &= keep;
+    b.kept &= keep;                     // (F is already 0 on every changed cell)
+    tile_halo_exchange(t, b, mine, up, down, left, right, bar_id, env_threads);
+}
+
+// Bit-sliced occupancy counters of the tile's interior (see OccCounters).
+struct TileOcc {
+    uint32_t cnt[8][OCC_BITS];
+    int pending;
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int c = 0; c < 8; c++)
+#pragma unroll
+            for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
+        pending = 0;
+    }
+    __device__ __forceinline__ void flush(const Tile &t, int32_t *board_counts) {
+        if (t.imask != 0) {
+            int32_t *dst = board_counts + (size_t)t.cell_base() * 8;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t nz = 0;
+#pragma unroll
+                for (int k = 0; k < OCC_BITS; k++) nz |= cnt[c][k];
+                while (nz != 0) {
+                    const int j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    int v = 0;
+#pragma unroll
+                    for (int k = 0; k < OCC_BITS; k++) v |= ((cnt[c][k] >> j) & 1u) << k;
+                    dst[j * 8 + c] += v;
+                }
+#pragma unroll
+                for (int k = 0; k < OCC_BITS; k++) cnt[c][k] = 0;
+            }
+        }
+        pending = 0;
+    }
+    // +1 for cells ALIVE and none of AGENT | EXIT | FROZEN, by colour (advance_board.c:153-162)
+    __device__ __forceinline__ void add(const Tile &t, const TileBoard &b, int32_t *board_counts) {
+        const uint32_t occ = b.lp.A & ~(b.agent | b.hp.E | b.lp.F) & t.imask;
+        if (__any_sync(FULL, occ != 0)) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                uint32_t carry = occ & ((c & 1) ? b.hp.R : ~b.hp.R) & ((c & 2) ? b.hp.G : ~b.hp.G) &
+                                 ((c & 4) ? b.hp.B : ~b.hp.B);
+                if (__any_sync(FULL, carry != 0)) {
+#pragma unroll
+                    for (int k = 0; k < OCC_BITS; k++) {
+                        const uint32_t tmp = cnt[c][k] & carry;
+                        cnt[c][k] ^= carry;
+                        carry = tmp;
+                    }
+                }
+            }
+        }
+        if (++pending == (1 << OCC_BITS) - 1) flush(t, board_counts);
+    }
+};
+
+__host__ __device__ inline size_t tile_multistep_smem_bytes(int epc, int TW, int cells) {
+    const size_t sync = ((size_t)epc * sizeof(TileSync) + 15) & ~(size_t)15;
+    return sync + (size_t)epc * TW * sizeof(TileHalo) + 64 + (size_t)epc * (((size_t)cells * 2 + 15) & ~(size_t)15) + 256;
+}
+
+// mode 0: out[b] = board after n_steps (advance_board_nstep); mode 1: counts[b] +=
+// life_occupancy over n_steps; mode 2: the three runs of side_effect_score
+// (counts[b][0..1], first run preceded by lead_steps[b] uncounted steps).
+__global__ void __launch_bounds__(TILE_MAX_WARPS * 32)
+k_multistep_tile(const __grid_constant__ TileParams sh, int mode, const uint16_t *in,
+                 const uint16_t *in2, uint16_t *out, int32_t *__restrict__ counts, int n, int H,
+                 int W, uint64_t thr_all, const uint64_t *__restrict__ thr_each, int n_steps,
+                 const int32_t *__restrict__ lead_steps, uint64_t *__restrict__ rng) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cells = H * W;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int es = sh.env_of_warp[warp], tile = sh.tile_of_warp[warp];
+    const int env_threads = sh.TW * 32, bar_id = 1 + es;
+    const bool counting = mode != 0;
+    const size_t sync_bytes = ((size_t)sh.epc * sizeof(TileSync) + 15) & ~(size_t)15;
+    TileSync *sy = (TileSync *)smem_raw + es;
+    TileHalo *halos = (TileHalo *)(smem_raw + sync_bytes) + es * sh.TW;
+    const size_t slab_bytes = ((size_t)cells * 2 + 15) & ~(size_t)15;
+    uint16_t *slab = (uint16_t *)(smem_raw + sync_bytes + (size_t)sh.epc * sh.TW * sizeof(TileHalo) + 64 +
+                                  es * slab_bytes);
+    const Tile t(H, W, sh, tile, lane);
+    // neighbours on the torus of tiles
+    const int tr = sh.tr_of_tile[tile], tc = sh.tc_of_tile[tile];
+    const int tr_up = tr == 0 ? sh.TR - 1 : tr - 1, tr_dn = tr == sh.TR - 1 ? 0 : tr + 1;
+    const int tc_l = tc == 0 ? sh.TC - 1 : tc - 1, tc_r = tc == sh.TC - 1 ? 0 : tc + 1;
+    TileHalo *mine = halos + tile;
+    const TileHalo *up = halos + tr_up * sh.TC + tc, *down = halos + tr_dn * sh.TC + tc;
+    const TileHalo *left = halos + tr * sh.TC + tc_l, *right = halos + tr * sh.TC + tc_r;
+
+    for (int b0 = blockIdx.x * sh.epc; b0 < n; b0 += gridDim.x * sh.epc) {
+        const int b = b0 + es;
+        if (b >= n) continue;                       // (whole envs drop out together: no barrier is split)
+        u128 state = {0, 0}, inc = {0, 0};
+        if (rng != nullptr) {
+            state = {rng[4 * (size_t)b], rng[4 * (size_t)b + 1]};
+            inc = {rng[4 * (size_t)b + 2], rng[4 * (size_t)b + 3]};
+        }
+        const uint64_t th = thr_each != nullptr ? thr_each[b] : thr_all;
+        const int runs = mode == 2 ? 2 : 1;
+        TileOcc occ;
+        for (int run = 0; run < runs; run++) {
+            const uint16_t *src = (run == 0 ? in : in2) + (size_t)b * cells;
+            env_barrier(bar_id, env_threads);       // the slab is free
+            for (int i = tile * 32 + lane; i < cells; i += env_threads) slab[i] = src[i];
+            if (tile == 0 && lane == 0) sy->goal_flags = 0;
+            env_barrier(bar_id, env_threads);
+            TileBoard bd = tile_board_load(t, slab);
+            // a board without a spawner never draws (spawners are not created)
+            if (__any_sync(FULL, (bd.lp.S & t.imask) != 0) && lane == 0) atomicOr(&sy->goal_flags, 1);
+            env_barrier(bar_id, env_threads);
+            const bool draws = rng != nullptr && sy->goal_flags != 0;
+            if (mode == 2 && run == 0) {
+                const int lead = lead_steps[b];
+                for (int s = 0; s < lead; s++)
+                    tile_board_step(t, bd, state, inc, th, draws, sy, sh, tile, mine, up, down, left, right,
+                                    bar_id, env_threads);
+            }
+            if (!counting) {
+                for (int s = 0; s < n_steps; s++)
+                    tile_board_step(t, bd, state, inc, th, draws, sy, sh, tile, mine, up, down, left, right,
+                                    bar_id, env_threads);
+                // cells that changed at least once are fully described by the planes
+                uint32_t m = t.imask & ~bd.kept;
+                const int base = t.cell_base();
+                while (m != 0) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    slab[base + j] = (uint16_t)(((bd.lp.A >> j) & 1u) | (((bd.lp.D >> j) & 1u) << 3) |
+                                                (((bd.hp.R >> j) & 1u) << 9) | (((bd.hp.G >> j) & 1u) << 10) |
+                                                (((bd.hp.B >> j) & 1u) << 11));
+                }
+                env_barrier(bar_id, env_threads);
+                uint16_t *dst = out + (size_t)b * cells;
+                for (int i = tile * 32 + lane; i < cells; i += env_threads) dst[i] = slab[i];
+            } else {
+                int32_t *dst = counts + ((size_t)b * runs + run) * cells * 8;
+                occ.clear();
+                for (int s = 0; s < n_steps; s++) {
+                    tile_board_step(t, bd, state, inc, th, draws, sy, sh, tile, mine, up, down, left, right,
+                                    bar_id, env_threads);
+                    occ.add(t, bd, dst);
+                }
+                if (occ.pending) occ.flush(t, dst);
+            }
+        }
+        if (rng != nullptr && tile == 0 && lane == 0) {
+            rng[4 * (size_t)b] = state.hi;
+            rng[4 * (size_t)b + 1] = state.lo;
+        }
+    }
+}
+
 }  // namespace sl

@@ -348,7 +348,9 @@ def test_step_plan_and_launch_floor():
     text, launches = big.step_plan()
     assert "k_env_step_pipe<" in text and "goals in place" in text and "k_env_step_warp" in text
     assert launches == 2                      # pipelined kernel + the ragged tail group
-    generic = BatchedSafeLifeEnv(_random_levels(rs, 4, 70, 41), 8)
+    tiled = BatchedSafeLifeEnv(_random_levels(rs, 4, 70, 41), 8)
+    assert "k_env_step_tile<3 x 2 tiles, 1 envs/CTA>" in tiled.step_plan()[0]
+    generic = BatchedSafeLifeEnv(_random_levels(rs, 2, 130, 41), 4)
     assert "k_env_step_generic" in generic.step_plan()[0]
     assert _lib.lib().sl_launch_floor(small._batch_ref, small._stream()) == _lib.SL_OK
     torch.cuda.synchronize()

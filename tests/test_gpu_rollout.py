@@ -21,9 +21,10 @@ def _policy(d, device):
 
     def policy(obs):
         counts = obs.to(torch.int64).sum(dim=(1, 2))
-        action = torch.argmax(counts @ wp, dim=1)
+        # (integer matmul is not implemented on CUDA: broadcast and sum, still exact)
+        action = torch.argmax((counts.unsqueeze(2) * wp.unsqueeze(0)).sum(dim=1), dim=1)
         policies = torch.nn.functional.one_hot(action, 9).to(torch.float32)
-        return (counts @ wv).to(torch.float32) / 64, policies
+        return (counts * wv.unsqueeze(0)).sum(dim=1).to(torch.float32) / 64, policies
     return policy
 
 
