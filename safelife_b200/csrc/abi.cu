@@ -153,6 +153,18 @@ int fast_step_path(int H, int W) {
     return 0;
 }
 
+// The multi-step kernels on tiles put TW warps on a board: that is what a small batch
+// of large boards needs (the finished episodes of one step); a batch that fills the
+// machine with one warp per board is better off on the 64-bit-row kernel, which runs
+// fewer instructions per board-step (measured: 256 boards 4.8e7 vs 2.0e7 board-steps/s,
+// 2048 boards 7.0e7 vs 1.0e8).  Boards beyond 64x64 always run on tiles.
+bool multistep_on_tiles(int n, int H, int W) {
+    if (fast_step_path(H, W) != 2) return false;
+    if (!sl::warp_kernel_supports(H, W)) return true;
+    static const int limit = sl::env_knob("SAFELIFE_B200_MULTISTEP_TILE_BOARDS", 768);
+    return n <= limit;
+}
+
 int launch_multistep_tile(int mode, const uint16_t *in, const uint16_t *in2, uint16_t *out,
                           int32_t *counts, int n, int H, int W, uint64_t thr_all,
                           const uint64_t *thr_each, int n_steps, const int32_t *lead_steps,
@@ -184,7 +196,7 @@ int advance_impl(const uint16_t *in, uint16_t *out, int32_t *counts, int n, int 
                                 rng, props.sm_count, st);
         return launch_status("k_advance_warp");
     }
-    if (fast_step_path(H, W) == 2) {          // beyond 32x32: several warps per board, planes in registers
+    if (multistep_on_tiles(n, H, W)) {        // beyond 32x32: several warps per board, planes in registers
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;
@@ -294,7 +306,7 @@ int sl_side_effect_occupancy(const uint16_t *init_board, const uint16_t *final_b
                                     num_samples, rng, props.sm_count, st);
         return launch_status("k_side_effect_warp");
     }
-    if (fast_step_path(H, W) == 2) {
+    if (multistep_on_tiles(n, H, W)) {
         DeviceProps props;
         rc = device_props(&props);
         if (rc) return rc;

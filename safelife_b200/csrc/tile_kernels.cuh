@@ -152,11 +152,14 @@ struct Tile {
 };
 
 // ---- what the warps of one env share ------------------------------------------
+constexpr int TILE_DRAW_ROUNDS = 8;     // rounds of 32 draws published at a time
 struct TileSync {
     uint8_t cand[TILE_MAX_WARPS][32];   // spawn candidates per tile and lane (row)
     int delta;                          // change of sum(table * alive_counts)
     int goal_flags;                     // 1: some goal cell changed, 2: a spawner is left in the goals
-    int pad[2];
+    int special[2];                     // multi-step kernel: a P / I / S / E bit changed (by step parity)
+    uint32_t ok[TILE_DRAW_ROUNDS];      // multi-step kernel: outcomes of 32 draws per word
+    uint64_t state[2];                  //                    and the stream after them
 };
 
 __device__ __forceinline__ void env_barrier(int id, int threads) {
@@ -538,8 +541,12 @@ __device__ __forceinline__ uint32_t &tile_plane(TileBoard &b, int p) {
 }
 
 // Halo refresh after a step.  `mine`: this tile's exchange record, up / down / left /
-// right: its neighbours' (possibly itself on a single tile row / column).
-__device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, TileHalo *mine,
+// right: its neighbours' (possibly itself on a single tile row / column).  Planes
+// 2-5 (PRESERVING, INHIBITING, SPAWNING, EXIT) only change when such a cell dies,
+// which is rare: `special` (this warp saw one die) is OR-ed over the env's warps
+// through sy->special[parity] and those planes are exchanged only then.
+__device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, TileSync *sy,
+                                                   int parity, bool special, TileHalo *mine,
                                                    const TileHalo *up, const TileHalo *down,
                                                    const TileHalo *left, const TileHalo *right,
                                                    int bar_id, int env_threads) {
@@ -550,9 +557,12 @@ __device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, 
         if (lane == 1) mine->row[0][p] = x;
         if (lane == t.hr) mine->row[1][p] = x;
     }
+    if (special && lane == 0) atomicOr(&sy->special[parity], 1);
     env_barrier(bar_id, env_threads);
+    const bool all = sy->special[parity] != 0;
 #pragma unroll
     for (int p = 0; p < 9; p++) {
+        if (p >= 2 && p <= 5 && !all) continue;
         uint32_t &x = tile_plane(b, p);
         if (lane == 0) x = up->row[1][p];
         if (lane == t.hr + 1) x = down->row[0][p];
@@ -560,6 +570,7 @@ __device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, 
     const int first = t.boff, last = t.boff + t.wc - 1;
 #pragma unroll
     for (int p = 0; p < 9; p++) {
+        if (p >= 2 && p <= 5 && !all) continue;
         const uint32_t x = tile_plane(b, p);
         const uint32_t c0 = __ballot_sync(FULL, (x >> first) & 1u), c1 = __ballot_sync(FULL, (x >> last) & 1u);
         if (lane == 0) {
@@ -567,10 +578,12 @@ __device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, 
             mine->col[1][p] = c1;
         }
     }
+    if (lane == 0) sy->special[parity ^ 1] = 0;     // the next step's flag (every warp writes the same 0)
     env_barrier(bar_id, env_threads);
     const uint32_t keep = ~((1u << (first - 1)) | (1u << (last + 1)));
 #pragma unroll
     for (int p = 0; p < 9; p++) {
+        if (p >= 2 && p <= 5 && !all) continue;
         uint32_t &x = tile_plane(b, p);
         const uint32_t l = (left->col[1][p] >> lane) & 1u, r = (right->col[0][p] >> lane) & 1u;
         x = (x & keep) | (l << (first - 1)) | (r << (last + 1));
@@ -580,7 +593,7 @@ __device__ __forceinline__ void tile_halo_exchange(const Tile &t, TileBoard &b, 
 // One advance_board step on the register image of a tile (halos valid on entry and
 // on exit).  `draws`: the board may draw at all (an RNG was given and it has a spawner).
 __device__ __forceinline__ void tile_board_step(const Tile &t, TileBoard &b, u128 &state,
-                                                const u128 &inc, uint64_t thr, bool draws,
+                                                const u128 &inc, uint64_t thr, bool draws, int parity,
                                                 TileSync *sy, const TileParams &tp, int tile,
                                                 TileHalo *mine, const TileHalo *up,
                                                 const TileHalo *down, const TileHalo *left,
@@ -593,10 +606,45 @@ __device__ __forceinline__ void tile_board_step(const Tile &t, TileBoard &b, u12
         sy->cand[tile][t.lane] = (uint8_t)__popc(d.cand);
         env_barrier(bar_id, env_threads);
         int total;
-        const int next = tile_draw_offsets(sy, tp, tile, t.lane, &total);
-        if (total) spawned = tile_spawn_draws(state, make_spawn_ctx(t.lane, inc), thr, d.cand, next, total);
+        int next = tile_draw_offsets(sy, tp, tile, t.lane, &total);
+        // The draws of the whole board, TILE_DRAW_ROUNDS x 32 at a time: the env's first warp
+        // runs the PCG64 leapfrog and publishes the outcome words and the stream, every warp
+        // picks the outcomes of its own candidates (raster order, see tile_draw_offsets).
+        uint32_t todo = d.cand;
+        for (int base = 0; base < total; base += 32 * TILE_DRAW_ROUNDS) {
+            const int rounds = min(TILE_DRAW_ROUNDS, (total - base + 31) >> 5);
+            if (tile == 0) {
+                const SpawnCtx ctx = make_spawn_ctx(t.lane, inc);
+                for (int r = 0; r < rounds; r++) {
+                    const u128 sn = add128(mul128(ctx.la, state), ctx.ginc);
+                    const uint32_t ok = __ballot_sync(FULL, (pcg_output(sn) >> 11) < thr);
+                    const int last = min(31, total - base - 32 * r - 1);
+                    state.hi = __shfl_sync(FULL, sn.hi, last);
+                    state.lo = __shfl_sync(FULL, sn.lo, last);
+                    if (t.lane == 0) sy->ok[r] = ok;
+                }
+                if (t.lane == 0) {
+                    sy->state[0] = state.hi;
+                    sy->state[1] = state.lo;
+                }
+            }
+            env_barrier(bar_id, env_threads);
+            for (int r = 0; r < rounds; r++) {
+                const uint32_t ok = sy->ok[r];
+                const int lo = base + 32 * r;
+                while (todo != 0 && next < lo + 32) {
+                    const int j = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    spawned |= ((ok >> (next - lo)) & 1u) << j;
+                    next++;
+                }
+            }
+            state = {sy->state[0], sy->state[1]};
+            if (base + 32 * TILE_DRAW_ROUNDS < total) env_barrier(bar_id, env_threads);   // words consumed
+        }
     }
     const uint32_t fresh = d.born | spawned, changed = d.die | fresh, keep = ~changed;
+    const bool special = __any_sync(FULL, (changed & (lp.P_ | lp.I | lp.S | hp.E)) != 0);
     lp.A = (lp.A & keep) | fresh;
     lp.D = (lp.D & keep) | (d.dn & d.born) | spawned;
     hp.R = (hp.R & keep) | (d.tR & fresh);
@@ -604,7 +652,7 @@ __device__ __forceinline__ void tile_board_step(const Tile &t, TileBoard &b, u12
     hp.B = (hp.B & keep) | (d.tB & fresh);
     lp.P_ &= keep; lp.I &= keep; lp.S &= keep; hp.E &= keep; b.agent &= keep;
     b.kept &= keep;                     // (F is already 0 on every changed cell)
-    tile_halo_exchange(t, b, mine, up, down, left, right, bar_id, env_threads);
+    tile_halo_exchange(t, b, sy, parity, special, mine, up, down, left, right, bar_id, env_threads);
 }
 
 // Bit-sliced occupancy counters of the tile's interior (see OccCounters).
@@ -712,23 +760,27 @@ k_multistep_tile(const __grid_constant__ TileParams sh, int mode, const uint16_t
             const uint16_t *src = (run == 0 ? in : in2) + (size_t)b * cells;
             env_barrier(bar_id, env_threads);       // the slab is free
             for (int i = tile * 32 + lane; i < cells; i += env_threads) slab[i] = src[i];
-            if (tile == 0 && lane == 0) sy->goal_flags = 0;
+            if (tile == 0 && lane == 0) {
+                sy->goal_flags = 0;
+                sy->special[0] = sy->special[1] = 0;
+            }
             env_barrier(bar_id, env_threads);
             TileBoard bd = tile_board_load(t, slab);
+            int step_no = 0;
             // a board without a spawner never draws (spawners are not created)
             if (__any_sync(FULL, (bd.lp.S & t.imask) != 0) && lane == 0) atomicOr(&sy->goal_flags, 1);
             env_barrier(bar_id, env_threads);
             const bool draws = rng != nullptr && sy->goal_flags != 0;
             if (mode == 2 && run == 0) {
                 const int lead = lead_steps[b];
-                for (int s = 0; s < lead; s++)
-                    tile_board_step(t, bd, state, inc, th, draws, sy, sh, tile, mine, up, down, left, right,
-                                    bar_id, env_threads);
+                for (int s = 0; s < lead; s++, step_no++)
+                    tile_board_step(t, bd, state, inc, th, draws, step_no & 1, sy, sh, tile, mine, up, down,
+                                    left, right, bar_id, env_threads);
             }
             if (!counting) {
-                for (int s = 0; s < n_steps; s++)
-                    tile_board_step(t, bd, state, inc, th, draws, sy, sh, tile, mine, up, down, left, right,
-                                    bar_id, env_threads);
+                for (int s = 0; s < n_steps; s++, step_no++)
+                    tile_board_step(t, bd, state, inc, th, draws, step_no & 1, sy, sh, tile, mine, up, down,
+                                    left, right, bar_id, env_threads);
                 // cells that changed at least once are fully described by the planes
                 uint32_t m = t.imask & ~bd.kept;
                 const int base = t.cell_base();
@@ -745,9 +797,9 @@ k_multistep_tile(const __grid_constant__ TileParams sh, int mode, const uint16_t
             } else {
                 int32_t *dst = counts + ((size_t)b * runs + run) * cells * 8;
                 occ.clear();
-                for (int s = 0; s < n_steps; s++) {
-                    tile_board_step(t, bd, state, inc, th, draws, sy, sh, tile, mine, up, down, left, right,
-                                    bar_id, env_threads);
+                for (int s = 0; s < n_steps; s++, step_no++) {
+                    tile_board_step(t, bd, state, inc, th, draws, step_no & 1, sy, sh, tile, mine, up, down,
+                                    left, right, bar_id, env_threads);
                     occ.add(t, bd, dst);
                 }
                 if (occ.pending) occ.flush(t, dst);
