@@ -153,23 +153,22 @@ int fast_step_path(int H, int W) {
     return 0;
 }
 
-// The multi-step kernels on tiles put TW warps on a board: that is what a small batch
-// of large boards needs (the finished episodes of one step); a batch that fills the
-// machine with one warp per board is better off on the 64-bit-row kernel, which runs
-// fewer instructions per board-step (measured: 256 boards 4.8e7 vs 2.0e7 board-steps/s,
-// 2048 boards 7.0e7 vs 1.0e8).  Boards beyond 64x64 always run on tiles.
+// The multi-step kernels on tiles put TW warps on a board.  Measured on 50x50
+// navigation boards against one warp per board on 64-bit rows (board-steps/s): 256
+// boards 5.2e7 vs 2.0e7, 2048 boards 1.38e8 vs 1.02e8 -- tiles at every batch size
+// (SAFELIFE_B200_WIDE=1 brings the one-warp kernel back for A/B runs).
 bool multistep_on_tiles(int n, int H, int W) {
-    if (fast_step_path(H, W) != 2) return false;
-    if (!sl::warp_kernel_supports(H, W)) return true;
-    static const int limit = sl::env_knob("SAFELIFE_B200_MULTISTEP_TILE_BOARDS", 768);
-    return n <= limit;
+    (void)n;
+    return fast_step_path(H, W) == 2;
 }
 
 int launch_multistep_tile(int mode, const uint16_t *in, const uint16_t *in2, uint16_t *out,
                           int32_t *counts, int n, int H, int W, uint64_t thr_all,
                           const uint64_t *thr_each, int n_steps, const int32_t *lead_steps,
                           uint64_t *rng, int sm_count, cudaStream_t st) {
-    const sl::TileParams sh = sl::tile_shape(H, W);
+    sl::TileParams sh = sl::tile_shape(H, W);
+    // a small batch: one board per CTA, so that its boards reach as many SMs as possible
+    if ((n + sh.epc - 1) / sh.epc < 2 * sm_count) sh.epc = 1;
     const size_t smem = sl::tile_multistep_smem_bytes(sh.epc, sh.TW, H * W);
     int rc = prepare_smem(sl::k_multistep_tile, smem);
     if (rc) return rc;
