@@ -166,11 +166,12 @@ struct Narrow {
     typedef uint32_t RowMask;
     static constexpr int ROWS = 1;
     static constexpr int PAD_CELLS = 32 * 32 + 32;   // row over-read past the last slab
-    int H, W, lane, up, down;
+    int H, W, lane, up, down, row_off;
     uint32_t wmask;
 
     __device__ __forceinline__ Narrow(int H_, int W_, int lane_) : H(H_), W(W_), lane(lane_) {
         int r = lane < H ? lane : 0;
+        row_off = r * W;     // lanes past the last row re-read row 0 of their own env (masked out)
         up = r == 0 ? H - 1 : r - 1;
         down = r == H - 1 ? 0 : r + 1;
         // lanes past the last row carry an empty mask: they never create, kill or draw
@@ -187,12 +188,12 @@ struct Narrow {
 
     __device__ __forceinline__ LowPlanesT<P> load_low(const uint16_t *slab) const {
         uint32_t x[8];
-        planes32<0x6240>(slab + lane * W, x);
+        planes32<0x6240>(slab + row_off, x);
         return {x[0] & wmask, x[3] & wmask, x[4] & wmask, x[5] & wmask, x[6] & wmask, x[7] & wmask};
     }
     __device__ __forceinline__ HighPlanesT<P> load_high(const uint16_t *slab) const {
         uint32_t x[8];
-        planes32<0x7351>(slab + lane * W, x);
+        planes32<0x7351>(slab + row_off, x);
         return {x[0] & wmask, x[1] & wmask, x[2] & wmask, x[3] & wmask};
     }
 };
@@ -754,9 +755,9 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShare
             if (lane == 0) atomicExch(cs.lock, 0);
         }
     }
-    const int pts = st->count_points + __reduce_add_sync(FULL, delta);
+    delta = __reduce_add_sync(FULL, delta);
     if (lane == 0) {
-        st->count_points = pts;
+        st->count_points += delta;
         st->static_goals = (uint8_t)sg;
         if (state.lo != state_lo0) {   // the LCG is a bijection: lo changes iff draws happened
             st->rng[0] = state.hi;
@@ -854,6 +855,7 @@ __device__ __forceinline__ bool step_tail_env(const SlEnvBatch &B, const SlWrapS
                                               uint16_t *board, uint16_t *goals, int flags, int lane) {
     StepOut so;
     const int done = step_tail_scalar(B, cs, e, st, board, goals, lane, &so);
+    __syncwarp();                         // lane 0's exit colours before the other lanes read the board
     // 2. the training wrappers see the final state of the step, before any reset (wrap.cuh)
     if (Wp.wstate != nullptr)
         warp_wrap_step(B, Wp, e, st, board, goals, so.reward, so.done, so.times_up, lane);
@@ -1285,7 +1287,7 @@ struct AdvBoard {
 // slab: this lane's padded copy of the board in shared memory.
 __device__ __forceinline__ AdvBoard adv_load(const Narrow &t, const uint16_t *slab) {
     uint32_t x[16];
-    const uint16_t *row = slab + t.lane * t.W;
+    const uint16_t *row = slab + t.row_off;
 #pragma unroll
     for (int k = 0; k < 16; k++) x[k] = __byte_perm(row[k], row[k + 16], 0x5410);
     transpose16(x);
@@ -1320,6 +1322,7 @@ __device__ __forceinline__ void adv_step(const Narrow &t, AdvBoard &b, u128 &sta
 // Cells that changed at least once are fully described by the planes: patch
 // them into the lane's row of the slab.
 __device__ __forceinline__ void adv_store(const Narrow &t, const AdvBoard &b, uint16_t *slab) {
+    __syncwarp();                         // a lane's load window reaches into the next lane's row
     uint16_t *row = slab + t.lane * t.W;
     uint32_t m = t.wmask & ~b.kept;
     while (m != 0) {
