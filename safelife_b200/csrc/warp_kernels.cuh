@@ -756,6 +756,7 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShare
         }
     }
     delta = __reduce_add_sync(FULL, delta);
+    __syncwarp();                         // every lane has read the record before lane 0 rewrites it
     if (lane == 0) {
         st->count_points += delta;
         st->static_goals = (uint8_t)sg;
