@@ -292,7 +292,7 @@ CONFIGS = [
     ("prune-still-25", 16384, 25),
     ("append-spawn-25", 8192, 40),
     ("append-still-26", 2048, 30),
-    ("navigation-50", 512, 25),
+    ("navigation-50", 4096, 25),
 ]
 
 
@@ -605,3 +605,55 @@ def test_host_groups_pipeline_matches_whole_batch_steps():
     assert np.array_equal(a.board.cpu().numpy(), b.board.cpu().numpy())
     with pytest.raises(ValueError):
         a.enable_host_groups(3)
+
+
+@pytest.mark.parametrize("pool,n", [("append-still-25", 4096), ("prune-still-25", 16384),
+                                    ("append-spawn-25", 8192), ("navigation-50", 4096)])
+def test_baseline_pools_across_an_episode_boundary(pool, n):
+    """BASELINE batch sizes with auto-reset: a strided subset follows the oracle through the
+    end of one episode, the in-kernel reset onto the next level, and the episode after it."""
+    path = os.path.join(gu.GOLDEN, "pools", pool + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("pool fixture missing")
+    from safelife_b200.env import BatchedSafeLifeEnv, seed_rng_states
+    from safelife_b200.levels import load_levels
+    levels = load_levels(path)
+    L, limit = len(levels), 8
+    env = BatchedSafeLifeEnv(levels, n, auto_reset=True, time_limit=limit, view_shape=(25, 25),
+                             output_channels=TRAIN_CHANNELS)
+    rng = seed_rng_states(6, n)
+    env.set_rng_state(rng)
+    env.reset()
+    idx = np.arange(0, n, max(1, n // 96))[:96]
+    acts = np.random.default_rng(3).integers(0, 9, (2 * limit, n)).astype(np.uint8)
+    level_of = idx % L
+    state = rng[idx]
+    for episode in range(2):
+        ora = orc.OracleEnv([levels[l] for l in level_of], list(state), time_limit=limit)
+        live = np.ones(len(idx), dtype=bool)
+        for t in range(limit):
+            a = acts[episode * limit + t]
+            r0, d0 = ora.step(a[idx].astype(np.int64))
+            obs, r1, d1, info = env.step(a)
+            where = (pool, episode, t)
+            assert np.array_equal(r1.cpu().numpy()[idx][live], r0[live]), where
+            assert np.array_equal(d1.cpu().numpy()[idx][live], d0[live]), where
+            cont = live & ~d0
+            assert np.array_equal(env.board.cpu().numpy()[idx][cont], ora.board[cont]), where
+            assert np.array_equal(env.goals.cpu().numpy()[idx][cont], ora.goals[cont]), where
+            assert np.array_equal(env.rng_state[idx][cont], ora.rng[cont]), where
+            if t < limit - 1:
+                live = cont          # an env that left early has already been reset: stop following it
+        assert d0[live].all() and live.sum() > len(idx) // 2
+        # every followed env was reset by the step kernel onto its next level
+        idx, level_of = idx[live], (level_of[live] + env.level_stride) % L
+        assert np.array_equal(env._t["level_id"].cpu().numpy()[idx], level_of), pool
+        assert env._t["num_steps"].cpu().numpy()[idx].max() == 0
+        state = env.rng_state[idx]
+        fresh = orc.OracleEnv([levels[l] for l in level_of], list(state), time_limit=limit)
+        assert np.array_equal(env.board.cpu().numpy()[idx], fresh.board), pool
+        obs = obs.cpu().numpy()
+        for k in range(0, len(idx), 9):     # the observation of a finished env is its next episode's first
+            want = orc.get_obs(fresh.board[k], fresh.goals[k], fresh.loc[k], fresh.exits[k], (25, 25),
+                               TRAIN_CHANNELS)
+            assert np.array_equal(obs[idx[k]], want), (pool, k)
