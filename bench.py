@@ -759,12 +759,12 @@ def run_ours(args, levels):
                               "call, outside the clock; max over ranks",
                     "us_per_step": 1e6 * e2e_s / K,
                     "host_us": {"launch": parts[0] / K, "wait": parts[1] / K,
-                                "note": "inside sl_env_step_host: validation + launch, then the spin on "
-                                        "the pinned completion word"},
+                                "note": "inside sl_env_step_host: validation + launch, then "
+                                        "cudaStreamSynchronize"},
                     "api": "BatchedSafeLifeEnv.step_host(auto_reset=True): uint8 actions in pinned "
                            "host memory read by the kernel, float32 reward + uint8 done/success/"
                            "times_up written to pinned host memory by the kernel (zero-copy over "
-                           "PCIe), completion word written in stream order, host read every step",
+                           "PCIe), stream synchronised, host read every step",
                     "back_to_back": {"value": n * world * K / e2e_b2b_s, "us_per_step": 1e6 * e2e_b2b_s / K,
                                      "note": "the same calls with no flush between them (state stays in L2)"},
                     "pipelined": None if pipelined is None else {

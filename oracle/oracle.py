@@ -211,6 +211,38 @@ def emd_lp(a, b, dist, extra_mass_penalty=-1.0):
     return float(res.fun + extra_mass_penalty * abs(a.sum() - b.sum()))
 
 
+def emd_pyemd_quantised(a, b, dist, extra_mass_penalty=-1.0):
+    """
+    pyemd 0.5.1's ``emd`` as it computes in floating point, restated from the
+    published FastEMD sources it wraps (Pele & Werman, emd_hat_impl.hpp:
+    ``emd_hat_gd_metric`` -> ``emd_hat_impl`` for non-integral types): mass common
+    to both histograms stays in place; masses and costs are scaled to integers
+    with MULT_FACTOR = 1e6 (``floor(x * 1e6 / max + 0.5)``), the integer
+    transportation problem is solved exactly, the result scaled back, and the
+    extra-mass penalty added in floating point.  pyemd itself is not installable
+    here, so this restatement is NOT pinned against it ("parity unpinned"); it
+    exists to BOUND how far an exact solver can be from what the reference's
+    dependency returns (tests/test_side_effects.py).
+    """
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    dist = np.asarray(dist, dtype=float)
+    common = np.minimum(a, b)
+    p, q = a - common, b - common
+    sum_p, sum_q, max_c = a.sum(), b.sum(), dist.max()
+    max_sum, min_sum = max(sum_p, sum_q), min(sum_p, sum_q)
+    if max_sum <= 0 or max_c <= 0:
+        return 0.0
+    pq_norm, c_norm = 1e6 / max_sum, 1e6 / max_c
+    ip = np.floor(p * pq_norm + 0.5)
+    iq = np.floor(q * pq_norm + 0.5)
+    ic = np.floor(dist * c_norm + 0.5)
+    d = emd_lp(ip, iq, ic, 0.0) / pq_norm / c_norm
+    if extra_mass_penalty < 0:
+        extra_mass_penalty = max_c
+    return float(d + (max_sum - min_sum) * extra_mass_penalty)
+
+
 def earth_mover_distance(a, b, tanh_scale=5.0, extra_mass_penalty=1.0):
     """side_effects.py:13-57 with its defaults (manhattan metric on the torus)."""
     a = np.asarray(a, dtype=float)

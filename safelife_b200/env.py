@@ -432,8 +432,7 @@ class BatchedSafeLifeEnv(object):
         One step with HOST buffers end to end: `actions` (array-like [N], values
         0..8) are placed in the pinned action buffer, the kernel reads them and
         writes reward / done / success / times_up straight into pinned host memory,
-        and the call returns once they are visible there (sl_env_step_host: the host
-        spins on a word of pinned memory written in stream order after the kernel).
+        and the call returns once they are visible there (sl_env_step_host).
         Returns numpy views (reward float32[N], done uint8[N]) that the next call
         overwrites.  `timing`: optional float64[2] numpy array receiving the
         microseconds spent in the launch and in the wait.  Runs on the stream that

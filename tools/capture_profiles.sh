@@ -1,0 +1,22 @@
+#!/bin/bash
+# ncu captures behind profiles/ (run on the GPU box through gpurun; reports land in gpurun_out/).
+#   bash tools/capture_profiles.sh r2
+# Numbers printed by a run under ncu are never bench values.
+set -u
+tag="${1:-r2}"
+out=gpurun_out
+full="ncu --set full --clock-control none --import-source on -f"
+# launch list of the bench command (kernel shares of the timed loops)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv \
+    --log-file $out/${tag}_launches_default.csv \
+    python bench.py --steps 20 --warmup 3 --no-sweep --no-cpu-baseline --no-configs > $out/${tag}_launches.log 2>&1
+# the step kernels, one launch each (after warm-up launches)
+timeout 300 $full -k regex:k_env_step_warp -s 6 -c 1 -o $out/${tag}_step_warp_4096 python tools/prof_step.py > /dev/null 2>&1
+timeout 300 $full -k regex:k_env_step_warp -s 6 -c 1 -o $out/${tag}_step_obs_warp_4096 python tools/prof_step.py --obs > /dev/null 2>&1
+timeout 300 $full -k regex:k_env_step_pipe -s 4 -c 1 -o $out/${tag}_step_pipe_65536 python tools/prof_step.py --envs 65536 --steps 8 > /dev/null 2>&1
+timeout 300 $full -k regex:k_env_step_pipe -s 4 -c 1 -o $out/${tag}_step_obs_pipe_65536 python tools/prof_step.py --envs 65536 --steps 8 --obs > /dev/null 2>&1
+timeout 300 $full -k regex:k_env_step_tile -s 6 -c 1 -o $out/${tag}_step_tile_nav50_4096 python tools/prof_step.py --pool navigation-50 > /dev/null 2>&1
+timeout 300 $full -k regex:k_env_step_tile -s 6 -c 1 -o $out/${tag}_step_obs_tile_nav50_4096 python tools/prof_step.py --pool navigation-50 --obs > /dev/null 2>&1
+timeout 300 $full -k regex:k_get_obs_warp -s 0 -c 1 -o $out/${tag}_get_obs_4096 python tools/prof_step.py > /dev/null 2>&1
+timeout 300 $full -k regex:k_multistep_tile -s 1 -c 1 -o $out/${tag}_multistep_tile_nav50_256 python tools/bench_side_effects.py navigation-50 256 300 > /dev/null 2>&1
+ls -la $out/${tag}_*.ncu-rep $out/${tag}_launches_default.csv
