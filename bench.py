@@ -719,6 +719,19 @@ def run_ours(args, levels):
     obs_only_bytes = n * (2 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
     step_obs_bytes = bytes_per_launch + obs_only_bytes
 
+    # ---- supplementary: the PUBLIC step() of the Python class, device-resident actions,
+    # K calls queued back to back and one sync: per-step wall clock including the Python
+    # layer (argument checks, the action copy, ctypes, output bookkeeping) ----
+    Kp = min(K, 300)
+    for t in range(3):
+        env.step(actions[t])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(Kp):
+        env.step(actions[Wm + t])
+    torch.cuda.synchronize()
+    public_step_us = 1e6 * allmax(time.perf_counter() - t0) / Kp
+
     # ---- supplementary: SafeLifeEnv.get_obs alone (what reset() returns) ----
     env.get_obs()
     barrier()
@@ -798,6 +811,11 @@ def run_ours(args, levels):
                         "auto-reset and the uint8[N,25,25,15] training observation written by one "
                         "launch (sl_env_step_obs); bytes = step bytes + goals read + obs written; "
                         "L2 flushed; max over ranks"},
+            "public_step": {
+                "us_per_step": public_step_us, "env_steps_per_s": n * world / (public_step_us * 1e-6),
+                "note": "supplementary: BatchedSafeLifeEnv.step(actions) -> (obs, reward, done, info) "
+                        "called %d times back to back with device-resident actions, wall clock "
+                        "incl. the Python layer, one sync at the end, no flush" % Kp},
             "obs": {
                 "ms": obs_ms, "bytes_per_launch": obs_bytes,
                 "achieved_gbs": obs_bytes / (obs_ms * 1e-3) / 1e9,

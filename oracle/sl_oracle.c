@@ -7,7 +7,7 @@
  * scalar implementation.  Parity of this restatement is pinned against the
  * compiled reference C extension (oracle/_ref, built by oracle/Makefile from
  * the sources under /root/reference) by tests/golden/make_golden.py and
- * tests/test_oracle_vs_golden.py -- see DESIGN.md "Oracle".
+ * tests/test_oracle_golden.py -- see DESIGN.md "Oracle".
  *
  * Every function states the rule declaratively (direct 3x3 gather, no
  * separable accumulator trick) and cites the reference lines it follows.
