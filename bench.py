@@ -766,7 +766,7 @@ def run_ours(args, levels):
             },
             "clocks": clocks,
             "e2e": {"value": n * world * K / e2e_s, "unit": "env-steps/s",
-                    "h2d_bytes_per_step": n, "d2h_bytes_per_step": 7 * n,
+                    "h2d_bytes_per_step": n, "d2h_bytes_per_step": 8 * n,
                     "timing": "wall clock (time.perf_counter) around every step_host call incl. the "
                               "host's read of the result; L2 flushed and device drained before each "
                               "call, outside the clock; max over ranks",
@@ -776,8 +776,9 @@ def run_ours(args, levels):
                                         "cudaStreamSynchronize"},
                     "api": "BatchedSafeLifeEnv.step_host(auto_reset=True): uint8 actions in pinned "
                            "host memory read by the kernel, float32 reward + uint8 done/success/"
-                           "times_up written to pinned host memory by the kernel (zero-copy over "
-                           "PCIe), stream synchronised, host read every step",
+                           "times_up written by the kernel into pinned host memory as one packed "
+                           "8-byte record per env (zero-copy over PCIe), stream synchronised, host "
+                           "read every step",
                     "back_to_back": {"value": n * world * K / e2e_b2b_s, "us_per_step": 1e6 * e2e_b2b_s / K,
                                      "note": "the same calls with no flush between them (state stays in L2)"},
                     "pipelined": None if pipelined is None else {

@@ -43,7 +43,7 @@ extern "C" {
 #define SL_ERR_CUDA      2   /* CUDA runtime error, see sl_last_error() */
 #define SL_ERR_NO_DEVICE 3   /* no usable CUDA device: there is no CPU fallback */
 
-#define SL_ABI_VERSION   2
+#define SL_ABI_VERSION   3
 
 /* ---- library plumbing ------------------------------------------------ */
 int sl_abi_version(void);
@@ -219,6 +219,12 @@ typedef struct SlEnvBatch {
     const int32_t  *pool_init_points; /* [n_levels] */
     const int32_t  *pool_required;    /* [n_levels] */
     const uint64_t *pool_spawn_thr;   /* [n_levels] */
+
+    /* optional (NULL: none): the step's outputs once more, packed 8 bytes per env
+     * { float reward; uint8 done, success, times_up, 0 } -- for host-driven loops that
+     * point this at pinned host memory: the 8 envs of a CTA then cross PCIe as ONE
+     * 64-byte write instead of four small ones */
+    uint64_t *host_out;               /* [n_envs] */
 } SlEnvBatch;
 
 /* One SafeLifeEnv.step for every env (safelife_env.py:148-201, single_agent):

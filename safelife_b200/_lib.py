@@ -19,7 +19,7 @@ _SRC = os.path.join(_PKG, "csrc")
 SL_OK, SL_ERR_ARG, SL_ERR_CUDA, SL_ERR_NO_DEVICE = 0, 1, 2, 3
 SL_RESET_NEXT_LEVEL, SL_RESET_KEEP_STATS = 1, 2
 SL_STEP_AUTO_RESET = 1
-SL_ABI_VERSION = 2
+SL_ABI_VERSION = 3
 SL_POOL_UNIFORM_TABLE, SL_POOL_STATIC_GOALS = 1, 2
 
 NVCC_FLAGS = [
@@ -64,7 +64,7 @@ class SlEnvBatch(ctypes.Structure):
                [(n, ctypes.c_void_p) for n in (
                    "board", "goals", "state", "reward", "done", "success", "times_up",
                    "pool_board", "pool_goals", "pool_loc", "pool_table", "pool_exits",
-                   "pool_init_points", "pool_required", "pool_spawn_thr")]
+                   "pool_init_points", "pool_required", "pool_spawn_thr", "host_out")]
 
 
 class SlObsSpec(ctypes.Structure):

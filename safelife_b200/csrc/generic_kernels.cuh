@@ -389,6 +389,9 @@ __device__ inline bool finish_step(const SlEnvBatch &B, int e, SlEnvState &st, i
     B.done[e] = done;
     B.success[e] = success;
     B.times_up[e] = times_up;
+    if (B.host_out != nullptr)
+        B.host_out[e] = (uint64_t)__float_as_uint(reward) | ((uint64_t)(done ? 1 : 0) << 32) |
+                        ((uint64_t)(success ? 1 : 0) << 40) | ((uint64_t)(times_up ? 1 : 0) << 48);
     if (out != nullptr) *out = {reward, done, times_up};
     return done;
 }

@@ -928,8 +928,14 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         if (GR) copy_slabs(sgoals, ggoals, group_bytes);
     }
     cs.table = stage_table(B, stable);
-    const int action = warp < nenv ? actions[e0 + warp] : 0;
-    __syncthreads();                      // mbarrier init / fallback copy / table visible
+    // the group's 8 actions with one 8-byte load (one PCIe read when they live in pinned
+    // host memory), handed out through shared memory
+    unsigned char *sact = smem_raw + 24;
+    const bool act8 = nenv == WARP_ENVS_PER_CTA && (((uintptr_t)(actions + e0)) & 7) == 0;
+    if (act8 && threadIdx.x == 32) *(uint64_t *)sact = *(const uint64_t *)(actions + e0);
+    int action = (!act8 && warp < nenv) ? actions[e0 + warp] : 0;
+    __syncthreads();                      // mbarrier init / fallback copy / table / actions visible
+    if (act8) action = sact[warp];
     if (bulk) mbar_wait(bar, 0);
     SL_TRACE_MARK(threadIdx.x == 0, 1);
 

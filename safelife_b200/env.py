@@ -407,22 +407,25 @@ class BatchedSafeLifeEnv(object):
         """
         Allocate pinned host buffers that the step kernel reads / writes in place
         (zero-copy over PCIe: pinned memory is device-addressable under UVA), for
-        callers whose policy lives on the host: see step_host().
+        callers whose policy lives on the host: see step_host().  The outputs cross
+        PCIe packed, 8 bytes per env (SlEnvBatch.host_out): the returned reward / done /
+        success / times_up arrays are strided numpy views of that one buffer.
         """
         n = self.num_envs
         self._host = {
             "actions": torch.zeros(n, dtype=torch.uint8).pin_memory(),
-            "reward": torch.zeros(n, dtype=torch.float32).pin_memory(),
-            "done": torch.zeros(n, dtype=torch.uint8).pin_memory(),
-            "success": torch.zeros(n, dtype=torch.uint8).pin_memory(),
-            "times_up": torch.zeros(n, dtype=torch.uint8).pin_memory(),
+            "out": torch.zeros(n, dtype=torch.int64).pin_memory(),
         }
-        fields = {name: getattr(self._batch, name) for name, _ in _lib.SlEnvBatch._fields_}
-        for k in ("reward", "done", "success", "times_up"):
-            fields[k] = self._host[k].data_ptr()
+        fields = {name: getattr(self._batches[0], name) for name, _ in _lib.SlEnvBatch._fields_}
+        fields["host_out"] = self._host["out"].data_ptr()
         self._batch_host = _lib.SlEnvBatch(**fields)
         self._batch_host_ref = ctypes.byref(self._batch_host)
-        self._host_np = {k: v.numpy() for k, v in self._host.items()}
+        packed = self._host["out"].numpy()
+        self._host_np = {
+            "actions": self._host["actions"].numpy(),
+            "reward": packed.view(np.float32)[0::2], "done": packed.view(np.uint8)[4::8],
+            "success": packed.view(np.uint8)[5::8], "times_up": packed.view(np.uint8)[6::8],
+        }
         self._host_actions_ptr = self._host["actions"].data_ptr()
         self._host_stream = self._stream()
         return self._host_np
@@ -431,8 +434,9 @@ class BatchedSafeLifeEnv(object):
         """
         One step with HOST buffers end to end: `actions` (array-like [N], values
         0..8) are placed in the pinned action buffer, the kernel reads them and
-        writes reward / done / success / times_up straight into pinned host memory,
-        and the call returns once they are visible there (sl_env_step_host).
+        writes reward / done / success / times_up (packed, 8 bytes per env) straight
+        into pinned host memory, and the call returns once they are visible there
+        (sl_env_step_host).
         Returns numpy views (reward float32[N], done uint8[N]) that the next call
         overwrites.  `timing`: optional float64[2] numpy array receiving the
         microseconds spent in the launch and in the wait.  Runs on the stream that
@@ -488,6 +492,7 @@ class BatchedSafeLifeEnv(object):
                 fields["goals"] += lo * cells * 2
                 fields["state"] += lo * 96
                 fields["reward"] += lo * 4
+                fields["host_out"] += lo * 8
                 for k in ("done", "success", "times_up"):
                     fields[k] += lo
                 batch = _lib.SlEnvBatch(**fields)

@@ -28,12 +28,12 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in names:
         assert hasattr(handle, name), name
     assert set(names) == set(_lib.PROTOTYPES), set(names) ^ set(_lib.PROTOTYPES)
-    assert handle.sl_abi_version() == 2
+    assert handle.sl_abi_version() == 3
 
 
 def test_struct_layout_matches_header():
-    # 7 int32 + padding + 15 pointers; SlEnvState is 96 bytes
-    assert ctypes.sizeof(_lib.SlEnvBatch) == 32 + 15 * 8
+    # 8 int32 + 16 pointers; SlEnvState is 96 bytes
+    assert ctypes.sizeof(_lib.SlEnvBatch) == 32 + 16 * 8
     assert _lib.SlEnvBatch.board.offset == 32
     dt = _lib.ENV_STATE_DTYPE
     assert dt.itemsize == 96 and dt.fields["loc"][1] == 32 and dt.fields["spawn_thr"][1] == 64
