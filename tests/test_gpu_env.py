@@ -657,3 +657,31 @@ def test_baseline_pools_across_an_episode_boundary(pool, n):
             want = orc.get_obs(fresh.board[k], fresh.goals[k], fresh.loc[k], fresh.exits[k], (25, 25),
                                TRAIN_CHANNELS)
             assert np.array_equal(obs[idx[k]], want), (pool, k)
+
+
+@pytest.mark.parametrize("shape,n", [((50, 50), 5), ((70, 30), 3), ((33, 33), 7), ((64, 64), 2)])
+def test_tile_kernel_ragged_batches_match_generic_kernel(shape, n):
+    """Batches that leave a CTA of the tiled kernel partly empty (and shapes whose env
+    groups cannot be bulk-copied), with the observation, against the generic kernel."""
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    H, W = shape
+    rs = np.random.default_rng(H + W + n)
+    levels = _random_levels(rs, 4, H, W)
+    rng = np.stack([orc.rng_from_seed(i) for i in range(n)])
+    envs = []
+    for kernel in (2, 1):
+        e = BatchedSafeLifeEnv(levels, n, time_limit=6, auto_reset=True, kernel=kernel,
+                               view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
+        e.set_rng_state(rng)
+        e.reset()
+        envs.append(e)
+    a, b = envs
+    assert "k_env_step_tile" in a.step_plan(obs=True)[0]
+    for t in range(15):
+        act = torch.from_numpy(rs.integers(0, 9, n).astype(np.uint8)).cuda()
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), (shape, t)
+        assert torch.equal(a.board, b.board) and torch.equal(a.goals, b.goals), (shape, t)
+        assert torch.equal(a._t["rng"], b._t["rng"]), (shape, t)

@@ -141,3 +141,31 @@ def test_wrapped_auto_reset_equals_driven_resets(kernel, baseline, ignore):
         assert torch.equal(a.unwrapped._wrap.baseline, b.unwrapped._wrap.baseline), t
         assert torch.equal(a.unwrapped._t["required"], b.unwrapped._t["required"]), t
     assert int(a.unwrapped._t["num_steps"].max()) < 9                   # episodes did restart
+
+
+def test_wrapped_pipelined_kernel_matches_generic_path():
+    """The wrapper epilogue inside the persistent pipelined kernel (a batch beyond two
+    waves) against the generic path's separate launches."""
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    from safelife_b200 import wrappers
+    d = gu.load_npz("wrapped_v1.0.npz")
+    levels = gu.levels_of(d)
+    n = 592 * 8 * 2 + 24
+    rs = np.random.default_rng(8)
+
+    def make(kernel):
+        base = BatchedSafeLifeEnv(levels, n, auto_reset=True, time_limit=5, view_shape=(5, 5),
+                                  kernel=kernel, seed=9)
+        return wrappers.training_stack(base, exit_difficulty=0.4, se_penalty=0.3)
+    a, b = make(2), make(1)
+    b.unwrapped.set_rng_state(a.unwrapped.rng_state)
+    assert "k_env_step_pipe" in a.unwrapped.step_plan(obs=True)[0]
+    a.reset()
+    b.reset()
+    for t in range(8):
+        act = torch.from_numpy(rs.integers(0, 9, n).astype(np.uint8)).cuda()
+        oa, ra, da, _ = a.step(act)
+        ob, rb, db, _ = b.step(act)
+        assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(oa, ob), t
+        assert torch.equal(a.unwrapped._wrap.wstate, b.unwrapped._wrap.wstate), t
