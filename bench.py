@@ -13,8 +13,9 @@ procedural boards (pool generated with the reference procgen, committed under
 tests/golden/pools), uniform random actions, time_limit 1000.  N GPUs run N
 independent shards of 4096 envs (weak scaling, no collective on the step path).
 
-Prints ONE JSON line on rank 0.  `value` is device-timed with the state
-resident in HBM and the L2 flushed between steps; `e2e` goes through the public
+Prints ONE JSON line on rank 0.  `value` is device-timed (one CUDA-event pair around
+the K steps) with the state resident in HBM and the steps rotating over batches that
+together exceed the L2, so that every launch reads from HBM; `e2e` goes through the public
 BatchedSafeLifeEnv API with pinned host actions in and host reward/done out.
 `--impl reference` times the reference's own C extension (oracle/_ref, compiled
 from the reference sources) on the host cores instead.
@@ -362,10 +363,47 @@ def timed_steps(torch, launch, K, flush, first=0):
     return sum(e[0].elapsed_time(e[1]) for e in ev) / K
 
 
+class Rotation(object):
+    """
+    Inputs larger than the L2: R independent batches of the same workload whose board
+    planes together are at least three times the L2, stepped round-robin.  When a batch comes
+    round again everything it touches has been evicted, so every launch reads its state
+    from HBM (and the previous launches' dirty lines are written back inside the timed
+    region) -- with no flush kernel between the launches and ONE event pair around the K
+    timed steps.  Each step is one launch over one batch of n envs, as in the workload.
+    """
+
+    def __init__(self, torch, dev, first_env, make_env, board_bytes):
+        l2 = int(torch.cuda.get_device_properties(dev).L2_cache_size)
+        self.l2_bytes = l2
+        self.R = int(max(2, min(96, -(-3 * l2 // board_bytes))))
+        self.board_bytes = board_bytes
+        self.envs = [first_env] + [make_env(r) for r in range(1, self.R)]
+
+    def note(self):
+        return ("inputs larger than L2: steps rotate over %d independent batches of the workload "
+                "(board planes %.1f MB each, %.0f MB together against %.0f MB of L2), so every "
+                "launch reads its batch from HBM; no flush inside or between the timed steps" % (
+                    self.R, self.board_bytes / 1e6, self.R * self.board_bytes / 1e6, self.l2_bytes / 1e6))
+
+    def timed(self, torch, launch, K, first=0):
+        """ms per step of `launch(env, t)` over K back-to-back steps, one CUDA-event pair."""
+        for r in range(self.R):                 # every batch has run this launch once (untimed)
+            launch(self.envs[r], first + r)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        torch.cuda.synchronize()
+        ev[0].record()
+        for t in range(K):
+            launch(self.envs[t % self.R], first + t)
+        ev[1].record()
+        torch.cuda.synchronize()
+        return ev[0].elapsed_time(ev[1]) / K
+
+
 def sweep(args, levels, dev, peak):
     """
-    The same device-timed measurement at larger batches (state beyond the L2 at
-    65536 envs), 60 steps each: where the kernel leaves the launch-latency regime;
+    The same device-timed measurement (rotating batches larger than the L2, one event
+    pair around 60 steps) at larger batches: where the kernel leaves the latency regime;
     with and without the observation in the same launch.
     """
     import ctypes
@@ -374,39 +412,42 @@ def sweep(args, levels, dev, peak):
     from safelife_b200.env import BatchedSafeLifeEnv
     out = []
     H, W = levels[0]["board"].shape
-    flush = _Flush(torch, dev, args.flush_mode)
+    pool = None
     for n in (16384, 65536):
-        env = BatchedSafeLifeEnv(levels, n, device=dev, kernel=args.kernel, time_limit=1000,
-                                 view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
-        env.reset()
+        def make(r):
+            e = BatchedSafeLifeEnv(pool if pool is not None else levels, n, device=dev,
+                                   kernel=args.kernel, time_limit=1000, view_shape=(25, 25),
+                                   output_channels=TRAIN_CHANNELS, seed=300 + r)
+            e.reset()
+            return e
+        env = make(0)
+        pool = env.pool
+        rot = Rotation(torch, dev, env, make, n * 2 * H * W)
         K = 60
-        actions = torch.randint(0, 9, (K + 5, n), device=dev, dtype=torch.uint8)
-        stream = env._stream()
-        spec = ctypes.byref(env._obs_specs[0])
+        actions = torch.randint(0, 9, (K + rot.R + 5, n), device=dev, dtype=torch.uint8)
 
-        def physics(t):
-            _lib.check(env._lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), args.kernel,
-                                            _lib.SL_STEP_AUTO_RESET, stream))
+        def physics(e, t):
+            _lib.check(e._lib.sl_env_step(e._batch_ref, actions[t].data_ptr(), args.kernel,
+                                          _lib.SL_STEP_AUTO_RESET, e._stream()))
 
-        def with_obs(t):
-            _lib.check(env._lib.sl_env_step_obs(env._batch_ref, actions[t].data_ptr(), spec,
-                                                args.kernel, _lib.SL_STEP_AUTO_RESET, stream))
-        for t in range(5):
-            physics(t)
-            with_obs(t)
-        ms = timed_steps(torch, physics, K, flush, 5)
-        ms_obs = timed_steps(torch, with_obs, K, flush, 5)
+        def with_obs(e, t):
+            _lib.check(e._lib.sl_env_step_obs(e._batch_ref, actions[t].data_ptr(),
+                                              ctypes.byref(e._obs_specs[0]), args.kernel,
+                                              _lib.SL_STEP_AUTO_RESET, e._stream()))
+        ms = rot.timed(torch, physics, K)
+        ms_obs = rot.timed(torch, with_obs, K)
         nbytes = step_bytes(H, W, n, 0)
         obs_bytes = nbytes + n * (2 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
         plan = env.step_plan()[0]
-        out.append({"envs": n, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3),
+        out.append({"envs": n, "batches": rot.R, "ms_per_step": ms, "env_steps_per_s": n / (ms * 1e-3),
                     "achieved_gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
                     "kernel": plan, "traffic": measured_traffic(plan, n, H, W),
                     "step_with_obs": {"ms": ms_obs, "env_steps_per_s": n / (ms_obs * 1e-3),
                                       "achieved_gbs": obs_bytes / (ms_obs * 1e-3) / 1e9,
                                       "frac": obs_bytes / (ms_obs * 1e-3) / 1e9 / peak,
                                       "kernel": env.step_plan(obs=True)[0]}})
-        del env
+        del env, rot
+        torch.cuda.empty_cache()
     return out
 
 
@@ -458,26 +499,39 @@ def other_configs(args, dev, world, rank, peak, barrier, allmax):
             continue
         levels = load_levels(path)
         H, W = levels[0]["board"].shape
-        env = BatchedSafeLifeEnv(levels, n, device=dev, kernel=args.kernel, time_limit=1000,
-                                 env_offset=rank * n, total_envs=n * world)
-        env.set_rng_state(seed_rng_states(4, n * world)[rank * n:(rank + 1) * n])
-        top = wrappers.SimpleSideEffectPenalty(env, penalty_coef=1.0) if penalty else env
-        top.reset()
-        actions = torch.randint(0, 9, (K + 5, n), device=dev, dtype=torch.uint8)
-        stream = env._stream()
+        states = seed_rng_states(4, n * world)[rank * n:(rank + 1) * n]
+        made = {}
 
-        def launch(t):
+        def make(r):
+            e = BatchedSafeLifeEnv(made["pool"] if made else levels, n, device=dev, kernel=args.kernel,
+                                   time_limit=1000, env_offset=rank * n + r * 7, total_envs=n * world)
+            made["pool"] = e.pool
+            st = states.copy()
+            st[:, 1] ^= np.uint64(r)                     # batch r: other streams, other first levels
+            e.set_rng_state(st)
+            top = wrappers.SimpleSideEffectPenalty(e, penalty_coef=1.0) if penalty else e
+            top.reset()
+            e._bench_top = top
+            return e
+        env = make(0)
+        rot = Rotation(torch, dev, env, make, n * 2 * H * W)
+        actions = torch.randint(0, 9, (K + rot.R + 5, n), device=dev, dtype=torch.uint8)
+
+        def launch(e, t):
             if penalty:
-                _lib.check(env._lib.sl_env_step_wrapped(
-                    env._batch_ref, actions[t].data_ptr(), None, env._wrap.fill_spec(0), args.kernel,
-                    _lib.SL_STEP_AUTO_RESET, stream))
+                _lib.check(e._lib.sl_env_step_wrapped(
+                    e._batch_ref, actions[t].data_ptr(), None, e._wrap.fill_spec(0), args.kernel,
+                    _lib.SL_STEP_AUTO_RESET, e._stream()))
             else:
-                _lib.check(env._lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), args.kernel,
-                                                _lib.SL_STEP_AUTO_RESET, stream))
+                _lib.check(e._lib.sl_env_step(e._batch_ref, actions[t].data_ptr(), args.kernel,
+                                              _lib.SL_STEP_AUTO_RESET, e._stream()))
         for t in range(5):
-            launch(t)
+            launch(env, t)
         barrier()
-        ms = allmax(timed_steps(torch, launch, K, flush, 5))
+        ms = allmax(rot.timed(torch, launch, K))
+        flushed_ms = None
+        if flush is not None:
+            flushed_ms = allmax(timed_steps(torch, lambda t: launch(env, t), min(K, 40), flush))
         dyn = int((env._t["static_goals"] == 2).sum())
         nbytes = step_bytes(H, W, n, dyn, baseline=penalty)
         entry = {
@@ -488,6 +542,7 @@ def other_configs(args, dev, world, rank, peak, barrier, allmax):
             "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
                          "algorithmic_bytes_per_launch": nbytes},
+            "l2": rot.note(), "single_step_flushed_ms": flushed_ms,
             "parity_spot_check": {"warp_kernels_equal_generic_kernel": kernels_agree(torch, levels, dev),
                                   "note": "64 envs x 16 steps, bit for bit; oracle parity: tests/"},
         }
@@ -505,7 +560,7 @@ def other_configs(args, dev, world, rank, peak, barrier, allmax):
             def occupancy(_t):
                 _lib.check(env._lib.sl_side_effect_occupancy(
                     init.data_ptr(), final.data_ptr(), counts.data_ptr(), L, H, W, thr.data_ptr(),
-                    steps_t.data_ptr(), samples, rng.data_ptr(), stream))
+                    steps_t.data_ptr(), samples, rng.data_ptr(), env._stream()))
             occupancy(0)
             occ_ms = allmax(timed_steps(torch, occupancy, 3, None))
             entry["episode_end"] = {
@@ -513,7 +568,8 @@ def other_configs(args, dev, world, rank, peak, barrier, allmax):
                         "per GPU, %d lead steps + 2 x %d counted steps each" % (L, lead, samples),
                 "ms": occ_ms, "board_steps_per_s": world * L * (lead + 2 * samples) / (occ_ms * 1e-3)}
         out.append(entry)
-        del env, top
+        del env, rot
+        torch.cuda.empty_cache()
     return out
 
 
@@ -576,16 +632,26 @@ def run_ours(args, levels):
     H, W = levels[0]["board"].shape
     # observations as the reference's training envs take them (env_factory.py:301-327):
     # 25x25 view, 15 channels; `value` is the step path alone, `step_with_obs` adds them
-    env = BatchedSafeLifeEnv(levels, n, device=dev, kernel=args.kernel, time_limit=1000,
-                             view_shape=(25, 25), output_channels=TRAIN_CHANNELS,
-                             env_offset=lo, total_envs=n * world)
-    env.set_rng_state(seed_rng_states(4, n * world)[lo:lo + n])   # global-index-derived streams
-    env.reset()
+    base_states = seed_rng_states(4, n * world)[lo:lo + n]          # global-index-derived streams
+    made = {}
+
+    def make_env(r):
+        e = BatchedSafeLifeEnv(made["pool"] if made else levels, n, device=dev, kernel=args.kernel,
+                               time_limit=1000, view_shape=(25, 25), output_channels=TRAIN_CHANNELS,
+                               env_offset=lo + 7 * r, total_envs=n * world)
+        made["pool"] = e.pool
+        st = base_states.copy()
+        st[:, 1] ^= np.uint64(r)                # batch r of the rotation: other streams, other levels
+        e.set_rng_state(st)
+        e.reset()
+        return e
+    env = make_env(0)
     K, Wm = args.steps, args.warmup
     g = torch.Generator(device=dev)
     g.manual_seed(2 + rank)
-    actions = torch.randint(0, 9, (K + Wm, n), generator=g, device=dev, dtype=torch.uint8)
     flush = None if args.no_flush else _Flush(torch, dev, args.flush_mode)
+    rot = Rotation(torch, dev, env, make_env, n * 2 * H * W)
+    actions = torch.randint(0, 9, (K + Wm + rot.R, n), generator=g, device=dev, dtype=torch.uint8)
     lib, bref = env._lib, env._batch_ref
     stream = env._stream()
     # generic kernel: the auto-reset is a second (masked) launch; warp kernels: fused
@@ -594,19 +660,29 @@ def run_ours(args, levels):
     if not fused:
         launches_per_step += 1
 
-    def step_kernels(t):
-        _lib.check(lib.sl_env_step(bref, actions[t].data_ptr(), args.kernel,
+    def step_of(e, t):
+        _lib.check(lib.sl_env_step(e._batch_ref, actions[t].data_ptr(), args.kernel,
                                    _lib.SL_STEP_AUTO_RESET, stream))
 
+    def step_kernels(t):
+        step_of(env, t)
+
     for t in range(Wm):
-        step_kernels(t)
+        step_of(rot.envs[t % rot.R], t)
     barrier()
-    # ---- value: device-timed, state resident in HBM, L2 flushed between steps ----
+    # ---- value: K steps back to back, device-timed with one event pair, every step's
+    # batch read from HBM (rotation over batches larger than the L2), max over ranks ----
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.mark()
-    step_ms = allmax(timed_steps(torch, step_kernels, K, flush, Wm))      # step incl. auto-reset
+    step_ms = allmax(rot.timed(torch, step_of, K, Wm))                     # step incl. auto-reset
     total_ms = step_ms * K
+    # the round-1 measurement, kept for continuity: ONE batch, the L2 flushed before every
+    # step, one event pair per step (each interval then also holds the launch latency of a
+    # lone kernel: see launch_floor_ms)
+    flushed_ms = None
+    if flush is not None:
+        flushed_ms = allmax(timed_steps(torch, step_kernels, min(K, 300), flush, Wm))
     dyn = int((env._t["static_goals"] == 2).sum())
     bytes_per_launch = step_bytes(H, W, n, dyn)
 
@@ -709,13 +785,20 @@ def run_ours(args, levels):
     obs_spec = ctypes.byref(env._obs_specs[0])
     obs_plan, obs_launches = env.step_plan(obs=True)
 
-    def step_obs(t):
-        _lib.check(lib.sl_env_step_obs(bref, actions[t].data_ptr(), obs_spec, args.kernel,
+    def step_obs_of(e, t):
+        _lib.check(lib.sl_env_step_obs(e._batch_ref, actions[t].data_ptr(),
+                                       ctypes.byref(e._obs_specs[0]), args.kernel,
                                        _lib.SL_STEP_AUTO_RESET, stream))
+
+    def step_obs(t):
+        step_obs_of(env, t)
     for t in range(3):
         step_obs(t)
     barrier()
-    step_obs_ms = allmax(timed_steps(torch, step_obs, min(K, 200), flush, Wm))
+    step_obs_ms = allmax(rot.timed(torch, step_obs_of, min(K, 300), Wm))
+    step_obs_flushed_ms = None
+    if flush is not None:
+        step_obs_flushed_ms = allmax(timed_steps(torch, step_obs, min(K, 200), flush, Wm))
     obs_only_bytes = n * (2 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
     step_obs_bytes = bytes_per_launch + obs_only_bytes
 
@@ -758,10 +841,9 @@ def run_ours(args, levels):
                 "workload": "%d envs/GPU x %dx%d %s procgen pool (%d levels), uniform random "
                             "actions, time_limit 1000, auto-reset" % (n, H, W, args.pool, len(levels)),
                 "envs_per_gpu": n, "board": [H, W], "pool": args.pool, "kernel": args.kernel,
-                "l2": ("state %.1f MB < L2; L2 flushed (256 MiB %s) between timed steps, flush "
-                       "not timed" % (n * (4 * H * W) / 1e6, args.flush_mode)) if flush is not None
-                      else "not flushed",
-                "timing": "mean of per-step CUDA-event intervals on the launch stream, max over ranks",
+                "l2": rot.note(),
+                "timing": "one CUDA-event pair on the launch stream around the K back-to-back "
+                          "steps (after the warm-up and one untimed launch per batch), max over ranks",
                 "parallelism": "dp%d (independent env shards, no collective)" % world,
             },
             "clocks": clocks,
@@ -800,6 +882,15 @@ def run_ours(args, levels):
                 "algorithmic_bytes_per_launch": bytes_per_launch,
                 "kernel_ms": step_ms, "dynamic_goal_envs": dyn,
             },
+            "single_step_flushed": {
+                "ms_per_step": flushed_ms,
+                "env_steps_per_s": None if not flushed_ms else n * world / (flushed_ms * 1e-3),
+                "frac": None if not flushed_ms else bytes_per_launch / (flushed_ms * 1e-3) / 1e9 / peak,
+                "launch_floor_ms": floor_ms,
+                "note": "supplementary (the round-1 headline): ONE batch, 256 MiB L2 flush before "
+                        "every step (not timed), one event pair per step; each interval also holds "
+                        "the launch latency of a lone kernel -- launch_floor_ms is an EMPTY kernel "
+                        "of the same launch shape in the same event pair after the same flush"},
             "launch_floor_ms": floor_ms,
             "step_with_obs": {
                 "ms": step_obs_ms, "env_steps_per_s": n * world / (step_obs_ms * 1e-3),
@@ -811,7 +902,8 @@ def run_ours(args, levels):
                 "note": "supplementary: SafeLifeEnv.step as the gym API returns it -- physics, "
                         "auto-reset and the uint8[N,25,25,15] training observation written by one "
                         "launch (sl_env_step_obs); bytes = step bytes + goals read + obs written; "
-                        "L2 flushed; max over ranks"},
+                        "timed like `value` (rotating batches, one event pair); max over ranks",
+                "single_step_flushed_ms": step_obs_flushed_ms},
             "public_step": {
                 "us_per_step": public_step_us, "env_steps_per_s": n * world / (public_step_us * 1e-6),
                 "note": "supplementary: BatchedSafeLifeEnv.step(actions) -> (obs, reward, done, info) "

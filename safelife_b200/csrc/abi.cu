@@ -608,8 +608,8 @@ static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const 
         rc = prepare_smem(sl::k_env_step_tile, smem);
         if (rc) return rc;
         const int bulk_ok = (((uintptr_t)batch->board | (uintptr_t)batch->goals | (uintptr_t)batch->state) & 15) == 0;
-        sl::k_env_step_tile<<<(batch->n_envs + sh.epc - 1) / sh.epc, sh.epc * sh.TW * 32, smem, st>>>(
-            *batch, obs ? O : no_obs, wrap ? *wrap : no_wrap, sh, actions, bulk_ok, flags);
+        sl::launch_pdl(sl::k_env_step_tile, (batch->n_envs + sh.epc - 1) / sh.epc, sh.epc * sh.TW * 32,
+                       smem, st, *batch, obs ? O : no_obs, wrap ? *wrap : no_wrap, sh, actions, bulk_ok, flags);
         return launch_status("k_env_step_tile");
     }
     if (kernel == 2 || (kernel == 0 && warp_ok)) {
@@ -712,8 +712,9 @@ static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int
             launches++;
         }
         if (p.single_groups > 0) {
-            n += snprintf(buf + n, sizeof buf - n, "%sk_env_step_warp<%s, %s%s> grid %d", n ? " + " : "",
-                          p.narrow ? "Narrow" : "Wide", goals, ob, p.single_groups);
+            n += snprintf(buf + n, sizeof buf - n, "%sk_env_step_warp<%s, %s%s> grid %d x %d envs",
+                          n ? " + " : "", p.narrow ? "Narrow" : "Wide", goals, ob, p.single_groups,
+                          p.single_epc);
             launches++;
         }
     } else {
@@ -745,8 +746,18 @@ __global__ void k_launch_floor(const __grid_constant__ SlEnvBatch B, int *sink) 
 int sl_launch_floor(const SlEnvBatch *batch, void *stream) {
     int rc = check_batch(batch);
     if (rc) return rc;
-    const int groups = batch->n_envs > 0 ? (batch->n_envs + 7) / 8 : 1;
-    k_launch_floor<<<groups, 256, 0, (cudaStream_t)stream>>>(*batch, nullptr);
+    int groups = batch->n_envs > 0 ? (batch->n_envs + 7) / 8 : 1, threads = 256;
+    if (batch->n_envs > 0 && fast_step_path(batch->H, batch->W) == 1) {     // the single-pass kernel's shape
+        DeviceProps props;
+        rc = device_props(&props);
+        if (rc) return rc;
+        const sl::StepPlan p = sl::plan_env_step_warp(*batch, nullptr, nullptr, props.sm_count, props.smem_per_sm);
+        if (p.single_groups > 0 && p.piped_groups == 0) {
+            groups = p.single_groups;
+            threads = p.single_epc * 32;
+        }
+    }
+    k_launch_floor<<<groups, threads, 0, (cudaStream_t)stream>>>(*batch, nullptr);
     return launch_status("k_launch_floor");
 }
 

@@ -320,10 +320,12 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
     SlEnvState *gstate = B.state + e0;
     const bool bulk = bulk_ok && (group_bytes & 15) == 0;
 
+    pdl_launch_dependents();
     if (bulk) {
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             mbar_init(bar + 1, 1);
+            pdl_wait();
             mbar_expect_tx(bar, (uint32_t)(group_bytes + state_bytes));
             bulk_load(sstate, gstate, state_bytes, bar);
             bulk_load(sboard, gboard, group_bytes, bar);
@@ -331,6 +333,7 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
             bulk_load(sgoals, ggoals, group_bytes, bar + 1);
         }
     } else {
+        pdl_wait();
         copy_slabs(sstate, gstate, state_bytes);
         copy_slabs(sboard, gboard, group_bytes);
         copy_slabs(sgoals, ggoals, group_bytes);
@@ -338,6 +341,7 @@ k_env_step_tile(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
     CtaShared cs;
     cs.scratch = nullptr;
     cs.lock = nullptr;
+    pdl_wait();
     cs.table = stage_table(B, stable);
     if (tile == 0 && lane == 0 && es < sh.epc) {
         sync_all[es].delta = 0;

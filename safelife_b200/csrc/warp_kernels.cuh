@@ -559,6 +559,20 @@ __device__ __forceinline__ void fence_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ---- programmatic dependent launch -------------------------------------------
+// The step kernels are launched with programmatic stream serialization
+// (launch_pdl below): the next launch of the stream may be scheduled onto the SMs
+// while this one drains, and runs its prologue (shared-memory carve-up, mbarrier
+// init) there.  `pdl_launch_dependents` allows that as soon as every CTA of this
+// grid has started; `pdl_wait` returns once the grids before this one have
+// completed and their memory is visible -- a kernel reads or writes nothing that
+// an earlier launch may have produced (state, boards, actions, the level pool)
+// before it.  Both are no-ops in a launch without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Optional per-CTA timeline for tools/trace_step.py (compiled in with -DSL_TRACE
 // into a separate diagnostic library, never into libsafelife_b200.so proper).
 #ifdef SL_TRACE
@@ -586,7 +600,7 @@ __device__ __forceinline__ void trace_mark(int slot) {
 //                          step of every episode, safelife_game.py:753-761 --
 //                          is advanced through one scratch slab per CTA.  A
 //                          broken promise costs time, not correctness.
-constexpr int WARP_SMEM_HEAD = 32;                                  // mbarrier, scratch lock
+constexpr int WARP_SMEM_HEAD = 48;                                  // 2 mbarriers, scratch lock, 16 action bytes
 constexpr int WARP_SMEM_TABLE = 72 * 4;                             // the pool's points table
 constexpr int WARP_SMEM_STATE = WARP_ENVS_PER_CTA * 96;             // SlEnvState[8]
 
@@ -594,12 +608,16 @@ __host__ __device__ inline int warp_slab_stride(int cells) {
     return (WARP_ENVS_PER_CTA * cells * 2 + 15) & ~15;
 }
 __host__ __device__ inline int warp_scratch_bytes(int cells) { return (cells * 2 + 15) & ~15; }
+// The single-pass kernel takes any number of envs per CTA (1..8), so a CTA's slabs may
+// start anywhere in a 16-byte unit of the board array: its shared-memory copy keeps
+// that offset (bulk copies move whole 16-byte units), hence 16 spare bytes per plane.
+__host__ __device__ inline int warp_slab_stride_any(int cells) { return warp_slab_stride(cells) + 16; }
 
 template <class G>
 __host__ __device__ inline size_t warp_step_smem_bytes(int cells, bool goals_resident, int obs_stage = 0) {
     return WARP_SMEM_HEAD + WARP_SMEM_TABLE + WARP_SMEM_STATE +
-           (goals_resident ? 2 * (size_t)warp_slab_stride(cells)
-                           : (size_t)warp_slab_stride(cells) + warp_scratch_bytes(cells)) +
+           (goals_resident ? 2 * (size_t)warp_slab_stride_any(cells)
+                           : (size_t)warp_slab_stride_any(cells) + warp_scratch_bytes(cells)) +
            2 * G::PAD_CELLS + (size_t)WARP_ENVS_PER_CTA * obs_stage;
 }
 
@@ -607,7 +625,7 @@ __host__ __device__ inline size_t warp_step_smem_bytes(int cells, bool goals_res
 // (SL_POOL_UNIFORM_TABLE): pricing a changed cell then never leaves the SM.
 __device__ __forceinline__ const int32_t *stage_table(const SlEnvBatch &B, int32_t *smem_table) {
     if (!(B.pool_flags & SL_POOL_UNIFORM_TABLE)) return nullptr;
-    if (threadIdx.x < 72) smem_table[threadIdx.x] = __ldg(B.pool_table + threadIdx.x);
+    for (int i = threadIdx.x; i < 72; i += blockDim.x) smem_table[i] = __ldg(B.pool_table + i);
     return smem_table;     // visible after the caller's next CTA barrier
 }
 
@@ -887,55 +905,74 @@ template <class G, bool GR, bool PW>
 __global__ void __launch_bounds__(WARP_ENVS_PER_CTA * 32, G::ROWS == 1 ? 4 : 2)
 k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ ObsParams O,
                 const __grid_constant__ SlWrapSpec Wp, const uint8_t *__restrict__ actions,
-                int bulk_ok, int flags, int first_group) {
+                int bulk_ok, int flags, int first_env, int epc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int cells = B.H * B.W;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int e0 = (first_group + blockIdx.x) * WARP_ENVS_PER_CTA;
-    const int nenv = min(WARP_ENVS_PER_CTA, B.n_envs - e0);
+    // CTA b steps envs [e0, e0 + nenv): epc (1..8) consecutive envs, one warp each.  The
+    // host picks epc so that every SM gets the same number of warps (plan_env_step_warp).
+    const int e0 = first_env + blockIdx.x * epc;
+    const int nenv = min(epc, B.n_envs - e0);
     const int group_bytes = nenv * cells * 2, state_bytes = nenv * 96;
+    // Bulk copies move whole 16-byte units.  The CTA's slabs start `mis` bytes into one
+    // (the arrays themselves are 16-byte aligned when bulk_ok), so the loads fetch the
+    // enclosing units -- a few cells of the neighbouring CTAs' envs come along and are
+    // never touched -- and the shared-memory slabs keep the offset; the stores write the
+    // whole units inside the CTA's range in bulk and the (< 16-byte) edges cell by cell.
+    const size_t byte0 = (size_t)e0 * cells * 2;
+    const int mis = bulk_ok ? (int)(byte0 & 15) : 0;
+    const int load_bytes = (mis + group_bytes + 15) & ~15;
+    const bool bulk = bulk_ok && group_bytes >= 64 &&
+                      byte0 - mis + load_bytes <= (((size_t)B.n_envs * cells * 2) & ~(size_t)15);
     uint64_t *bar = (uint64_t *)smem_raw;             // [0] state + boards, [1] goals
     int32_t *stable = (int32_t *)(smem_raw + WARP_SMEM_HEAD);
     SlEnvState *sstate = (SlEnvState *)(smem_raw + WARP_SMEM_HEAD + WARP_SMEM_TABLE);
-    uint16_t *sboard = (uint16_t *)(smem_raw + WARP_SMEM_HEAD + WARP_SMEM_TABLE + WARP_SMEM_STATE);
-    uint16_t *sgoals = sboard + warp_slab_stride(cells) / 2;   // GR: goal slabs; else: the scratch slab
+    unsigned char *rboard = smem_raw + WARP_SMEM_HEAD + WARP_SMEM_TABLE + WARP_SMEM_STATE;
+    unsigned char *rgoals = rboard + warp_slab_stride_any(cells);      // GR: goal slabs; else: the scratch slab
+    uint16_t *sboard = (uint16_t *)(rboard + (bulk ? mis : 0));
+    uint16_t *sgoals = (uint16_t *)(rgoals + (bulk && GR ? mis : 0));
     uint16_t *gboard = B.board + (size_t)e0 * cells;
     uint16_t *ggoals = B.goals + (size_t)e0 * cells;
     SlEnvState *gstate = B.state + e0;
-    const bool bulk = bulk_ok && (group_bytes & 15) == 0;
+    pdl_launch_dependents();
     SL_TRACE_MARK(threadIdx.x == 0, 0);
 
     CtaShared cs;
-    cs.scratch = sgoals;
+    cs.scratch = (uint16_t *)rgoals;
     cs.lock = (int *)(smem_raw + 16);
     if (bulk) {
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             mbar_init(bar + 1, 1);
             *cs.lock = 0;
-            mbar_expect_tx(bar, (uint32_t)(group_bytes + state_bytes));
+            pdl_wait();                   // nothing written by the launch before this one is read earlier
+            mbar_expect_tx(bar, (uint32_t)(load_bytes + state_bytes));
             bulk_load(sstate, gstate, state_bytes, bar);
-            bulk_load(sboard, gboard, group_bytes, bar);
+            bulk_load(rboard, (const unsigned char *)gboard - mis, load_bytes, bar);
             if (GR) {
-                mbar_expect_tx(bar + 1, (uint32_t)group_bytes);
-                bulk_load(sgoals, ggoals, group_bytes, bar + 1);
+                mbar_expect_tx(bar + 1, (uint32_t)load_bytes);
+                bulk_load(rgoals, (const unsigned char *)ggoals - mis, load_bytes, bar + 1);
             }
         }
     } else {
+        pdl_wait();
         if (threadIdx.x == 0) *cs.lock = 0;
         copy_slabs(sstate, gstate, state_bytes);
         copy_slabs(sboard, gboard, group_bytes);
         if (GR) copy_slabs(sgoals, ggoals, group_bytes);
     }
+    pdl_wait();
     cs.table = stage_table(B, stable);
-    // the group's 8 actions with one 8-byte load (one PCIe read when they live in pinned
-    // host memory), handed out through shared memory
-    unsigned char *sact = smem_raw + 24;
-    const bool act8 = nenv == WARP_ENVS_PER_CTA && (((uintptr_t)(actions + e0)) & 7) == 0;
-    if (act8 && threadIdx.x == 32) *(uint64_t *)sact = *(const uint64_t *)(actions + e0);
+    // the CTA's actions with one or two aligned 8-byte loads (PCIe reads when they live in
+    // pinned host memory), handed out through shared memory
+    unsigned char *sact = smem_raw + 32;
+    const int a0 = e0 & ~7;
+    const bool act8 = (((uintptr_t)actions) & 7) == 0 && ((e0 + nenv + 7) & ~7) <= B.n_envs;
+    if (act8 && warp == 0 && lane >= 1 && lane <= 2 && a0 + 8 * (lane - 1) < e0 + nenv)
+        ((uint64_t *)sact)[lane - 1] = *(const uint64_t *)(actions + a0 + 8 * (lane - 1));
     int action = (!act8 && warp < nenv) ? actions[e0 + warp] : 0;
     __syncthreads();                      // mbarrier init / fallback copy / table / actions visible
-    if (act8) action = sact[warp];
+    if (act8 && warp < nenv) action = sact[e0 - a0 + warp];
     if (bulk) mbar_wait(bar, 0);
     SL_TRACE_MARK(threadIdx.x == 0, 1);
 
@@ -962,42 +999,38 @@ k_env_step_warp(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
     fence_async_smem();                   // generic-proxy writes -> visible to the bulk engine
     SL_TRACE_MARK(threadIdx.x == 0, 4);
     int any_goals_dirty = __syncthreads_or(goals_dirty);
+    if (warp != 0) return;
     if (!PW) {
-        // the scalar tails of the group's 8 envs on 8 lanes of warp 0 (cheaper in issue
-        // slots than one tail per warp when nothing else follows the tail)
-        if (warp != 0) return;
+        // the scalar tails of the CTA's envs on lanes of warp 0 (cheaper in issue slots
+        // than one tail per warp when nothing else follows the tail)
         any_goals_dirty |= step_phase_b(B, cs, e0, nenv, sstate, sboard, GR ? sgoals : ggoals, flags, lane);
         fence_async_smem();
         __syncwarp();
-        if (bulk) {
-            if (lane == 0) {
-                bulk_store(gboard, sboard, group_bytes);
-                if (GR && any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
-                bulk_store(gstate, sstate, state_bytes);
-                bulk_commit_and_wait_read();
-            }
-        } else {
-            for (int i = lane; i < (group_bytes >> 1); i += 32) gboard[i] = sboard[i];
-            if (GR && any_goals_dirty)
-                for (int i = lane; i < (group_bytes >> 1); i += 32) ggoals[i] = sgoals[i];
-            for (int i = lane; i < (state_bytes >> 1); i += 32)
-                ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
-        }
-        return;
     }
     if (bulk) {
-        if (threadIdx.x == 0) {
-            bulk_store(gboard, sboard, group_bytes);
-            if (GR && any_goals_dirty) bulk_store(ggoals, sgoals, group_bytes);
+        // whole 16-byte units in bulk, the edges (shared with the neighbouring CTAs) by cell
+        const int head = (16 - mis) & 15;
+        const int body = (group_bytes - head) & ~15, tail = group_bytes - head - body;
+        if (lane == 0) {
+            bulk_store((unsigned char *)gboard + head, (unsigned char *)sboard + head, body);
+            if (GR && any_goals_dirty)
+                bulk_store((unsigned char *)ggoals + head, (unsigned char *)sgoals + head, body);
             bulk_store(gstate, sstate, state_bytes);
-            bulk_commit_and_wait_read();
         }
+        const int edge = lane < 8 ? lane : (head + body) / 2 + lane - 8;     // lanes 0-7: head, 8-15: tail
+        if (lane < 16 && (lane < 8 ? 2 * lane < head : 2 * (lane - 8) < tail)) {
+            gboard[edge] = sboard[edge];
+            if (GR && any_goals_dirty) ggoals[edge] = sgoals[edge];
+        }
+        if (lane == 0) bulk_commit_and_wait_read();
     } else {
-        copy_slabs(gboard, sboard, group_bytes);
-        if (GR && any_goals_dirty) copy_slabs(ggoals, sgoals, group_bytes);
-        copy_slabs(gstate, sstate, state_bytes);
+        for (int i = lane; i < (group_bytes >> 1); i += 32) gboard[i] = sboard[i];
+        if (GR && any_goals_dirty)
+            for (int i = lane; i < (group_bytes >> 1); i += 32) ggoals[i] = sgoals[i];
+        for (int i = lane; i < (state_bytes >> 1); i += 32)
+            ((uint16_t *)gstate)[i] = ((const uint16_t *)sstate)[i];
     }
-    SL_TRACE_MARK(threadIdx.x == 0, 5);
+    SL_TRACE_MARK(lane == 0, 5);
 }
 
 // ---- persistent, warp-specialised, multi-stage variant (narrow boards) ----------
@@ -1061,6 +1094,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
     cs.scratch = (uint16_t *)(stages + STAGES * stage_bytes);
     cs.lock = (int *)(smem_raw + PIPE_SMEM_HEAD - 16);
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full + s, 1);
@@ -1068,6 +1102,7 @@ k_env_step_pipe(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Ob
         }
         *cs.lock = 0;
     }
+    pdl_wait();
     cs.table = stage_table(B, stable);
     __syncthreads();
     const int first = blockIdx.x, stride = gridDim.x;
@@ -1150,6 +1185,26 @@ inline int env_knob(const char *name, int fallback) {
     return v ? atoi(v) : fallback;
 }
 
+// Launch with programmatic stream serialization (see pdl_wait above);
+// SAFELIFE_B200_PDL=0 launches plainly (A/B knob).
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int threads, size_t smem,
+                              cudaStream_t st, const Args &...args) {
+    static const bool pdl = env_knob("SAFELIFE_B200_PDL", 1) != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+
 // The shapes compiled in; `shape` picks one (tuning knob SAFELIFE_B200_PIPE_SHAPE).
 #define SL_PIPE_SHAPES(X) X(2, 4, true) X(3, 3, true) X(3, 4, false) X(4, 4, false) X(5, 3, false) X(6, 3, false)
 
@@ -1164,8 +1219,9 @@ struct StepPlan {
     int bulk_ok;
     int obs_stage;                  // staging bytes per warp of the fused observation (0: none)
     int pipe_stages, pipe_ctas;     // 0, 0: no pipelined launch
-    int pipe_grid, piped_groups;    // persistent CTAs and the groups they cover
-    int single_groups;              // groups left to the single-pass kernel (one CTA each)
+    int pipe_grid, piped_groups;    // persistent CTAs and the groups (of 8 envs) they cover
+    int single_groups;              // CTAs of the single-pass kernel,
+    int single_epc;                 // its envs per CTA (1..8), from env piped_groups * 8 on
 };
 
 // O: the observation the step writes, or nullptr.
@@ -1185,6 +1241,7 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, cons
     p.wrapped = Wp != nullptr;
     p.obs_stage = O ? obs_stage_bytes(O->vh, O->vw, O->n_channels) : 0;
     p.single_groups = groups;
+    p.single_epc = WARP_ENVS_PER_CTA;
     if (!p.narrow) return p;
     // pipelining pays once a CTA slot sees more than one group
     static const int shape_knob = env_knob("SAFELIFE_B200_PIPE_SHAPE", 0);   // stages * 10 + ctas
@@ -1209,6 +1266,18 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, cons
         p.pipe_grid = (full_groups + per_cta - 1) / per_cta;
         p.piped_groups = full_groups;
         p.single_groups = groups - full_groups;
+    } else {
+        // single pass: as many envs per CTA (= warps) as spread the batch evenly over the
+        // SMs' CTA slots -- 4096 envs are 586 CTAs of 7 (28 warps on every SM) rather than
+        // 512 CTAs of 8 (32 warps on some SMs, 24 on the others)
+        static const int epc_knob = env_knob("SAFELIFE_B200_EPC", 0);          // A/B knob
+        const int slots = sm_count * 4;
+        const int waves = (B.n_envs + slots * WARP_ENVS_PER_CTA - 1) / (slots * WARP_ENVS_PER_CTA);
+        int epc = (B.n_envs + slots * waves - 1) / (slots * waves);
+        if (epc_knob) epc = epc_knob;
+        epc = epc < 1 ? 1 : (epc > WARP_ENVS_PER_CTA ? WARP_ENVS_PER_CTA : epc);
+        p.single_epc = epc;
+        p.single_groups = (B.n_envs + epc - 1) / epc;
     }
     return p;
 }
@@ -1221,7 +1290,7 @@ inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const S
                                 const uint8_t *actions, int flags, const StepPlan &p,
                                 cudaStream_t st, Prep prep) {
     const int cells = B.H * B.W;
-    const int threads = WARP_ENVS_PER_CTA * 32;
+    const int threads = p.single_epc * 32;
     static const ObsParams no_obs = {};
     static const SlWrapSpec no_wrap = {};
     const ObsParams &obs = O ? *O : no_obs;
@@ -1233,8 +1302,9 @@ inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const S
         const size_t smem = warp_step_smem_bytes<G>(cells, R, p.obs_stage);                    \
         rc = prep((const void *)k_env_step_warp<G, R, PW>, smem);                              \
         if (rc) return rc;                                                                     \
-        k_env_step_warp<G, R, PW><<<p.single_groups, threads, smem, st>>>(                     \
-            B, obs, wrap, actions, p.bulk_ok, flags, p.piped_groups);                          \
+        launch_pdl(k_env_step_warp<G, R, PW>, p.single_groups, threads, smem, st,              \
+                   B, obs, wrap, actions, p.bulk_ok, flags,                                    \
+                   p.piped_groups * WARP_ENVS_PER_CTA, p.single_epc);                          \
     } while (0)
 #define SL_LAUNCH_WARP(G, R)                                                                   \
     do {                                                                                       \
@@ -1250,8 +1320,8 @@ inline int launch_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const S
             const size_t smem = pipe_smem_bytes(cells, S, R, p.obs_stage);                     \
             rc = prep((const void *)k_env_step_pipe<S, C, R, PW>, smem);                       \
             if (rc) return rc;                                                                 \
-            k_env_step_pipe<S, C, R, PW><<<p.pipe_grid, PIPE_THREADS, smem, st>>>(             \
-                B, obs, wrap, actions, flags, p.piped_groups);                                 \
+            launch_pdl(k_env_step_pipe<S, C, R, PW>, p.pipe_grid, PIPE_THREADS, smem, st,      \
+                       B, obs, wrap, actions, flags, p.piped_groups);                          \
         }
 #define SL_LAUNCH_SHAPE(S, C, R) SL_LAUNCH_SHAPE_PW(S, C, R, false) SL_LAUNCH_SHAPE_PW(S, C, R, true)
         SL_PIPE_SHAPES(SL_LAUNCH_SHAPE)

@@ -685,3 +685,39 @@ def test_tile_kernel_ragged_batches_match_generic_kernel(shape, n):
         assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), (shape, t)
         assert torch.equal(a.board, b.board) and torch.equal(a.goals, b.goals), (shape, t)
         assert torch.equal(a._t["rng"], b._t["rng"]), (shape, t)
+
+
+@pytest.mark.parametrize("n", [5, 600, 1500, 2000, 2900, 3500, 4096, 4700, 8192])
+@pytest.mark.parametrize("in_place", [True, False])
+def test_single_pass_kernel_any_envs_per_cta_matches_generic_kernel(n, in_place):
+    """The single-pass kernel spreads a batch evenly over the SMs with 1..8 envs per CTA
+    (a CTA's slabs then start anywhere inside a 16-byte unit of the board array: bulk
+    loads of the enclosing units, bulk stores of the inner ones, edges by cell), with
+    and without the observation in the launch, against the generic kernel."""
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(n)
+    levels = _random_levels(rs, 8, 25, 25)
+    rng = np.stack([orc.rng_from_seed(i) for i in range(n)])
+    envs = []
+    for kernel in (2, 1):
+        e = BatchedSafeLifeEnv(levels, n, time_limit=5, auto_reset=True, kernel=kernel,
+                               view_shape=(9, 9), output_channels=TRAIN_CHANNELS,
+                               goals_in_place=in_place)
+        e.set_rng_state(rng)
+        e.reset()
+        envs.append(e)
+    a, b = envs
+    assert "k_env_step_warp" in a.step_plan()[0]
+    for t in range(8):
+        act = torch.from_numpy(rs.integers(0, 9, n).astype(np.uint8)).cuda()
+        if t % 2:
+            oa, ra, da, _ = a.step(act)
+            ob, rb, db, _ = b.step(act)
+            assert torch.equal(oa, ob), t
+        else:
+            ra, da = (a.step_physics(act, auto_reset=True)[k] for k in ("reward", "done"))
+            rb, db = (b.step_physics(act, auto_reset=True)[k] for k in ("reward", "done"))
+        assert torch.equal(ra, rb) and torch.equal(da, db), t
+        assert torch.equal(a.board, b.board) and torch.equal(a.goals, b.goals), t
+        assert torch.equal(a._t["rng"], b._t["rng"]), t

@@ -45,7 +45,7 @@ def main():
     env.reset()
     lib = _lib.lib()
     lib.sl_debug_trace.argtypes = [ctypes.c_void_p]
-    grid = (n + 7) // 8
+    grid = n                   # upper bound: the single-pass kernel takes 1..8 envs per CTA
     buf = torch.zeros((grid, 8), dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     actions = torch.randint(0, 9, (24, n), device=dev, dtype=torch.uint8)
@@ -53,7 +53,9 @@ def main():
     for t in range(8):
         _lib.check(lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), 2, 1, stream))
     _lib.check(lib.sl_debug_trace(buf.data_ptr()))
-    names = ["start", "loaded", "phaseA", "barrier", "phaseB", "stored"]
+    # marks of the single-pass kernel without per-warp tails: 0 start, 1 loads landed,
+    # 2 phase A done (warp 0), 4 all warps through phase A (before the CTA barrier), 5 stores read
+    names, cols = ["start", "loaded", "phaseA", "phaseA_all", "stored"], [0, 1, 2, 4, 5]
     acc = []
     for t in range(8, 24):
         flush.fill_(t)
@@ -61,17 +63,18 @@ def main():
         torch.cuda.synchronize()
         _lib.check(lib.sl_env_step(env._batch_ref, actions[t].data_ptr(), 2, 1, stream))
         torch.cuda.synchronize()
-        a = buf.cpu().numpy()[:, :6].astype(np.float64)
+        a = buf.cpu().numpy()[:, cols].astype(np.float64)
         a = a[a[:, 0] > 0]
         acc.append(a - a[:, 0].min())
     a = np.concatenate(acc)
-    print("%d envs, %d CTAs x %d launches; ns since the first CTA start of the launch" % (n, grid, len(acc)))
-    print("%-8s %8s %8s %8s %8s" % ("mark", "min", "median", "p90", "max"))
+    print("%d envs, %d CTAs x %d launches (%s); ns since the first CTA start of the launch" % (
+        n, len(acc[0]), len(acc), env.step_plan()[0]))
+    print("%-10s %8s %8s %8s %8s" % ("mark", "min", "median", "p90", "max"))
     for k, name in enumerate(names):
         v = a[:, k]
-        print("%-8s %8.0f %8.0f %8.0f %8.0f" % (name, v.min(), np.median(v), np.percentile(v, 90), v.max()))
-    print("per-CTA durations (median ns): load %.0f  phaseA %.0f  barrier-wait %.0f  phaseB %.0f  store %.0f" % tuple(
-        np.median(a[:, k + 1] - a[:, k]) for k in range(5)))
+        print("%-10s %8.0f %8.0f %8.0f %8.0f" % (name, v.min(), np.median(v), np.percentile(v, 90), v.max()))
+    print("per-CTA durations (median ns): load %.0f  phaseA %.0f  wait for the CTA's warps %.0f  "
+          "tails + stores %.0f" % tuple(np.median(a[:, k + 1] - a[:, k]) for k in range(4)))
 
 
 if __name__ == "__main__":
