@@ -77,6 +77,8 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--quick", action="store_true",
+                    help="A/B runs: only `value` and `step_with_obs` (rotating batches), printed as a short line")
     return ap.parse_args()
 
 
@@ -681,11 +683,27 @@ def run_ours(args, levels):
     # step, one event pair per step (each interval then also holds the launch latency of a
     # lone kernel: see launch_floor_ms)
     flushed_ms = None
-    if flush is not None:
+    if flush is not None and not args.quick:
         flushed_ms = allmax(timed_steps(torch, step_kernels, min(K, 300), flush, Wm))
     dyn = int((env._t["static_goals"] == 2).sum())
     bytes_per_launch = step_bytes(H, W, n, dyn)
 
+    if args.quick:
+        def quick_obs(e, t):
+            _lib.check(lib.sl_env_step_obs(e._batch_ref, actions[t].data_ptr(),
+                                           ctypes.byref(e._obs_specs[0]), args.kernel,
+                                           _lib.SL_STEP_AUTO_RESET, stream))
+        obs_ms = allmax(rot.timed(torch, quick_obs, min(K, 300), Wm))
+        if rank == 0:
+            peak, _ = peaks()
+            ob = bytes_per_launch + n * (2 * H * W + 25 * 25 * len(TRAIN_CHANNELS))
+            emit({"quick": True, "envs": n, "pool": args.pool, "ms_per_step": step_ms,
+                  "frac": bytes_per_launch / (step_ms * 1e-3) / 1e9 / peak, "kernel": plan,
+                  "obs_ms": obs_ms, "obs_frac": ob / (obs_ms * 1e-3) / 1e9 / peak,
+                  "obs_kernel": env.step_plan(obs=True)[0], "batches": rot.R})
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- e2e: public API, host buffers, WALL CLOCK around every call ----
     # (a) step_host: the kernel reads the pinned action buffer and writes reward / done
     #     into pinned host memory itself (zero-copy over PCIe); the call returns when

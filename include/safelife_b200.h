@@ -232,7 +232,9 @@ typedef struct SlEnvBatch {
  * update_exit_colors -> reward / done / episode counters.  actions is
  * uint8[n_envs] (device), values as the reference's Discrete(9).
  * kernel: 0 = pick automatically, 1 = generic CTA-per-env kernel,
- * 2 = warp-per-env bit-plane kernel (requires H, W <= 64).
+ * 2 = the fast kernels (warp per env up to 32 x 32, tiles up to 120 x 120) or an error,
+ * 3 = as 2, with the persistent pipelined kernel wherever it applies (by default it
+ *     runs only where it measured faster: large batches without the observation).
  * flags: SL_STEP_AUTO_RESET resets every env that finished in this step in
  * the same call, exactly as sl_env_reset(batch, done, NULL,
  * SL_RESET_NEXT_LEVEL | SL_RESET_KEEP_STATS) would (the batched form of
@@ -356,6 +358,45 @@ int sl_env_step_host(const SlEnvBatch *batch, const uint8_t *actions, int kernel
 int sl_env_step_submit(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                        void *stream, uint32_t *flag, uint32_t seq);
 int sl_host_wait(const uint32_t *flag, uint32_t seq, void *stream);
+
+/* ---- host sessions: many host-driven steps, one resident kernel --------------
+ * For a policy that lives on the host (actions in, reward / done out, once per
+ * host round trip: the CPU form of BaseAlgo.act_on_envs, training/base_algo.py:
+ * 231-236) a launch per step is mostly launch and completion latency.  A session
+ * keeps one kernel resident: the envs stay in shared memory, the host posts a
+ * step by writing tagged actions into pinned memory, the kernel answers by
+ * writing the packed result records (SlEnvBatch.host_out) and a sequence number
+ * into pinned memory.  Boards up to 32 x 32, batches whose CTAs are all resident
+ * at once (about 4700 envs per GPU); physics + auto-reset, no observation.
+ * The caller allocates the mailbox:
+ *   host_actions  pinned, n_pad = (n_envs + 15) & ~15 bytes, zeroed
+ *   dev_actions   device, 2 * n_pad bytes
+ *   dev_ctrl      device, 4 x uint32, zeroed
+ *   host_ctrl     pinned, 4 x uint32: [0] last completed step, [1] alive,
+ *                 [2] written by the host: 1 = end the session
+ * While a session is open the batch's state in HBM is stale and no other call
+ * may touch the batch; other CUDA work on the device waits for the session to
+ * end (it ends by itself after idle_timeout_ms without a step). */
+typedef struct SlHostSession {
+    uint8_t *host_actions;
+    uint8_t *dev_actions;
+    uint32_t *dev_ctrl;
+    uint32_t *host_ctrl;
+    uint32_t idle_timeout_ms;
+    uint32_t seq;           /* steps posted in this session (library-owned) */
+    int32_t n_envs;         /* library-owned */
+    int32_t reserved;
+} SlHostSession;
+#define SL_SESSION_ENDED 4  /* sl_host_session_step: the session has ended (idle timeout); begin again */
+/* Starts the session kernel on `stream` (the batch must have host_out set and all
+ * its arrays 16-byte aligned).  flags as for sl_env_step. */
+int sl_host_session_begin(const SlEnvBatch *batch, SlHostSession *session, int flags, void *stream);
+/* One step: posts actions[n_envs] (host memory, values 0..8) and returns when the
+ * result records of the step are in host_out.  No CUDA call is made.  timing_us
+ * (may be NULL): [0] posting, [1] waiting.  SL_SESSION_ENDED: nothing was stepped. */
+int sl_host_session_step(SlHostSession *session, const uint8_t *actions, double *timing_us);
+/* Ends the session and waits for the kernel: the batch's state is back in HBM. */
+int sl_host_session_end(SlHostSession *session, void *stream);
 
 /* SafeLifeEnv.reset (safelife_env.py:203-218) for every env whose mask byte is
  * non-zero (mask NULL = all envs): copy a level from the pool, then

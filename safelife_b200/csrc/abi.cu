@@ -22,6 +22,7 @@
 #include "wrap.cuh"
 #include "warp_kernels.cuh"
 #include "tile_kernels.cuh"
+#include "session.cuh"
 
 namespace {
 
@@ -590,8 +591,10 @@ static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const 
     }
     if (batch->n_envs == 0) return SL_OK;
     if (!actions) return fail(SL_ERR_ARG, "null actions");
-    if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
+    if (kernel < 0 || kernel > 3) return fail(SL_ERR_ARG, "kernel must be 0, 1, 2 or 3");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool prefer_pipe = kernel == 3;
+    if (kernel == 3) kernel = 2;
     const int path = fast_step_path(batch->H, batch->W);
     bool warp_ok = path != 0;
     if (kernel == 2 && !warp_ok)
@@ -617,7 +620,7 @@ static int env_step_impl(const SlEnvBatch *batch, const uint8_t *actions, const 
         rc = device_props(&props);
         if (rc) return rc;
         const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, wrap,
-                                                      props.sm_count, props.smem_per_sm);
+                                                      props.sm_count, props.smem_per_sm, prefer_pipe);
         rc = sl::launch_env_step_warp(*batch, obs ? &O : nullptr, wrap, actions, flags, p, st,
                                       [](const void *fn, size_t smem) { return prepare_smem_ptr(fn, smem); });
         if (rc) return rc;
@@ -682,9 +685,11 @@ static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int
         rc = check_obs_spec(obs);
         if (rc) return rc;
     }
-    if (kernel < 0 || kernel > 2) return fail(SL_ERR_ARG, "kernel must be 0, 1 or 2");
+    if (kernel < 0 || kernel > 3) return fail(SL_ERR_ARG, "kernel must be 0, 1, 2 or 3");
     char buf[320];
     int launches = 0;
+    const bool prefer_pipe = kernel == 3;
+    if (kernel == 3) kernel = 2;
     const int path = fast_step_path(batch->H, batch->W);
     const bool warp_ok = path != 0;
     if (batch->n_envs == 0) {
@@ -702,7 +707,7 @@ static int env_step_plan_impl(const SlEnvBatch *batch, const SlObsSpec *obs, int
         sl::ObsParams O;
         if (obs) O = sl::make_obs_params(*obs);
         const sl::StepPlan p = sl::plan_env_step_warp(*batch, obs ? &O : nullptr, nullptr,
-                                                      props.sm_count, props.smem_per_sm);
+                                                      props.sm_count, props.smem_per_sm, prefer_pipe);
         const char *goals = p.goals_resident ? "goals resident" : "goals in place";
         const char *ob = p.obs ? ", obs fused" : "";
         int n = 0;
@@ -884,6 +889,102 @@ int sl_env_step_host(const SlEnvBatch *batch, const uint8_t *actions, int kernel
 int sl_env_step_sync(const SlEnvBatch *batch, const uint8_t *actions, int kernel, int flags,
                      void *stream) {
     return sl_env_step_host(batch, actions, kernel, flags, stream, nullptr);
+}
+
+// ---- host sessions (session.cuh) -----------------------------------------------
+int sl_host_session_begin(const SlEnvBatch *batch, SlHostSession *s, int flags, void *stream) {
+    int rc = check_batch(batch);
+    if (rc) return rc;
+    if (!s || !s->host_actions || !s->dev_actions || !s->dev_ctrl || !s->host_ctrl)
+        return fail(SL_ERR_ARG, "null pointer in SlHostSession");
+    if (flags & ~SL_STEP_AUTO_RESET) return fail(SL_ERR_ARG, "unknown step flags");
+    if (batch->n_envs < 1) return fail(SL_ERR_ARG, "empty batch");
+    if (!batch->host_out) return fail(SL_ERR_ARG, "a host session needs SlEnvBatch.host_out");
+    if (fast_step_path(batch->H, batch->W) != 1)
+        return fail(SL_ERR_ARG, "host sessions take boards up to 32 x 32 (got %d x %d)", batch->H, batch->W);
+    if ((((uintptr_t)batch->board | (uintptr_t)batch->goals | (uintptr_t)batch->state |
+          (uintptr_t)s->host_actions | (uintptr_t)s->dev_actions) & 15) != 0)
+        return fail(SL_ERR_ARG, "host sessions need 16-byte aligned arrays");
+    DeviceProps props;
+    rc = device_props(&props);
+    if (rc) return rc;
+    const int cells = batch->H * batch->W;
+    const bool resident = !(batch->pool_flags & SL_POOL_STATIC_GOALS);
+    const void *fn = resident ? (const void *)sl::k_env_session<true> : (const void *)sl::k_env_session<false>;
+    const size_t smem = sl::warp_step_smem_bytes<sl::Narrow>(cells, resident, 0);
+    rc = prepare_smem_ptr(fn, smem);
+    if (rc) return rc;
+    // every CTA must be resident at once: as many envs per CTA (= warps) as that takes
+    int epc = 0, workers = 0;
+    for (int e = 1; e <= sl::WARP_ENVS_PER_CTA && !epc; e++) {
+        int per_sm = 0;
+        SL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, e * 32, smem));
+        const int w = (batch->n_envs + e - 1) / e;
+        if (w + 1 <= per_sm * props.sm_count) {
+            epc = e;
+            workers = w;
+        }
+    }
+    if (!epc)
+        return fail(SL_ERR_ARG, "a host session keeps every env resident: %d envs of %d x %d are too many",
+                    batch->n_envs, batch->H, batch->W);
+    volatile uint32_t *hc = s->host_ctrl;
+    hc[0] = 0;
+    hc[1] = 1;
+    hc[2] = 0;
+    s->seq = 0;
+    s->n_envs = batch->n_envs;
+    cudaStream_t st = (cudaStream_t)stream;
+    SL_CUDA(cudaMemsetAsync(s->dev_ctrl, 0, 4 * sizeof(uint32_t), st));
+    const int n_pad = (batch->n_envs + 15) & ~15;
+    memset(s->host_actions, 0, (size_t)n_pad);
+    sl::SessionParams P;
+    P.host_actions = s->host_actions;
+    P.dev_actions = s->dev_actions;
+    P.dev_ctrl = s->dev_ctrl;
+    P.host_ctrl = s->host_ctrl;
+    P.n_pad = n_pad;
+    P.idle_ns = (unsigned long long)(s->idle_timeout_ms ? s->idle_timeout_ms : 200) * 1000000ull;
+    if (resident)
+        sl::k_env_session<true><<<workers + 1, epc * 32, smem, st>>>(*batch, P, flags, epc, workers);
+    else
+        sl::k_env_session<false><<<workers + 1, epc * 32, smem, st>>>(*batch, P, flags, epc, workers);
+    return launch_status("k_env_session");
+}
+
+int sl_host_session_step(SlHostSession *s, const uint8_t *actions, double *timing_us) {
+    if (!s || !actions) return fail(SL_ERR_ARG, "null pointer");
+    volatile uint32_t *hc = s->host_ctrl;
+    if (hc[1] == 0) return SL_SESSION_ENDED;
+    const double t0 = timing_us ? now_us() : 0.0;
+    const uint32_t seq = s->seq + 1;
+    const uint8_t tag = (uint8_t)((seq & 15u) << 4);
+    const int n = s->n_envs, n_pad = (n + 15) & ~15;
+    uint8_t *dst = s->host_actions;
+    for (int i = 0; i < n; i++) dst[i] = (uint8_t)((actions[i] & 15u) | tag);
+    for (int i = n; i < n_pad; i++) dst[i] = tag;
+    __sync_synchronize();
+    const double t1 = timing_us ? now_us() : 0.0;
+    while (hc[0] != seq) {
+        if (hc[1] == 0 && hc[0] != seq) return SL_SESSION_ENDED;      // idle timeout raced the post
+        __builtin_ia32_pause();
+    }
+    s->seq = seq;
+    if (timing_us) {
+        timing_us[0] = t1 - t0;
+        timing_us[1] = now_us() - t1;
+    }
+    return SL_OK;
+}
+
+int sl_host_session_end(SlHostSession *s, void *stream) {
+    if (!s || !s->host_ctrl) return fail(SL_ERR_ARG, "null pointer");
+    volatile uint32_t *hc = s->host_ctrl;
+    hc[2] = 1;
+    __sync_synchronize();
+    SL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    hc[1] = 0;
+    return SL_OK;
 }
 
 int sl_env_reset(const SlEnvBatch *batch, const uint8_t *mask, const int32_t *new_level,

@@ -1226,7 +1226,7 @@ struct StepPlan {
 
 // O: the observation the step writes, or nullptr.
 inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, const SlWrapSpec *Wp,
-                                   int sm_count, int smem_per_sm) {
+                                   int sm_count, int smem_per_sm, bool prefer_pipe = false) {
     StepPlan p = {};
     const int cells = B.H * B.W;
     const int groups = (B.n_envs + WARP_ENVS_PER_CTA - 1) / WARP_ENVS_PER_CTA;
@@ -1258,7 +1258,12 @@ inline StepPlan plan_env_step_warp(const SlEnvBatch &B, const ObsParams *O, cons
     // (measured crossover: the single-pass kernel wins up to about two waves of its 4 CTAs
     // per SM -- 8192 envs: 18.4 vs 19.2 us, 16384 envs: 27.2 vs 25.6 us)
     static const int min_waves = env_knob("SAFELIFE_B200_PIPE_MIN_WAVES", 2);   // tuning knob
-    if (p.bulk_ok && full_groups > sm_count * 4 * min_waves) {
+    // With the observation in the launch the single-pass kernel wins at every batch size
+    // (28-32 warps per SM against the pipeline's 24 stencil warps; rotating batches, us per
+    // step: 16384 envs 58.9 vs 70.6, 32768 envs 109 vs 136, 65536 envs 215 vs 255), so the
+    // pipeline then runs only on request (kernel 3).
+    const bool pipe_pays = prefer_pipe || !p.obs;
+    if (p.bulk_ok && pipe_pays && full_groups > sm_count * 4 * (prefer_pipe ? 1 : min_waves)) {
         const int slots = sm_count * ctas;
         const int per_cta = (full_groups + slots - 1) / slots;      // same trip count everywhere
         p.pipe_stages = stages;

@@ -287,10 +287,12 @@ class BatchedSafeLifeEnv(object):
     @property
     def board(self):
         """uint16 [N,H,W] view of the device boards (SafeLifeGame.board layout)."""
+        self.end_host_session()
         return self._t["board"].view(torch.uint16)
 
     @property
     def goals(self):
+        self.end_host_session()
         return self._t["goals"].view(torch.uint16)
 
     @property
@@ -301,12 +303,17 @@ class BatchedSafeLifeEnv(object):
     @property
     def rng_state(self):
         """uint64[N,4] PCG64 words as a numpy array (host copy)."""
+        self.end_host_session()
         return self._t["rng"].contiguous().cpu().numpy().view(np.uint64)
 
     def set_rng_state(self, states):
         self._t["rng"].copy_(_as_i64(states))
 
     def _stream(self):
+        # every launch path comes through here: an open host session is closed first
+        # (its kernel holds the envs in shared memory and the GPU with them)
+        if getattr(self, "_session_open", False):
+            self.end_host_session()
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # -------------------------------------------------------------- gym API
@@ -442,6 +449,8 @@ class BatchedSafeLifeEnv(object):
         microseconds spent in the launch and in the wait.  Runs on the stream that
         was current when enable_host_io() was called.
         """
+        if getattr(self, "_session_open", False):
+            return self._session_step(actions, timing)
         if getattr(self, "_host", None) is None:
             self.enable_host_io()
         h = self._host_np
@@ -461,6 +470,67 @@ class BatchedSafeLifeEnv(object):
                                                     self.kernel, flags, self._host_stream, tptr)
         if status:
             _lib.check(status)
+        return h["reward"], h["done"]
+
+    # ---- host sessions: many host-driven steps on one resident kernel -------------
+    def begin_host_session(self, auto_reset=None, idle_timeout_ms=200):
+        """
+        Open a host session (sl_host_session_begin): one kernel stays resident, keeps
+        the envs in shared memory and steps them whenever step_host() posts actions,
+        so a host-driven step costs a PCIe round trip instead of a kernel launch and a
+        stream synchronisation.  Boards up to 32 x 32 and batches that fit the GPU at
+        once (about 4700 envs); physics + auto-reset only.  Until end_host_session()
+        the env's tensors are stale and only step_host() may be used; other CUDA work
+        on the device waits.  The session ends by itself after `idle_timeout_ms`
+        without a step and is reopened by the next step_host().
+        """
+        if getattr(self, "_host", None) is None:
+            self.enable_host_io()
+        if self._wrap is not None:
+            raise ValueError("host sessions step the bare env (no training wrappers)")
+        n_pad = (self.num_envs + 15) & ~15
+        if getattr(self, "_session_bufs", None) is None:
+            self._session_bufs = {
+                "host_actions": torch.zeros(n_pad, dtype=torch.uint8).pin_memory(),
+                "host_ctrl": torch.zeros(4, dtype=torch.int32).pin_memory(),
+                "dev_actions": torch.zeros(2 * n_pad, dtype=torch.uint8, device=self.device),
+                "dev_ctrl": torch.zeros(4, dtype=torch.int32, device=self.device),
+            }
+        b = self._session_bufs
+        self._session = _lib.SlHostSession(
+            host_actions=b["host_actions"].data_ptr(), dev_actions=b["dev_actions"].data_ptr(),
+            dev_ctrl=b["dev_ctrl"].data_ptr(), host_ctrl=b["host_ctrl"].data_ptr(),
+            idle_timeout_ms=int(idle_timeout_ms))
+        self._session_ref = ctypes.byref(self._session)
+        auto = self.auto_reset if auto_reset is None else auto_reset
+        self._session_flags = _lib.SL_STEP_AUTO_RESET if auto else 0
+        self._session_args = (auto_reset, idle_timeout_ms)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream(self.device).synchronize()
+            _lib.check(self._lib.sl_host_session_begin(self._batch_host_ref, self._session_ref,
+                                                       self._session_flags, self._host_stream))
+        self._session_open = True
+
+    def end_host_session(self):
+        """Close the host session: the envs are written back and every method works again."""
+        if getattr(self, "_session_open", False):
+            self._session_open = False
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.sl_host_session_end(self._session_ref, self._host_stream))
+
+    def _session_step(self, actions, timing):
+        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        if a.shape != (self.num_envs,):
+            raise ValueError("actions must have shape (num_envs,)")
+        tptr = None if timing is None else timing.ctypes.data
+        status = self._lib.sl_host_session_step(self._session_ref, a.ctypes.data, tptr)
+        if status == _lib.SL_SESSION_ENDED:      # idle timeout: the state is back in HBM; reopen
+            self.end_host_session()
+            self.begin_host_session(*self._session_args)
+            status = self._lib.sl_host_session_step(self._session_ref, a.ctypes.data, tptr)
+        if status:
+            _lib.check(status)
+        h = self._host_np
         return h["reward"], h["done"]
 
     # ---- host-driven loops with several groups of envs in flight -----------------

@@ -413,7 +413,9 @@ def test_fused_observation_pipelined_kernel(in_place):
     rs = np.random.default_rng(5)
     n = 592 * 8 * 2 + 8 * 3 + 5
     base = _random_levels(rs, 32, 25, 25)
-    env = BatchedSafeLifeEnv(base, n, time_limit=6, auto_reset=True, kernel=2, goals_in_place=in_place,
+    # kernel 3: the pipelined kernel also with the observation in the launch (the default
+    # plan then prefers the single-pass kernel, which measured faster)
+    env = BatchedSafeLifeEnv(base, n, time_limit=6, auto_reset=True, kernel=3, goals_in_place=in_place,
                              view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
     ref = BatchedSafeLifeEnv(base, n, time_limit=6, auto_reset=True, kernel=2, goals_in_place=in_place,
                              view_shape=(25, 25), output_channels=TRAIN_CHANNELS)
@@ -721,3 +723,40 @@ def test_single_pass_kernel_any_envs_per_cta_matches_generic_kernel(n, in_place)
         assert torch.equal(ra, rb) and torch.equal(da, db), t
         assert torch.equal(a.board, b.board) and torch.equal(a.goals, b.goals), t
         assert torch.equal(a._t["rng"], b._t["rng"]), t
+
+
+@pytest.mark.parametrize("n,in_place", [(64, True), (4096, True), (1000, False), (4700, False)])
+def test_host_session_matches_launch_per_step(n, in_place):
+    """A host session (one resident kernel, actions and results through pinned-memory
+    mailboxes) steps exactly like one launch per step -- rewards, flags, boards, goals,
+    RNG -- across auto-resets, across an idle timeout that ends the session kernel, and
+    when the session is closed by touching the env."""
+    import time
+    import torch
+    from safelife_b200.env import BatchedSafeLifeEnv
+    rs = np.random.default_rng(n)
+    levels = _random_levels(rs, 8, 25, 25)
+    rng = np.stack([orc.rng_from_seed(i % 311) for i in range(n)])
+    envs = []
+    for _ in range(2):
+        e = BatchedSafeLifeEnv(levels, n, time_limit=7, auto_reset=True, kernel=2, goals_in_place=in_place)
+        e.set_rng_state(rng)
+        e.reset()
+        envs.append(e)
+    a, b = envs
+    a.begin_host_session(idle_timeout_ms=50)
+    for t in range(40):
+        act = rs.integers(0, 9, n).astype(np.uint8)
+        if t == 20:
+            time.sleep(0.2)                       # the session kernel gives up; the next step reopens it
+        if t == 30:
+            assert torch.equal(a.board, b.board)  # closes the session; the next step runs as a launch
+            a.begin_host_session(idle_timeout_ms=50)
+        ra, da = a.step_host(act)
+        rb, db = b.step_host(act)
+        assert np.array_equal(ra, rb) and np.array_equal(da, db), t
+        assert np.array_equal(a._host_np["success"], b._host_np["success"]), t
+        assert np.array_equal(a._host_np["times_up"], b._host_np["times_up"]), t
+    a.end_host_session()
+    assert torch.equal(a.board, b.board) and torch.equal(a.goals, b.goals)
+    assert torch.equal(a._t["state"], b._t["state"])

@@ -158,7 +158,7 @@ def test_wrapped_pipelined_kernel_matches_generic_path():
         base = BatchedSafeLifeEnv(levels, n, auto_reset=True, time_limit=5, view_shape=(5, 5),
                                   kernel=kernel, seed=9)
         return wrappers.training_stack(base, exit_difficulty=0.4, se_penalty=0.3)
-    a, b = make(2), make(1)
+    a, b = make(3), make(1)                  # kernel 3: pipelined also with the observation
     b.unwrapped.set_rng_state(a.unwrapped.rng_state)
     assert "k_env_step_pipe" in a.unwrapped.step_plan(obs=True)[0]
     a.reset()

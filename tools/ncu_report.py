@@ -85,7 +85,7 @@ def main():
     for f, n in by_file.most_common(8):
         print("  %10.1f  %s" % (n / units, f))
     print("# hottest source lines: instr/unit  inst%  stall-sample%  file:line  text")
-    for (f, l, t), v in sorted(lines.items(), key=lambda kv: -(kv[1][0] / tot_i + kv[1][1] / tot_s))[:28]:
+    for (f, l, t), v in sorted(lines.items(), key=lambda kv: -(kv[1][0] / tot_i + kv[1][1] / tot_s))[:int(sys.argv[3]) if len(sys.argv) > 3 else 28]:
         print("  %9.1f %5.1f %5.1f  %s:%d  %s" % (v[0] / units, 100 * v[0] / tot_i, 100 * v[1] / tot_s, f, l, t))
 
 
