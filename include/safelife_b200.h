@@ -365,29 +365,41 @@ int sl_host_wait(const uint32_t *flag, uint32_t seq, void *stream);
  * 231-236) a launch per step is mostly launch and completion latency.  A session
  * keeps one kernel resident: the envs stay in shared memory, the host posts a
  * step by writing tagged actions into pinned memory, the kernel answers by
- * writing the packed result records (SlEnvBatch.host_out) and a sequence number
- * into pinned memory.  Boards up to 32 x 32, batches whose CTAs are all resident
+ * writing the packed result records (SlEnvBatch.host_out), each tagged with the
+ * step's sequence number in its top byte, into pinned memory.  Boards up to 32 x 32, batches whose CTAs are all resident
  * at once (about 4700 envs per GPU); physics + auto-reset, no observation.
  * The caller allocates the mailbox:
  *   host_actions  pinned, n_pad = (n_envs + 15) & ~15 bytes, zeroed
  *   dev_actions   device, 2 * n_pad bytes
- *   dev_ctrl      device, 4 x uint32, zeroed
+ *   dev_ctrl      device, SL_SESSION_CTRL_WORDS x uint32 (words 8..23: globaltimer
+ *                 timeline of the last step; then the per-SM mailbox lines)
  *   host_ctrl     pinned, 4 x uint32: [0] last completed step, [1] alive,
  *                 [2] written by the host: 1 = end the session
  * While a session is open the batch's state in HBM is stale and no other call
  * may touch the batch; other CUDA work on the device waits for the session to
  * end (it ends by itself after idle_timeout_ms without a step). */
+#define SL_SESSION_CTRL_WORDS (32 + 32 * 256)
 typedef struct SlHostSession {
     uint8_t *host_actions;
     uint8_t *dev_actions;
     uint32_t *dev_ctrl;
     uint32_t *host_ctrl;
+    uint64_t *host_out;     /* library-owned: the batch's result records (SlEnvBatch.host_out) */
     uint32_t idle_timeout_ms;
     uint32_t seq;           /* steps posted in this session (library-owned) */
     int32_t n_envs;         /* library-owned */
     int32_t reserved;
 } SlHostSession;
 #define SL_SESSION_ENDED 4  /* sl_host_session_step: the session has ended (idle timeout); begin again */
+/* Allocates the mailbox for n_envs envs on the current device (host_actions
+ * write-combined if asked: the device then reads it without snooping the CPU's
+ * caches, which is several times faster for lines the CPU has just written);
+ * sl_host_session_free releases it.  A caller may also bring its own buffers. */
+int sl_host_session_alloc(SlHostSession *session, int n_envs, int write_combined);
+int sl_host_session_free(SlHostSession *session);
+/* Diagnostic: the eight globaltimer stamps (ns) the session kernel left for its last
+ * step (csrc/session.cuh); call between sessions. */
+int sl_host_session_timeline(const SlHostSession *session, uint64_t *stamps8);
 /* Starts the session kernel on `stream` (the batch must have host_out set and all
  * its arrays 16-byte aligned).  flags as for sl_env_step. */
 int sl_host_session_begin(const SlEnvBatch *batch, SlHostSession *session, int flags, void *stream);

@@ -88,11 +88,12 @@ class SlHostSession(ctypes.Structure):
     """Mirror of struct SlHostSession (include/safelife_b200.h)."""
     _fields_ = [("host_actions", ctypes.c_void_p), ("dev_actions", ctypes.c_void_p),
                 ("dev_ctrl", ctypes.c_void_p), ("host_ctrl", ctypes.c_void_p),
-                ("idle_timeout_ms", ctypes.c_uint32), ("seq", ctypes.c_uint32),
+                ("host_out", ctypes.c_void_p), ("idle_timeout_ms", ctypes.c_uint32), ("seq", ctypes.c_uint32),
                 ("n_envs", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 SL_SESSION_ENDED = 4
+SL_SESSION_CTRL_WORDS = 32 + 32 * 256
 SL_WRAP_MOVEMENT, SL_WRAP_MOVEMENT_PENALTY, SL_WRAP_EXIT_BONUS = 1, 2, 4
 SL_WRAP_SIDE_EFFECT, SL_WRAP_IGNORE_REWARD_CELLS = 8, 16
 WRAP_STATE_WORDS = 12   # int32 words per SlWrapState record (48 bytes)
@@ -136,6 +137,9 @@ PROTOTYPES = {
     "sl_env_step_host": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _vp],
     "sl_env_step_submit": [ctypes.POINTER(SlEnvBatch), _vp, _i, _i, _vp, _vp, ctypes.c_uint32],
     "sl_host_wait": [_vp, ctypes.c_uint32, _vp],
+    "sl_host_session_alloc": [ctypes.POINTER(SlHostSession), _i, _i],
+    "sl_host_session_free": [ctypes.POINTER(SlHostSession)],
+    "sl_host_session_timeline": [ctypes.POINTER(SlHostSession), _vp],
     "sl_host_session_begin": [ctypes.POINTER(SlEnvBatch), ctypes.POINTER(SlHostSession), _i, _vp],
     "sl_host_session_step": [ctypes.POINTER(SlHostSession), _vp, _vp],
     "sl_host_session_end": [ctypes.POINTER(SlHostSession), _vp],

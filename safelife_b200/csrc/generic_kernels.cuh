@@ -362,7 +362,8 @@ struct StepOut {           // what finish_step wrote for the env, for an epilogu
 
 __device__ inline bool finish_step(const SlEnvBatch &B, int e, SlEnvState &st, int row, int col,
                                    int value, bool agent_alive, bool exited, int static_goals,
-                                   int count_points_mem, StepOut *out = nullptr) {
+                                   int count_points_mem, StepOut *out = nullptr,
+                                   uint32_t host_tag = 0) {
     int steps = st.num_steps + 1;
     bool times_up = steps >= B.time_limit;
     bool active = st.active != 0;
@@ -391,7 +392,8 @@ __device__ inline bool finish_step(const SlEnvBatch &B, int e, SlEnvState &st, i
     B.times_up[e] = times_up;
     if (B.host_out != nullptr)
         B.host_out[e] = (uint64_t)__float_as_uint(reward) | ((uint64_t)(done ? 1 : 0) << 32) |
-                        ((uint64_t)(success ? 1 : 0) << 40) | ((uint64_t)(times_up ? 1 : 0) << 48);
+                        ((uint64_t)(success ? 1 : 0) << 40) | ((uint64_t)(times_up ? 1 : 0) << 48) |
+                        ((uint64_t)(host_tag & 0xffu) << 56);      // host sessions: the step that wrote it
     if (out != nullptr) *out = {reward, done, times_up};
     return done;
 }

@@ -14,9 +14,16 @@
 //     expected tag copies the actions into device memory and publishes the sequence
 //     number there; the workers spin on that word in the L2, never on the host;
 //   * the workers run the step (phase A per warp, the scalar tails on warp 0), write
-//     the packed result records into pinned host memory (SlEnvBatch.host_out), and
-//     the last CTA to arrive writes the sequence number into the host's done word,
+//     the packed result records into pinned host memory (SlEnvBatch.host_out) and count
+//     their arrivals in device memory; the last CTA to arrive issues the step's one
+//     system-scope fence and writes the sequence number into the host's done word,
 //     which the host spins on.
+//     (Measured, tools/probes/pcie_probe.cu and tools/trace_session.py, 4096 envs: a
+//     system fence costs 2 us alone and 5 us with 586 worker CTAs at it, hence one per
+//     step; letting the host scan tags in the records instead of a done word costs it
+//     27 ns per freshly written line, 14 us; carrying the records to the host through
+//     the courier's SM alone takes 7 us; dependent PCIe reads cost 1.7 us each, so the
+//     courier issues all the reads of a poll before it looks at any.)
 // The courier ends the session when the host asks for it, or by itself when no step
 // has been posted for idle_timeout_ms (a host that died must not leave a spinning
 // kernel behind): the workers then write their envs back and the kernel exits; the
@@ -28,6 +35,14 @@
 namespace sl {
 
 constexpr uint32_t SESSION_EXIT = 0xffffffffu;
+constexpr int SESSION_LINES = 256;             // 128-byte lines of published sequence numbers, one per SM
+constexpr int SESSION_CTRL_WORDS = 32 + 32 * SESSION_LINES;
+
+__device__ __forceinline__ unsigned int sm_id() {
+    unsigned int v;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+    return v;
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
     uint32_t v;
@@ -36,6 +51,9 @@ __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
 }
 __device__ __forceinline__ void st_release_gpu(uint32_t *p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_sys(volatile uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -59,11 +77,21 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
+// Timeline of the last step (globaltimer ns) in dev_ctrl words 8..23, for
+// tools/trace_session.py: 0 courier starts the poll that sees the step, 1 every tag
+// seen, 2 sequence number published; worker CTA 0: 3 sees it, 4 phase A done (all
+// warps), 5 tails done and records written; the last CTA to arrive: 6 arrived, 7 fenced and
+// done word sent.
+__device__ __forceinline__ void session_stamp(uint32_t *dev_ctrl, int slot) {
+    ((unsigned long long *)(dev_ctrl + 8))[slot] = globaltimer_ns();
+}
+
 // Kernel-side copy of SlHostSession.
 struct SessionParams {
     const uint8_t *host_actions;       // pinned [n_pad]: action | (seq & 15) << 4
     uint8_t *dev_actions;              // device [2][n_pad]
-    uint32_t *dev_ctrl;                // device: [0] published sequence number, [1] arrivals of the step
+    uint32_t *dev_ctrl;                // device: [8..23] timeline; from word 32 on one 128-byte line per SM
+                                       // with the published sequence number in its first word
     volatile uint32_t *host_ctrl;      // pinned: [0] done seq, [1] alive, [2] command (1 = end)
     int n_pad;                         // n_envs rounded up to 16
     unsigned long long idle_ns;
@@ -84,28 +112,38 @@ __device__ __forceinline__ void session_courier(const SessionParams &S) {
         uint4 v[SESSION_COURIER_CHUNKS];
         for (;;) {
             bool ok = true;
+            const unsigned long long t_poll = globaltimer_ns();
+            // every PCIe read of the round is issued before the first result is looked at
+            // (a read costs 1.7 us: three dependent ones were most of a 6.4 us poll)
+            uint32_t cmd = 0;
+            if (threadIdx.x == 0) cmd = ld_volatile_u32(S.host_ctrl + 2);
 #pragma unroll
             for (int k = 0; k < SESSION_COURIER_CHUNKS; k++) {
                 const int i = threadIdx.x + k * blockDim.x;
-                if (i < n16) {
-                    v[k] = ld_volatile_v4(src + i);
-                    ok &= ((v[k].x & 0xf0f0f0f0u) == tag) & ((v[k].y & 0xf0f0f0f0u) == tag) &
-                          ((v[k].z & 0xf0f0f0f0u) == tag) & ((v[k].w & 0xf0f0f0f0u) == tag);
-                }
+                v[k] = i < n16 ? ld_volatile_v4(src + i) : make_uint4(tag, tag, tag, tag);
             }
+#pragma unroll
+            for (int k = 0; k < SESSION_COURIER_CHUNKS; k++)
+                ok &= ((v[k].x & 0xf0f0f0f0u) == tag) & ((v[k].y & 0xf0f0f0f0u) == tag) &
+                      ((v[k].z & 0xf0f0f0f0u) == tag) & ((v[k].w & 0xf0f0f0f0u) == tag);
             for (int i = threadIdx.x + SESSION_COURIER_CHUNKS * blockDim.x; i < n16; i += blockDim.x) {
                 const uint4 w = ld_volatile_v4(src + i);
                 ok &= ((w.x & 0xf0f0f0f0u) == tag) & ((w.y & 0xf0f0f0f0u) == tag) &
                       ((w.z & 0xf0f0f0f0u) == tag) & ((w.w & 0xf0f0f0f0u) == tag);
             }
             int stop = 0;
-            if (threadIdx.x == 0)
-                stop = ld_volatile_u32(S.host_ctrl + 2) != 0 || globaltimer_ns() - t0 > S.idle_ns;
+            if (threadIdx.x == 0) stop = cmd != 0 || globaltimer_ns() - t0 > S.idle_ns;
             const int all_ok = __syncthreads_and(ok ? 1 : 0);
             if (threadIdx.x == 0) s_flag = stop;
             __syncthreads();
             // a posted step wins over a simultaneous request to end: it is run first
-            if (all_ok) break;
+            if (all_ok) {
+                if (threadIdx.x == 0) {
+                    ((unsigned long long *)(S.dev_ctrl + 8))[0] = t_poll;
+                    session_stamp(S.dev_ctrl, 1);
+                }
+                break;
+            }
             if (s_flag) {
                 live = false;
                 break;
@@ -124,19 +162,20 @@ __device__ __forceinline__ void session_courier(const SessionParams &S) {
             const uint4 w = ld_volatile_v4(src + i);      // (tags already verified)
             dst[i] = make_uint4(w.x & 0x0f0f0f0fu, w.y & 0x0f0f0f0fu, w.z & 0x0f0f0f0fu, w.w & 0x0f0f0f0fu);
         }
-        __threadfence();
+        // one fence for the CTA's copies (thread 0, after the barrier has made them its
+        // business), then one copy of the sequence number per SM: the workers of an SM spin
+        // on their own line (586 CTAs on one line slow every access that shares its L2 slice)
         __syncthreads();
-        if (threadIdx.x == 0) {
-            S.dev_ctrl[1] = 0;                  // arrivals of this step (the previous step has completed)
-            __threadfence();
-            st_release_gpu(S.dev_ctrl, seq);
-        }
+        if (threadIdx.x == 0) __threadfence();
+        __syncthreads();
+        for (int i = threadIdx.x; i < SESSION_LINES; i += blockDim.x)
+            st_relaxed_gpu(S.dev_ctrl + 32 + 32 * i, seq);
+        if (threadIdx.x == 0) session_stamp(S.dev_ctrl, 2);
         seq++;
     }
-    if (threadIdx.x == 0) {
-        st_release_gpu(S.dev_ctrl, SESSION_EXIT);
-        st_release_sys(S.host_ctrl + 1, 0u);          // not alive: the host must begin a new session
-    }
+    for (int i = threadIdx.x; i < SESSION_LINES; i += blockDim.x)
+        st_release_gpu(S.dev_ctrl + 32 + 32 * i, SESSION_EXIT);
+    if (threadIdx.x == 0) st_release_sys(S.host_ctrl + 1, 0u);   // not alive: the host must begin a new session
 }
 
 // The session kernel: n_workers worker CTAs (epc envs each, like k_env_step_warp
@@ -196,12 +235,14 @@ k_env_session(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Sess
     if (bulk) mbar_wait(bar, 0);
 
     const Narrow t(B.H, B.W, lane);
+    const uint32_t *my_line = S.dev_ctrl + 32 + 32 * (sm_id() % SESSION_LINES);
     bool goals_dirty = false;       // warp 0: some step rewrote a shared-memory goals slab
     for (uint32_t seq = 1;; seq++) {
         if (threadIdx.x == 0) {
             uint32_t v;
-            while ((v = ld_acquire_gpu(S.dev_ctrl)) != seq && v != SESSION_EXIT) __nanosleep(40);
+            while ((v = ld_acquire_gpu(my_line)) != seq && v != SESSION_EXIT) __nanosleep(40);
             *s_cmd = v;
+            if (blockIdx.x == 0) session_stamp(S.dev_ctrl, 3);
         }
         __syncthreads();
         if (*s_cmd == SESSION_EXIT) break;
@@ -214,15 +255,26 @@ k_env_session(const __grid_constant__ SlEnvBatch B, const __grid_constant__ Sess
         }
         const int any_dirty = __syncthreads_or(dirty);
         if (warp == 0) {
+            const bool tr = blockIdx.x == 0 && lane == 0;
+            if (tr) session_stamp(S.dev_ctrl, 4);
             goals_dirty |= any_dirty != 0;
-            goals_dirty |= step_phase_b(B, cs, e0, nenv, sstate, sboard, GR ? sgoals : ggoals, flags, lane);
-            __threadfence_system();             // the result records, before the arrival is counted
+            // every record carries the step's tag: valid for the host the moment it lands
+            goals_dirty |= step_phase_b(B, cs, e0, nenv, sstate, sboard, GR ? sgoals : ggoals, flags, lane,
+                                        seq);
+            if (tr) session_stamp(S.dev_ctrl, 5);
+            // Arrival.  The records of this CTA are ordered before its arrival at GPU scope;
+            // the last CTA to arrive has thereby observed every other CTA's arrival, and ITS
+            // system-scope fence orders all of their records before the done word (fences
+            // are cumulative): one system fence per step, and the host spins on one word.
             __syncwarp();
             if (lane == 0) {
-                const uint32_t before = atomicAdd(S.dev_ctrl + 1, 1u);
-                if (before == (uint32_t)n_workers - 1u) {
+                __threadfence();
+                if (atomicAdd(S.dev_ctrl + 1, 1u) == (uint32_t)n_workers - 1u) {
+                    S.dev_ctrl[1] = 0;                      // everyone has arrived: ready for the next step
+                    session_stamp(S.dev_ctrl, 6);
                     __threadfence_system();
                     st_release_sys(S.host_ctrl, seq);
+                    session_stamp(S.dev_ctrl, 7);
                 }
             }
         }

@@ -793,7 +793,8 @@ __device__ __forceinline__ bool step_phase_a(const SlEnvBatch &B, const CtaShare
 // goals slab.
 __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, const CtaShared &cs, int e0,
                                              int nenv, SlEnvState *sstate, uint16_t *sboard,
-                                             uint16_t *goals0, int flags, int lane) {
+                                             uint16_t *goals0, int flags, int lane,
+                                             uint32_t host_tag = 0) {
     const int cells = B.H * B.W;
     bool done = false;
     if (lane < nenv) {
@@ -809,7 +810,7 @@ __device__ __forceinline__ bool step_phase_b(const SlEnvBatch &B, const CtaShare
                                       cs.table ? cs.table : B.pool_table + (size_t)lvl * 72,
                                       &agent_alive, &exited, &dmem);
         done = finish_step(B, e0 + lane, *s0, row, col, value, agent_alive, exited,
-                           s0->static_goals, pts + dmem);
+                           s0->static_goals, pts + dmem, nullptr, host_tag);
     }
     bool any_reset = false;
     if (flags & SL_STEP_AUTO_RESET) {

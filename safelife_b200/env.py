@@ -488,20 +488,13 @@ class BatchedSafeLifeEnv(object):
             self.enable_host_io()
         if self._wrap is not None:
             raise ValueError("host sessions step the bare env (no training wrappers)")
-        n_pad = (self.num_envs + 15) & ~15
-        if getattr(self, "_session_bufs", None) is None:
-            self._session_bufs = {
-                "host_actions": torch.zeros(n_pad, dtype=torch.uint8).pin_memory(),
-                "host_ctrl": torch.zeros(4, dtype=torch.int32).pin_memory(),
-                "dev_actions": torch.zeros(2 * n_pad, dtype=torch.uint8, device=self.device),
-                "dev_ctrl": torch.zeros(4, dtype=torch.int32, device=self.device),
-            }
-        b = self._session_bufs
-        self._session = _lib.SlHostSession(
-            host_actions=b["host_actions"].data_ptr(), dev_actions=b["dev_actions"].data_ptr(),
-            dev_ctrl=b["dev_ctrl"].data_ptr(), host_ctrl=b["host_ctrl"].data_ptr(),
-            idle_timeout_ms=int(idle_timeout_ms))
-        self._session_ref = ctypes.byref(self._session)
+        if getattr(self, "_session", None) is None:
+            # the mailbox, allocated by the library (the action buffer write-combined)
+            self._session = _lib.SlHostSession()
+            self._session_ref = ctypes.byref(self._session)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.sl_host_session_alloc(self._session_ref, self.num_envs, 1))
+        self._session.idle_timeout_ms = int(idle_timeout_ms)
         auto = self.auto_reset if auto_reset is None else auto_reset
         self._session_flags = _lib.SL_STEP_AUTO_RESET if auto else 0
         self._session_args = (auto_reset, idle_timeout_ms)
@@ -511,6 +504,23 @@ class BatchedSafeLifeEnv(object):
                                                        self._session_flags, self._host_stream))
         self._session_open = True
 
+    def __del__(self):
+        try:
+            if getattr(self, "_session", None) is not None:
+                self.end_host_session()
+                self._lib.sl_host_session_free(self._session_ref)
+                self._session = None
+        except Exception:   # noqa: BLE001  (interpreter shutdown)
+            pass
+
+    def session_timeline(self):
+        """globaltimer stamps (ns) the session kernel left for its last step (csrc/session.cuh)."""
+        self.end_host_session()
+        stamps = np.zeros(8, dtype=np.uint64)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.sl_host_session_timeline(self._session_ref, stamps.ctypes.data))
+        return stamps.astype(np.int64)
+
     def end_host_session(self):
         """Close the host session: the envs are written back and every method works again."""
         if getattr(self, "_session_open", False):
@@ -519,7 +529,9 @@ class BatchedSafeLifeEnv(object):
                 _lib.check(self._lib.sl_host_session_end(self._session_ref, self._host_stream))
 
     def _session_step(self, actions, timing):
-        a = np.ascontiguousarray(actions, dtype=np.uint8)
+        a = actions
+        if not (isinstance(a, np.ndarray) and a.dtype == np.uint8 and a.flags.c_contiguous):
+            a = np.ascontiguousarray(actions, dtype=np.uint8)
         if a.shape != (self.num_envs,):
             raise ValueError("actions must have shape (num_envs,)")
         tptr = None if timing is None else timing.ctypes.data
