@@ -211,6 +211,11 @@ def cpu_arm(levels, n_envs, steps, warmup, seconds_budget):
     elapsed = max(r[0] for r in res)
     value = sample * steps / elapsed
     extra = _cpu_pure_c(levels) if kind == "reference" else {}
+    try:
+        extra.update(_cpu_full_env(levels))
+    except Exception as exc:   # noqa: BLE001  (a baseline extra must not take the bench down)
+        extra["reference_env_step"] = None
+        extra["reference_env_step_note"] = repr(exc)
     return {
         "value": value, "unit": "env-steps/s", "cores": cores, "kind": kind,
         "sample": "%d envs x %d steps (of %d envs/step), %s speedups execute_actions+advance_board"
@@ -218,6 +223,68 @@ def cpu_arm(levels, n_envs, steps, warmup, seconds_budget):
                       sample, steps, n_envs, "reference C" if kind == "reference" else "oracle"),
         **extra,
     }, elapsed
+
+
+def _cpu_full_env_worker(args):
+    """
+    BASELINE.md section 3.2: the UNMODIFIED reference SafeLifeEnv.step (physics, reward,
+    get_obs with the training view) on this process's share of the levels, reset on done.
+    """
+    levels, seed, warmup, seconds, barrier = args
+    from oracle import refload
+    refload.load_reference()
+    from safelife.safelife_env import SafeLifeEnv
+    from safelife.safelife_game import SafeLifeGame
+
+    def games():
+        k = 0
+        while True:
+            lv = levels[k % len(levels)]
+            k += 1
+            loc = lv["agent_loc"]
+            yield SafeLifeGame.loaddata({
+                "board": np.array(lv["board"], dtype=np.uint16), "goals": np.array(lv["goals"], dtype=np.uint16),
+                "agent_locs": np.zeros((0, 2), dtype=np.int64) if loc is None else np.array([loc], dtype=np.int64),
+                "points_table": np.asarray(lv["points_table"], dtype=np.int64).reshape(1, 8, 9),
+                "min_performance": lv["min_performance"], "spawn_prob": lv["spawn_prob"]}, auto_cls=False)
+    env = SafeLifeEnv(games(), time_limit=1000, view_shape=(25, 25), output_channels=TRAIN_CHANNELS,
+                      should_calculate_side_effects=False)
+    rs = np.random.default_rng(seed)
+    env.reset()
+    for _ in range(warmup):
+        _, _, done, _ = env.step(int(rs.integers(0, 9)))
+        if done:
+            env.reset()
+    barrier.wait()
+    steps, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(50):
+            _, _, done, _ = env.step(int(rs.integers(0, 9)))
+            if done:
+                env.reset()
+        steps += 50
+    return steps, time.perf_counter() - t0
+
+
+def _cpu_full_env(levels, seconds=4.0):
+    """Aggregate env-steps/s of the reference's own SafeLifeEnv.step, one process per host core."""
+    import multiprocessing as mp
+    from oracle import refload
+    if not refload.have_reference():
+        return {"reference_env_step": None,
+                "reference_env_step_note": "reference Python not shipped (baseline/_ref missing)"}
+    cores = os.cpu_count() or 1
+    m = mp.Manager()
+    barrier = m.Barrier(cores)
+    jobs = [([levels[(w * 8 + k) % len(levels)] for k in range(8)], 100 + w, 20, seconds, barrier)
+            for w in range(cores)]
+    with mp.Pool(cores) as pool:
+        res = pool.map(_cpu_full_env_worker, jobs)
+    rate = sum(r[0] / r[1] for r in res)
+    return {"reference_env_step": {
+        "value": rate, "unit": "env-steps/s", "cores": cores, "per_core": rate / cores,
+        "sample": "unmodified reference SafeLifeEnv.step (physics + reward + get_obs, 25x25 view, 15 "
+                  "channels, reset on done), one env per process, one process per core, %.0f s" % seconds}}
 
 
 def _cpu_pure_c(levels):

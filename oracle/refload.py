@@ -23,8 +23,14 @@ import types
 
 import numpy as np
 
-REF_ROOT = os.environ.get("SAFELIFE_REFERENCE", "/root/reference")
 _REF_SO_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+# The reference checkout, or -- on the GPU box, where it does not exist -- the verbatim
+# copy of its Python package that __graft_entry__.build() leaves in the git-ignored
+# baseline/_ref/ (used only by bench.py's cpu_baseline: BASELINE.md section 3.2).
+_REF_COPY = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REF_ROOT = os.environ.get("SAFELIFE_REFERENCE", "/root/reference")
+if not os.path.isdir(os.path.join(REF_ROOT, "safelife")) and os.path.isdir(os.path.join(_REF_COPY, "safelife")):
+    REF_ROOT = _REF_COPY
 
 
 def have_ref_so():
