@@ -77,6 +77,9 @@ def parse_args():
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 3-5")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--batches", type=int, default=0,
+                    help="batches of the rotation (0: enough for three times the L2); a small number "
+                         "keeps the set-up short for launch-list captures and is NOT a valid timing")
     ap.add_argument("--quick", action="store_true",
                     help="A/B runs: only `value` and `step_with_obs` (rotating batches), printed as a short line")
     return ap.parse_args()
@@ -442,14 +445,22 @@ class Rotation(object):
     timed steps.  Each step is one launch over one batch of n envs, as in the workload.
     """
 
+    forced = 0          # --batches
+
     def __init__(self, torch, dev, first_env, make_env, board_bytes):
         l2 = int(torch.cuda.get_device_properties(dev).L2_cache_size)
         self.l2_bytes = l2
         self.R = int(max(2, min(96, -(-3 * l2 // board_bytes))))
+        if Rotation.forced:
+            self.R = Rotation.forced
         self.board_bytes = board_bytes
         self.envs = [first_env] + [make_env(r) for r in range(1, self.R)]
 
     def note(self):
+        if self.R * self.board_bytes < 2 * self.l2_bytes:
+            return ("NOT larger than L2 (--batches %d: %.0f MB of board planes against %.0f MB of L2): "
+                    "a launch-list / debugging run, not a timing" % (
+                        self.R, self.R * self.board_bytes / 1e6, self.l2_bytes / 1e6))
         return ("inputs larger than L2: steps rotate over %d independent batches of the workload "
                 "(board planes %.1f MB each, %.0f MB together against %.0f MB of L2), so every "
                 "launch reads its batch from HBM; no flush inside or between the timed steps" % (
@@ -698,6 +709,7 @@ def graph_replay(torch, env, lib, actions, kernel, reps=10):
 
 
 def run_ours(args, levels):
+    Rotation.forced = max(0, args.batches)
     import ctypes
     import torch
     import torch.distributed as dist

@@ -19,7 +19,8 @@ def main():
     from safelife_b200 import speedups, wrappers
     from safelife_b200.env import BatchedSafeLifeEnv
     from test_gpu_env import _random_levels, TRAIN_CHANNELS
-    only = sys.argv[1:] or ["single", "pipe", "pipe_obs", "in_place_dynamic", "tile", "multistep"]
+    only = sys.argv[1:] or ["single", "epc", "pipe", "pipe_obs", "in_place_dynamic", "tile", "multistep",
+                            "session"]
     rs = np.random.default_rng(1)
     lv25 = _random_levels(rs, 16, 25, 25)            # spawners, dynamic goals on ~30 % of the levels
     lv50 = _random_levels(rs, 8, 50, 50)
@@ -42,6 +43,26 @@ def main():
             env.step_physics(torch.randint(0, 9, (67,), device="cuda", dtype=torch.uint8), auto_reset=True)
         torch.cuda.synchronize()
         print("ok single-pass, scalar tail on warp 0, ragged tail group")
+    if "epc" in only:         # 1..8 envs per CTA: slab-offset bulk loads, edge stores next to bulk stores
+        for n in (5, 1500, 2900, 4096):
+            env = BatchedSafeLifeEnv(lv25, n, time_limit=3, auto_reset=True, kernel=2, view_shape=(9, 9),
+                                     output_channels=TRAIN_CHANNELS)
+            env.reset()
+            for t in range(3):
+                a = torch.randint(0, 9, (n,), device="cuda", dtype=torch.uint8)
+                env.step(a)
+                env.step_physics(a, auto_reset=True)
+            torch.cuda.synchronize()
+            print("ok", env.step_plan()[0])
+    if "session" in only:     # the resident session kernel (mailboxes in pinned memory)
+        env = BatchedSafeLifeEnv(lv25, 300, time_limit=3, auto_reset=True, kernel=2)
+        env.reset()
+        env.begin_host_session(idle_timeout_ms=20000)
+        for t in range(5):
+            env.step_host(rs.integers(0, 9, 300).astype(np.uint8))
+        env.end_host_session()
+        torch.cuda.synchronize()
+        print("ok host session")
     if "pipe" in only:        # persistent pipelined kernel, scalar warp
         n = 148 * 4 * 2 * 8 + 8 * 9 + 5
         env = BatchedSafeLifeEnv(lv25, n, time_limit=2, auto_reset=True, kernel=2, goals_in_place=False)
@@ -52,7 +73,7 @@ def main():
         print("ok", env.step_plan()[0])
     if "pipe_obs" in only:
         n = 148 * 4 * 2 * 8 + 8 * 9
-        env = BatchedSafeLifeEnv(lv25, n, time_limit=2, auto_reset=True, kernel=2, view_shape=(25, 25),
+        env = BatchedSafeLifeEnv(lv25, n, time_limit=2, auto_reset=True, kernel=3, view_shape=(25, 25),
                                  output_channels=TRAIN_CHANNELS)
         run("pipelined + obs", env, 3)
     if "in_place_dynamic" in only:   # goals left in HBM although some are dynamic: scratch slab + lock
