@@ -686,6 +686,61 @@ def e2e_line(n, world, K, launch_s, launch_parts, session):
                 session=session)
 
 
+def rollout_bench(torch, env, steps_per_env=20, reps=3):
+    """
+    PPO data collection end to end on the device (training/ppo.py:75-143 through
+    safelife_b200.rollout.BatchedRollout): every step is the fused gym step (physics +
+    auto-reset + observation written straight into the rollout buffer) followed by a
+    policy forward pass and an action sample; then trajectory stitching, returns and
+    advantages.  The policy is a STUB of the reference's shape (training/models.py:9-42:
+    conv 5x5/2 x32, 3x3/2 x64, 3x3 x64, dense 512, 9 logits + value; random weights, bf16,
+    plain torch modules) -- it is the consumer, not the product.
+    """
+    from safelife_b200.rollout import BatchedRollout
+    nn = torch.nn
+    dev = env.device
+    C = len(TRAIN_CHANNELS)
+
+    class Stub(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.cnn = nn.Sequential(nn.Conv2d(C, 32, 5, 2), nn.ReLU(), nn.Conv2d(32, 64, 3, 2), nn.ReLU(),
+                                     nn.Conv2d(64, 64, 3, 1), nn.ReLU())
+            self.dense = nn.Sequential(nn.Linear(64 * 3 * 3, 512), nn.ReLU())
+            self.logits, self.value = nn.Linear(512, 9), nn.Linear(512, 1)
+
+        def forward(self, obs):
+            x = obs.permute(0, 3, 2, 1).to(torch.bfloat16)
+            x = self.dense(self.cnn(x).flatten(1))
+            return self.value(x)[:, 0].float(), torch.softmax(self.logits(x).float(), dim=-1)
+    torch.manual_seed(0)
+    net = Stub().to(dev).to(torch.bfloat16).eval()
+    runner = BatchedRollout(env)
+    with torch.no_grad():
+        runner.gen_training_batch(net, steps_per_env=2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            batch = runner.gen_training_batch(net, steps_per_env=steps_per_env)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        # the policy alone on the same observations, for the split
+        obs = batch.obs[:env.num_envs]
+        net(obs)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps_per_env):
+            net(obs)
+        torch.cuda.synchronize()
+        policy_ms = 1e3 * (time.perf_counter() - t0) / steps_per_env
+    n = env.num_envs
+    return {"env_steps_per_s": n * steps_per_env * reps / dt, "ms_per_step": 1e3 * dt / (steps_per_env * reps),
+            "policy_forward_ms": policy_ms, "steps_per_env": steps_per_env,
+            "note": "supplementary: BatchedRollout.gen_training_batch (fused step + observation, stub CNN "
+                    "policy in bf16, multinomial sample, trajectory stitching + GAE), wall clock, one "
+                    "sync per batch; rank 0.  policy_forward_ms is the stub alone."}
+
+
 def graph_replay(torch, env, lib, actions, kernel, reps=10):
     """K steps captured once in a CUDA graph (device-resident actions) and replayed."""
     from safelife_b200 import _lib
@@ -968,6 +1023,13 @@ def run_ours(args, levels):
     torch.cuda.synchronize()
     public_step_us = 1e6 * allmax(time.perf_counter() - t0) / Kp
 
+    # ---- supplementary: PPO data collection with a stub CNN policy ----
+    try:
+        rollout = rollout_bench(torch, env) if rank == 0 else None
+    except Exception as exc:   # noqa: BLE001
+        rollout = {"error": repr(exc)}
+    barrier()
+
     # ---- supplementary: SafeLifeEnv.get_obs alone (what reset() returns) ----
     env.get_obs()
     barrier()
@@ -1076,6 +1138,7 @@ def run_ours(args, levels):
                         "126 MB L2), one event pair; rank 0" % (
                             K, "fits" if n * 4 * H * W < 100e6 else "exceeds")},
             "graph_replay": graph,
+            "rollout": rollout,
         }
         if configs is not None:
             line["configs"] = configs

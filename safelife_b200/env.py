@@ -103,6 +103,14 @@ def coprime_stride(n_envs, n_levels):
     return s % n_levels
 
 
+def _address(arr):
+    """Address of a numpy array's first byte (`arr.ctypes.data` costs 2.5 us, this 0.9)."""
+    try:
+        return ctypes.addressof(ctypes.c_char.from_buffer(arr))
+    except (TypeError, ValueError):          # read-only or empty buffer
+        return arr.ctypes.data
+
+
 class _TensorTable(dict):
     """The env's device tensors by name; per-env scalars are views into `state`."""
 
@@ -458,7 +466,7 @@ class BatchedSafeLifeEnv(object):
             np.copyto(h["actions"], actions, casting="unsafe")
         auto = self.auto_reset if auto_reset is None else auto_reset
         flags = _lib.SL_STEP_AUTO_RESET if auto else 0
-        tptr = None if timing is None else timing.ctypes.data
+        tptr = None if timing is None else _address(timing)
         # host-driven loop: keep the per-step Python overhead out of the way (the
         # device context manager costs more than the kernel launch)
         if torch.cuda.current_device() == self.device.index:
@@ -534,12 +542,13 @@ class BatchedSafeLifeEnv(object):
             a = np.ascontiguousarray(actions, dtype=np.uint8)
         if a.shape != (self.num_envs,):
             raise ValueError("actions must have shape (num_envs,)")
-        tptr = None if timing is None else timing.ctypes.data
-        status = self._lib.sl_host_session_step(self._session_ref, a.ctypes.data, tptr)
+        tptr = None if timing is None else _address(timing)
+        aptr = _address(a)
+        status = self._lib.sl_host_session_step(self._session_ref, aptr, tptr)
         if status == _lib.SL_SESSION_ENDED:      # idle timeout: the state is back in HBM; reopen
             self.end_host_session()
             self.begin_host_session(*self._session_args)
-            status = self._lib.sl_host_session_step(self._session_ref, a.ctypes.data, tptr)
+            status = self._lib.sl_host_session_step(self._session_ref, aptr, tptr)
         if status:
             _lib.check(status)
         h = self._host_np
