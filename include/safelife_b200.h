@@ -221,9 +221,10 @@ typedef struct SlEnvBatch {
     const uint64_t *pool_spawn_thr;   /* [n_levels] */
 
     /* optional (NULL: none): the step's outputs once more, packed 8 bytes per env
-     * { float reward; uint8 done, success, times_up, 0 } -- for host-driven loops that
-     * point this at pinned host memory: the 8 envs of a CTA then cross PCIe as ONE
-     * 64-byte write instead of four small ones */
+     * { float reward; uint8 done, success, times_up, tag } -- for host-driven loops that
+     * point this at pinned host memory: the envs of a CTA then cross PCIe as ONE write
+     * of up to 64 bytes instead of four small ones.  tag is 0, or inside a host session
+     * the low byte of the step's sequence number. */
     uint64_t *host_out;               /* [n_envs] */
 } SlEnvBatch;
 
@@ -332,9 +333,9 @@ int sl_env_step_plan(const SlEnvBatch *batch, int kernel, char *text, int text_l
 int sl_env_step_obs_plan(const SlEnvBatch *batch, const SlObsSpec *obs, int kernel, char *text,
                          int text_len, int *n_launches);
 
-/* An empty kernel with the step kernel's launch shape (one 256-thread CTA per 8
- * envs, the same parameter block): what a benchmark's event pair measures
- * around a step that does no work. */
+/* An empty kernel with the step kernel's launch shape (the single-pass kernel's grid and
+ * CTA size for this batch, the same parameter block): what a benchmark's event pair
+ * measures around a step that does no work. */
 int sl_launch_floor(const SlEnvBatch *batch, void *stream);
 
 /* sl_env_step followed by a wait for the stream: for host-driven loops.  The
