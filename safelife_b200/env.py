@@ -219,6 +219,12 @@ class BatchedSafeLifeEnv(object):
             self._out = [{k: self._t[k] for k in names},
                          {k: torch.zeros_like(self._t[k]) for k in names}]
             self._obs_bufs = [z(obs_shape, obs_dtype), z(obs_shape, obs_dtype)]
+            # the views step() hands out, made once (a .view() costs more than the launch)
+            self._out_views = [{k: o[k].view(torch.bool) for k in ("done", "success", "times_up")}
+                               for o in self._out]
+            self._board_u16 = self._t["board"].view(torch.uint16)
+            self._goals_u16 = self._t["goals"].view(torch.uint16)
+            self._agent_locs = self._views["loc"].reshape(N, 1, 2)
             self._actions = z((N,), torch.uint8)
         flags = self._pool_flags()
         self._batches, self._batch_refs, self._obs_specs = [], [], []
@@ -296,17 +302,17 @@ class BatchedSafeLifeEnv(object):
     def board(self):
         """uint16 [N,H,W] view of the device boards (SafeLifeGame.board layout)."""
         self.end_host_session()
-        return self._t["board"].view(torch.uint16)
+        return self._board_u16
 
     @property
     def goals(self):
         self.end_host_session()
-        return self._t["goals"].view(torch.uint16)
+        return self._goals_u16
 
     @property
     def agent_locs(self):
         """int32 [N,1,2] (row, col), as SafeLifeGame.agent_locs."""
-        return self._t["loc"].reshape(self.num_envs, 1, 2)
+        return self._agent_locs
 
     @property
     def rng_state(self):
@@ -383,21 +389,34 @@ class BatchedSafeLifeEnv(object):
             actions = torch.from_numpy(a.astype(np.uint8))
         if actions.shape != (self.num_envs,):
             raise ValueError("actions must have shape (num_envs,)")
-        self._actions.copy_(actions, non_blocking=True)
+        if (actions.dtype == torch.uint8 and actions.is_cuda and actions.device == self.device
+                and actions.is_contiguous()):
+            # read in place by the kernel, in stream order like any torch op would (a
+            # staging copy is a launch of its own and costs more host time than the step)
+            aptr, self._held_actions = actions.data_ptr(), actions
+        else:
+            self._actions.copy_(actions, non_blocking=True)
+            aptr = self._actions.data_ptr()
         bref, out = self._next_outputs()
         spec, obs = (None, None) if obs_out is False else self._next_obs(obs_out)
         spec = None if spec is None else ctypes.byref(spec)
         flags = _lib.SL_STEP_AUTO_RESET if auto_reset else 0
-        with torch.cuda.device(self.device):
-            if self._wrap is None:
-                _lib.check(self._lib.sl_env_step_obs(
-                    bref, self._actions.data_ptr(), spec, self.kernel, flags, self._stream()))
-            else:   # the training wrappers run as an epilogue of the same launch
-                self._wrap.before_step()
-                _lib.check(self._lib.sl_env_step_wrapped(
-                    bref, self._actions.data_ptr(), spec, self._wrap.fill_spec(self._flip),
-                    self.kernel, flags, self._stream()))
+        if torch.cuda.current_device() == self.device.index:
+            self._launch_step(bref, aptr, spec, flags)
+        else:
+            with torch.cuda.device(self.device):
+                self._launch_step(bref, aptr, spec, flags)
         return dict(out, obs=obs)
+
+    def _launch_step(self, bref, aptr, spec, flags):
+        if self._wrap is None:
+            status = self._lib.sl_env_step_obs(bref, aptr, spec, self.kernel, flags, self._stream())
+        else:   # the training wrappers run as an epilogue of the same launch
+            self._wrap.before_step()
+            status = self._lib.sl_env_step_wrapped(bref, aptr, spec, self._wrap.fill_spec(self._flip),
+                                                   self.kernel, flags, self._stream())
+        if status:
+            _lib.check(status)
 
     def _wrap_reset(self, mask):
         if self._wrap is not None:
@@ -638,11 +657,12 @@ class BatchedSafeLifeEnv(object):
         out = self.step_physics(actions, self.auto_reset and not score, obs_out=obs_out)
         t = self._t
         obs = self._view_of(out["obs"])
-        reward, done = out["reward"], out["done"].view(torch.bool)
+        views = self._out_views[self._flip]            # of the output set this step wrote
+        reward, done = out["reward"], views["done"]
         info = {
-            "times_up": out["times_up"].view(torch.bool),
+            "times_up": views["times_up"],
             "episode": {"length": t["ep_length"], "reward": t["ep_reward"],
-                        "success": out["success"].view(torch.bool)},
+                        "success": views["success"]},
         }
         if score:
             side_effects = self._episode_side_effects()
