@@ -38,6 +38,9 @@ def test_struct_layout_matches_header():
     dt = _lib.ENV_STATE_DTYPE
     assert dt.itemsize == 96 and dt.fields["loc"][1] == 32 and dt.fields["spawn_thr"][1] == 64
     assert dt.fields["count_points"][1] == 80 and dt.fields["ep_reward"][1] == 56
+    # SlHostSession: five pointers, then idle_timeout_ms, seq, n_envs, reserved
+    assert ctypes.sizeof(_lib.SlHostSession) == 5 * 8 + 4 * 4
+    assert _lib.SlHostSession.host_out.offset == 32 and _lib.SlHostSession.seq.offset == 44
 
 
 def test_argument_errors_without_gpu():
@@ -133,3 +136,61 @@ def test_normalize_level_old_and_new_keys():
     assert n["agent_loc"] == (2, 5) and n["min_performance"] == 0.5
     with pytest.raises(ValueError):
         lv.normalize_level({"board": board, "goals": board, "agent_locs": np.zeros((2, 2), int)})
+
+
+def test_host_session_mailbox_protocol_host_side():
+    """
+    sl_host_session_step is pure host code: it tags the actions into the mailbox and
+    waits for the done word.  A Python thread plays the device side of the protocol
+    (csrc/session.cuh: every byte of the action buffer must carry the low nibble of
+    the step's sequence number before the step may run; the done word carries the
+    sequence number; a dead session is reported as SL_SESSION_ENDED with nothing
+    stepped).
+    """
+    import ctypes
+    import threading
+    import time
+    lib = _lib.lib()
+    n = 37                                   # not a multiple of 16: the padding is tagged too
+    n_pad = (n + 15) & ~15
+    # (numpy buffers are 16-byte aligned for these sizes; the library stores 16 bytes at a time)
+    raw = np.zeros(n_pad + 16, dtype=np.uint8)
+    off = (-raw.ctypes.data) % 16
+    host_actions = raw[off:off + n_pad]
+    host_ctrl = np.zeros(4, dtype=np.uint32)
+    host_out = np.zeros(n, dtype=np.uint64)
+    s = _lib.SlHostSession(host_actions=host_actions.ctypes.data, dev_actions=1, dev_ctrl=1,
+                           host_ctrl=host_ctrl.ctypes.data, host_out=host_out.ctypes.data,
+                           idle_timeout_ms=50, seq=0, n_envs=n)
+    host_ctrl[1] = 1                         # alive
+    seen, stop = [], threading.Event()
+
+    def device():
+        seq = 1
+        while not stop.is_set():
+            tag = (seq & 15) << 4
+            if np.all((host_actions & 0xF0) == tag):
+                seen.append((host_actions[:n] & 0x0F).copy())
+                assert np.all(host_actions[n:] == tag)
+                host_out[:] = seq                  # "result records"
+                host_ctrl[0] = seq                 # done word
+                seq += 1
+            else:
+                time.sleep(0)
+    th = threading.Thread(target=device, daemon=True)
+    th.start()
+    rs = np.random.default_rng(0)
+    timing = np.zeros(2)
+    for step in range(1, 40):                # crosses the 4-bit tag's wrap-around twice
+        a = rs.integers(0, 9, n).astype(np.uint8)
+        rc = lib.sl_host_session_step(ctypes.byref(s), a.ctypes.data, timing.ctypes.data)
+        assert rc == _lib.SL_OK and s.seq == step
+        assert np.array_equal(seen[-1], a) and int(host_out[0]) == step
+        assert timing[1] >= 0.0
+    stop.set()
+    th.join()
+    # a session that ended (idle time-out on the device) steps nothing and says so
+    host_ctrl[1] = 0
+    a = rs.integers(0, 9, n).astype(np.uint8)
+    assert lib.sl_host_session_step(ctypes.byref(s), a.ctypes.data, None) == _lib.SL_SESSION_ENDED
+    assert s.seq == 39 and len(seen) == 39
