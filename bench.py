@@ -326,8 +326,12 @@ def run_reference(args, levels):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-        "config": {"workload": "%d envs x %dx%d %s, random actions (CPU sample: see cpu_baseline)" % (
-            n_total, H, W, args.pool), "envs_per_gpu": args.envs, "pool": args.pool},
+        # the same workload string as our arm's line; the CPU sample of it is in cpu_baseline.sample
+        "config": {"workload": "%d envs/GPU x %dx%d %s procgen pool (%d levels), uniform random "
+                               "actions, time_limit 1000, auto-reset" % (args.envs, H, W, args.pool, len(levels)),
+                   "envs_per_gpu": args.envs, "board": [H, W], "pool": args.pool,
+                   "timing": "wall clock around the timed steps of a bounded sample of the workload "
+                             "on the host cores (cpu_baseline.sample)"},
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
