@@ -194,3 +194,39 @@ def test_host_session_mailbox_protocol_host_side():
     a = rs.integers(0, 9, n).astype(np.uint8)
     assert lib.sl_host_session_step(ctypes.byref(s), a.ctypes.data, None) == _lib.SL_SESSION_ENDED
     assert s.seq == 39 and len(seen) == 39
+
+
+def test_slab_offset_copy_arithmetic():
+    """
+    The arithmetic of the single-pass kernel's slab-offset copies (csrc/warp_kernels.cuh,
+    k_env_step_warp; csrc/session.cuh), restated: for any number of envs per CTA the bulk
+    load covers the CTA's slabs with whole 16-byte units inside the array, and the bulk
+    store plus the two cell-wise edges write exactly the CTA's own bytes, once.
+    """
+    rs = np.random.default_rng(0)
+    for _ in range(2000):
+        H, W = int(rs.integers(3, 33)), int(rs.integers(3, 33))
+        cells, epc, n_envs = H * W, int(rs.integers(1, 9)), int(rs.integers(1, 5000))
+        total = n_envs * cells * 2
+        written = np.zeros(total, dtype=np.uint8)
+        for cta in range((n_envs + epc - 1) // epc):
+            e0 = cta * epc
+            nenv = min(epc, n_envs - e0)
+            group_bytes, byte0 = nenv * cells * 2, e0 * cells * 2
+            mis = byte0 & 15
+            load_bytes = (mis + group_bytes + 15) & ~15
+            bulk = group_bytes >= 64 and byte0 - mis + load_bytes <= (total & ~15)
+            if not bulk:                         # scalar copies of exactly the CTA's bytes
+                written[byte0:byte0 + group_bytes] += 1
+                continue
+            assert (byte0 - mis) % 16 == 0 and load_bytes % 16 == 0
+            assert byte0 - mis + load_bytes >= byte0 + group_bytes        # the load covers the slabs
+            head = (16 - mis) & 15
+            body = (group_bytes - head) & ~15
+            tail = group_bytes - head - body
+            assert (byte0 + head) % 16 == 0 and body % 16 == 0 and 0 <= tail < 16 and head % 2 == 0
+            assert head // 2 <= 8 and tail // 2 <= 8                      # eight lanes per edge
+            written[byte0:byte0 + head] += 1                              # lanes 0-7, cell by cell
+            written[byte0 + head:byte0 + head + body] += 1                # bulk store
+            written[byte0 + head + body:byte0 + group_bytes] += 1         # lanes 8-15
+        assert (written == 1).all()
